@@ -1,0 +1,168 @@
+/*
+ * pytenet_b200 -- C ABI of the B200-native effective-Hamiltonian path.
+ *
+ * Drop-in boundary for the hot path of cmendl/pytenet v1.3.0.  The reference is
+ * pure Python (no FFI of its own), so every entry point cites the *Python*
+ * function it replaces; INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers (void*), 64-bit extents, no torch / C++ types.
+ *   - all tensors are C-ordered (row-major) and dense, exactly as NumPy holds
+ *     them: MPS tensor (Dl, d, Dr); MPO tensor (chi_l, d_out, d_in, chi_r);
+ *     environment blocks (ket bond, MPO bond, bra bond).
+ *   - suffix _d: every tensor float64.  suffix _z: a, b, c, l, r, out are
+ *     complex128 (interleaved re, im, 16 bytes); the MPO tensor w is float64
+ *     when w_is_complex == 0 (what pytenet/mpo.py:132 allocates) or complex128.
+ *   - the library never allocates: the caller passes `out` and a `workspace` of
+ *     at least *_workspace_bytes(...) bytes (device memory, 16-byte aligned).
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous with
+ *     respect to the host and re-entrant across streams.
+ *   - return value: 0 = ok; negative = PTB_ERR_* (bad argument); positive = a
+ *     cudaError_t / ncclResult_t code.  No exceptions, no exit().
+ *   - outputs never alias inputs.
+ */
+#ifndef PYTENET_B200_H
+#define PYTENET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_OK 0
+#define PTB_ERR_BAD_ARG (-1)
+#define PTB_ERR_BAD_DTYPE (-2)
+#define PTB_ERR_WORKSPACE (-3)
+#define PTB_ERR_ALIGNMENT (-4)
+#define PTB_ERR_TOO_LARGE (-5)
+#define PTB_ERR_NOT_INITIALISED (-6)
+
+#define PTB_REAL64 0
+#define PTB_COMPLEX128 1
+
+/* library version (major*10000 + minor*100 + patch) and status text */
+int ptb_version(void);
+const char* ptb_status_string(int status);
+
+/* ---------------------------------------------------------------------------
+ * Building block: strided-batched GEMM on the FP64 tensor pipe (DMMA.8x8x4).
+ *   C[b] (M x N, ldc) (+)= op(A[b]) * op(B[b]),  b = 0..batch-1
+ *   trans_a = 0: A is M x K row-major (lda);  1: A is stored K x M row-major
+ *   trans_b = 0: B is K x N row-major (ldb);  1: B is stored N x K row-major
+ *   conj_b     : use conj(B) (complex only)
+ * Leading dimensions and batch strides are in ELEMENTS of `dtype`.
+ * Replaces the np.tensordot -> OpenBLAS zgemm/dgemm calls at
+ * pytenet/chain_ops.py:50,52,56,94,96,98,273,276,278,314,316.
+ * ------------------------------------------------------------------------- */
+int ptb_gemm(int dtype, int trans_a, int trans_b, int conj_b,
+             int64_t m, int64_t n, int64_t k,
+             const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc,
+             int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c,
+             int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * apply_local_hamiltonian(a, w, l, r)            pytenet/chain_ops.py:237-279
+ *   out[i',s',j'] = sum l[i,k,i'] w[k,s',s,kappa] a[i,s,j] r[j,kappa,j']
+ *   a (Dl,d_in,Dr)  w (chi_l,d_out,d_in,chi_r)  l (Dl,chi_l,Dlp)  r (Dr,chi_r,Drp)
+ *   out (Dlp,d_out,Drp)
+ * ------------------------------------------------------------------------- */
+size_t ptb_apply_local_hamiltonian_workspace_bytes(int dtype, int64_t Dl, int64_t d_in, int64_t Dr,
+                                                   int64_t chi_l, int64_t chi_r, int64_t d_out,
+                                                   int64_t Dlp, int64_t Drp);
+int ptb_apply_local_hamiltonian_z(const void* a, const void* w, int w_is_complex, const void* l, const void* r,
+                                  void* out, int64_t Dl, int64_t d_in, int64_t Dr, int64_t chi_l, int64_t chi_r,
+                                  int64_t d_out, int64_t Dlp, int64_t Drp, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+int ptb_apply_local_hamiltonian_d(const void* a, const void* w, const void* l, const void* r, void* out,
+                                  int64_t Dl, int64_t d_in, int64_t Dr, int64_t chi_l, int64_t chi_r,
+                                  int64_t d_out, int64_t Dlp, int64_t Drp, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * apply_local_bond_contraction(c, l, r)          pytenet/chain_ops.py:282-317
+ *   out[i',j'] = sum l[i,k,i'] c[i,j] r[j,k,j']
+ *   c (Dl,Dr)  l (Dl,chi,Dlp)  r (Dr,chi,Drp)  out (Dlp,Drp)
+ * ------------------------------------------------------------------------- */
+size_t ptb_apply_local_bond_contraction_workspace_bytes(int dtype, int64_t Dl, int64_t Dr, int64_t chi,
+                                                        int64_t Dlp, int64_t Drp);
+int ptb_apply_local_bond_contraction_z(const void* c, const void* l, const void* r, void* out, int64_t Dl,
+                                       int64_t Dr, int64_t chi, int64_t Dlp, int64_t Drp, void* workspace,
+                                       size_t workspace_bytes, void* stream);
+int ptb_apply_local_bond_contraction_d(const void* c, const void* l, const void* r, void* out, int64_t Dl,
+                                       int64_t Dr, int64_t chi, int64_t Dlp, int64_t Drp, void* workspace,
+                                       size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * contraction_operator_step_left(a, b, w, l)     pytenet/chain_ops.py:60-99
+ *   l_next[j,kappa,j'] = sum l[i,k,i'] conj(b[i',s',j']) w[k,s',s,kappa] a[i,s,j]
+ *   a (Dl,d_in,Dr)  b (Dlp,d_out,Drp)  l (Dl,chi_l,Dlp)  l_next (Dr,chi_r,Drp)
+ * contraction_operator_step_right(a, b, w, r)    pytenet/chain_ops.py:16-57
+ *   r_next[i,k,i'] = sum a[i,s,j] r[j,kappa,j'] w[k,s',s,kappa] conj(b[i',s',j'])
+ *   r (Dr,chi_r,Drp)  r_next (Dl,chi_l,Dlp)
+ * (one workspace query serves both directions)
+ * ------------------------------------------------------------------------- */
+size_t ptb_env_step_workspace_bytes(int dtype, int64_t Dl, int64_t d_in, int64_t Dr, int64_t chi_l,
+                                    int64_t chi_r, int64_t d_out, int64_t Dlp, int64_t Drp);
+int ptb_env_step_left_z(const void* a, const void* b, const void* w, int w_is_complex, const void* l,
+                        void* l_next, int64_t Dl, int64_t d_in, int64_t Dr, int64_t chi_l, int64_t chi_r,
+                        int64_t d_out, int64_t Dlp, int64_t Drp, void* workspace, size_t workspace_bytes,
+                        void* stream);
+int ptb_env_step_left_d(const void* a, const void* b, const void* w, const void* l, void* l_next, int64_t Dl,
+                        int64_t d_in, int64_t Dr, int64_t chi_l, int64_t chi_r, int64_t d_out, int64_t Dlp,
+                        int64_t Drp, void* workspace, size_t workspace_bytes, void* stream);
+int ptb_env_step_right_z(const void* a, const void* b, const void* w, int w_is_complex, const void* r,
+                         void* r_next, int64_t Dl, int64_t d_in, int64_t Dr, int64_t chi_l, int64_t chi_r,
+                         int64_t d_out, int64_t Dlp, int64_t Drp, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int ptb_env_step_right_d(const void* a, const void* b, const void* w, const void* r, void* r_next, int64_t Dl,
+                         int64_t d_in, int64_t Dr, int64_t chi_l, int64_t chi_r, int64_t d_out, int64_t Dlp,
+                         int64_t Drp, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Device-resident Lanczos vector operations        pytenet/krylov.py:12-57
+ * All scalars stay on the device (double*), nothing synchronises with the host.
+ *
+ * ptb_lanczos_scratch_bytes: size of the reduction scratch buffer.
+ *
+ * ptb_lanczos_start_{d,z}:  v0 = x / |x|;  *nrm = |x|            krylov.py:26-29,36
+ *
+ * ptb_lanczos_ortho_step_{d,z}: one three-term step               krylov.py:41-43,51
+ *     alpha      = Re <w, v_j>
+ *     w         -= alpha v_j + beta_prev v_jm1      (v_jm1 / beta_prev may be NULL for j = 0)
+ *     beta       = |w|
+ *     v_next     = w / beta                         (v_next may alias w)
+ *   alpha_out, beta_out, beta_prev are device doubles.
+ *
+ * ptb_lanczos_alpha_{d,z}: closing alpha = Re <w, v_j>            krylov.py:53-56
+ *
+ * ptb_krylov_combine: out[n] = sum_j coeff[j] V[j,:], V (k x n) row-major,
+ *   coeff on the device.  v_dtype / coeff_dtype in {PTB_REAL64, PTB_COMPLEX128};
+ *   out has the promoted dtype.                     krylov.py:118 and :136
+ * ------------------------------------------------------------------------- */
+size_t ptb_lanczos_scratch_bytes(void);
+int ptb_lanczos_start_d(int64_t n, const void* x, void* v0, double* nrm, void* scratch, void* stream);
+int ptb_lanczos_start_z(int64_t n, const void* x, void* v0, double* nrm, void* scratch, void* stream);
+int ptb_lanczos_ortho_step_d(int64_t n, void* w, const void* v_j, const void* v_jm1, const double* beta_prev,
+                             double* alpha_out, double* beta_out, void* v_next, void* scratch, void* stream);
+int ptb_lanczos_ortho_step_z(int64_t n, void* w, const void* v_j, const void* v_jm1, const double* beta_prev,
+                             double* alpha_out, double* beta_out, void* v_next, void* scratch, void* stream);
+int ptb_lanczos_alpha_d(int64_t n, const void* w, const void* v_j, double* alpha_out, void* scratch, void* stream);
+int ptb_lanczos_alpha_z(int64_t n, const void* w, const void* v_j, double* alpha_out, void* scratch, void* stream);
+int ptb_krylov_combine(int v_dtype, int coeff_dtype, int64_t n, int64_t k, const void* v, int64_t ldv,
+                       const void* coeff, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Diagnostics: register-resident DMMA.8x8x4 (use_dmma != 0) or DFMA loop on
+ * `blocks` CTAs x 256 threads, to measure the FP64 pipe peak that the roofline
+ * fractions are quoted against.  `out`: blocks*256 device doubles; *flops
+ * (host) receives the number of floating-point operations issued.
+ * ------------------------------------------------------------------------- */
+int ptb_probe_fp64_pipe(int use_dmma, int blocks, int iters, double* out, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYTENET_B200_H */

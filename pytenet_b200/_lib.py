@@ -1,0 +1,83 @@
+"""
+ctypes binding of libpytenet_b200.so (the C ABI declared in include/pytenet_b200.h).
+
+There is no CPU fallback: if the library is missing or fails to load, importing
+any compute entry point raises.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpytenet_b200.so")
+
+PTB_REAL64 = 0
+PTB_COMPLEX128 = 1
+
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_ptr = ctypes.c_void_p
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/pytenet_b200.h line by line
+_DIMS8 = [_i64] * 8
+SIGNATURES = {
+    "ptb_version": (_int, []),
+    "ptb_status_string": (ctypes.c_char_p, [_int]),
+    "ptb_gemm": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
+                        _i64, _i64, _i64, _i64, _int, _ptr]),
+    "ptb_apply_local_hamiltonian_workspace_bytes": (_sz, [_int] + _DIMS8),
+    "ptb_apply_local_hamiltonian_z": (_int, [_ptr, _ptr, _int, _ptr, _ptr, _ptr] + _DIMS8 + [_ptr, _sz, _ptr]),
+    "ptb_apply_local_hamiltonian_d": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr] + _DIMS8 + [_ptr, _sz, _ptr]),
+    "ptb_apply_local_bond_contraction_workspace_bytes": (_sz, [_int] + [_i64] * 5),
+    "ptb_apply_local_bond_contraction_z": (_int, [_ptr] * 4 + [_i64] * 5 + [_ptr, _sz, _ptr]),
+    "ptb_apply_local_bond_contraction_d": (_int, [_ptr] * 4 + [_i64] * 5 + [_ptr, _sz, _ptr]),
+    "ptb_env_step_workspace_bytes": (_sz, [_int] + _DIMS8),
+    "ptb_env_step_left_z": (_int, [_ptr, _ptr, _ptr, _int, _ptr, _ptr] + _DIMS8 + [_ptr, _sz, _ptr]),
+    "ptb_env_step_left_d": (_int, [_ptr] * 5 + _DIMS8 + [_ptr, _sz, _ptr]),
+    "ptb_env_step_right_z": (_int, [_ptr, _ptr, _ptr, _int, _ptr, _ptr] + _DIMS8 + [_ptr, _sz, _ptr]),
+    "ptb_env_step_right_d": (_int, [_ptr] * 5 + _DIMS8 + [_ptr, _sz, _ptr]),
+    "ptb_lanczos_scratch_bytes": (_sz, []),
+    "ptb_lanczos_start_d": (_int, [_i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "ptb_lanczos_start_z": (_int, [_i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "ptb_lanczos_ortho_step_d": (_int, [_i64] + [_ptr] * 9),
+    "ptb_lanczos_ortho_step_z": (_int, [_i64] + [_ptr] * 9),
+    "ptb_lanczos_alpha_d": (_int, [_i64] + [_ptr] * 5),
+    "ptb_lanczos_alpha_z": (_int, [_i64] + [_ptr] * 5),
+    "ptb_krylov_combine": (_int, [_int, _int, _i64, _i64, _ptr, _i64, _ptr, _ptr, _ptr]),
+    "ptb_probe_fp64_pipe": (_int, [_int, _int, _int, _ptr, ctypes.POINTER(ctypes.c_double), _ptr]),
+}
+
+_lib = None
+
+
+class PtbError(RuntimeError):
+    """Non-zero status from the C ABI."""
+
+
+def load():
+    """Load the shared library (once).  Raises ImportError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m pytenet_b200._build` "
+            "(there is no CPU fallback for the pytenet_b200 compute path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status, what=""):
+    """Convert a C-ABI status into the reference's error behaviour."""
+    if status == 0:
+        return
+    msg = load().ptb_status_string(int(status)).decode()
+    if status == -1:
+        # the reference asserts on ranks / shapes (chain_ops.py:45-48, 89-92, 268-271, 310-312)
+        raise AssertionError(f"{what}: {msg}")
+    raise PtbError(f"{what}: status {status}: {msg}")

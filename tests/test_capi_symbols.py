@@ -1,0 +1,59 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/*.h declares
+(no compute calls -- there is no GPU on the CPU test box)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pytenet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ptb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_survey_minimum():
+    names = declared_symbols()
+    for stem in ["apply_local_hamiltonian", "apply_local_bond_contraction", "env_step_left", "env_step_right",
+                 "lanczos_ortho_step"]:
+        for sfx in ("_d", "_z"):
+            assert f"ptb_{stem}{sfx}" in names
+    assert "ptb_krylov_combine" in names
+    assert "ptb_apply_local_hamiltonian_workspace_bytes" in names
+
+
+def test_library_exports_every_declared_symbol(cuda_lib):
+    from pytenet_b200 import _lib
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(raw, name), f"{name} declared in include/pytenet_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in pytenet_b200/_lib.py"
+    assert cuda_lib.ptb_version() >= 100
+    assert cuda_lib.ptb_status_string(0) == b"ok"
+    assert b"workspace" in cuda_lib.ptb_status_string(-3)
+
+
+def test_host_side_argument_checks(cuda_lib):
+    """Bad arguments are rejected on the host before any launch (no GPU needed)."""
+    assert cuda_lib.ptb_gemm(0, 0, 0, 0, 4, 4, 4, None, 4, None, 4, None, 4, 1, 0, 0, 0, 0, None) == -1
+    assert cuda_lib.ptb_gemm(7, 0, 0, 0, 4, 4, 4, 16, 4, 16, 4, 16, 4, 1, 0, 0, 0, 0, None) == -2
+    nb = cuda_lib.ptb_apply_local_hamiltonian_workspace_bytes(1, 8, 2, 8, 5, 5, 2, 8, 8)
+    assert nb == 2 * 8 * 2 * 5 * 8 * 16
+    # workspace too small
+    assert cuda_lib.ptb_apply_local_hamiltonian_z(16, 16, 0, 16, 16, 16, 8, 2, 8, 5, 5, 2, 8, 8, 16, 10, None) == -3
+    # non-positive extent
+    assert cuda_lib.ptb_apply_local_hamiltonian_z(16, 16, 0, 16, 16, 16, 0, 2, 8, 5, 5, 2, 8, 8, 16, nb, None) == -1
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never route through oracle/ (or /root/reference)."""
+    pkg = os.path.join(ROOT, "pytenet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src, f
