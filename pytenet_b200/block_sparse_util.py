@@ -1,0 +1,174 @@
+"""
+Quantum-number (block-sparse) helpers around the hot path, device-resident
+(pytenet/block_sparse_util.py).  Quantum numbers are small host-side integer
+arrays; tensors are CUDA torch tensors.  Sector-wise QR / SVD run on the device
+through cuSOLVER (torch.linalg), which north_star names as "not the
+optimisation target"; sector order, the stable grouping of indices and the
+number of bond indices each sector contributes follow the reference exactly
+(block_sparse_util.py:33-37, 82-83, 151-169, 288-303).
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _device as dev
+
+__all__ = ["qnumber_outer_sum", "common_qnumbers", "qnumber_flatten", "is_qsparse", "enforce_qsparsity",
+           "block_sparse_qr", "block_sparse_svd"]
+
+# SVD driver for cuSOLVER: "gesvd" (QR iteration, closest to LAPACK) unless overridden
+_SVD_DRIVER = os.environ.get("PYTENET_B200_SVD_DRIVER", "gesvd")
+
+
+def qnumber_outer_sum(qnums):
+    """All sums q0[i0] + q1[i1] + ... as a tensor (host integers; :13-30)."""
+    if len(qnums) == 0:
+        return np.array(0)
+    acc = np.asarray(qnums[0])
+    for q in qnums[1:]:
+        acc = np.add.outer(acc, np.asarray(q))
+    return acc
+
+
+def common_qnumbers(qnums0, qnums1):
+    """Sorted quantum numbers present in both lists (:33-37)."""
+    return np.intersect1d(qnums0, qnums1)
+
+
+def qnumber_flatten(qnums):
+    """Quantum numbers of a fused index (:40-44)."""
+    return qnumber_outer_sum(qnums).reshape(-1)
+
+
+def _forbidden_mask(qnums, device):
+    """Boolean device tensor: True where the quantum numbers do not sum to zero.
+    Built by broadcasting the per-axis vectors on the device (no dense host mask)."""
+    nd = len(qnums)
+    total = None
+    for ax, q in enumerate(qnums):
+        shape = [1] * nd
+        shape[ax] = len(q)
+        t = torch.as_tensor(np.asarray(q, dtype=np.int64), device=device).reshape(shape)
+        total = t if total is None else total + t
+    return total != 0
+
+
+def is_qsparse(a, qnums):
+    """True iff `a` vanishes wherever the quantum numbers do not sum to zero (:47-53)."""
+    if isinstance(a, torch.Tensor) and a.is_cuda:
+        if all(not np.any(np.asarray(q)) for q in qnums):
+            return True                      # all quantum numbers zero: nothing is forbidden
+        mask = _forbidden_mask(qnums, a.device)
+        return not bool(torch.any(a[mask] != 0).item())
+    mask = qnumber_outer_sum(qnums) != 0
+    return not np.any(np.asarray(a)[mask])
+
+
+def enforce_qsparsity(a, qnums):
+    """Zero the forbidden entries of `a` in place (vectorised form of :56-64)."""
+    if isinstance(a, torch.Tensor) and a.is_cuda:
+        a[_forbidden_mask(qnums, a.device)] = 0
+    else:
+        a[qnumber_outer_sum(qnums) != 0] = 0
+
+
+def _sector_plan(q0, q1):
+    """(sectors, rows, cols): ascending common quantum numbers and, per sector, the original
+    row / column indices in stable order (mergesort of the reference, :82-83)."""
+    q0 = np.asarray(q0); q1 = np.asarray(q1)
+    sectors = common_qnumbers(q0, q1)
+    o0 = np.argsort(q0, kind="stable")
+    o1 = np.argsort(q1, kind="stable")
+    rows = [o0[q0[o0] == q] for q in sectors]
+    cols = [o1[q1[o1] == q] for q in sectors]
+    return sectors, rows, cols
+
+
+def _is_identity_range(idx, n):
+    return len(idx) == n and (n == 0 or (idx[0] == 0 and idx[-1] == n - 1 and np.all(np.diff(idx) == 1)))
+
+
+def _block(a, ri, ci):
+    """a[ri][:, ci] on the device; no copy when the sector is the whole matrix."""
+    if _is_identity_range(ri, a.shape[0]) and _is_identity_range(ci, a.shape[1]):
+        return a
+    rt = torch.as_tensor(ri, device=a.device)
+    ct = torch.as_tensor(ci, device=a.device)
+    return a.index_select(0, rt).index_select(1, ct)
+
+
+def block_sparse_qr(a, q0, q1):
+    """
+    Sector-wise reduced QR of a block-sparse matrix (`a[i, j] != 0` only if
+    `q0[i] == q1[j]`) -> `(q, r, qinterm)`; `r` is upper triangular only inside
+    each sector (:106-180, incl. the no-common-sector case :124-134).
+    """
+    assert a.ndim == 2
+    q0 = np.asarray(q0); q1 = np.asarray(q1)
+    assert len(q0) == a.shape[0] and len(q1) == a.shape[1]
+    assert is_qsparse(a, [q0, -q1])
+    sectors, rows, cols = _sector_plan(q0, q1)
+    if len(sectors) == 0:
+        assert float(torch.linalg.norm(a)) == 0
+        q = torch.zeros((a.shape[0], 1), dtype=a.dtype, device=a.device)
+        r = torch.zeros((1, a.shape[1]), dtype=a.dtype, device=a.device)
+        q[0, 0] = 1
+        return q, r, q0[:1]
+    sizes = [min(len(ri), len(ci)) for ri, ci in zip(rows, cols)]
+    nb = int(sum(sizes))
+    if len(sectors) == 1 and _is_identity_range(rows[0], a.shape[0]) and _is_identity_range(cols[0], a.shape[1]):
+        qs, rs = torch.linalg.qr(a, mode="reduced")          # dense fast path: one sector, no gather
+        return qs, rs, np.full(nb, sectors[0], dtype=q0.dtype)
+    q = torch.zeros((a.shape[0], nb), dtype=a.dtype, device=a.device)
+    r = torch.zeros((nb, a.shape[1]), dtype=a.dtype, device=a.device)
+    qinterm = np.zeros(nb, dtype=q0.dtype)
+    pos = 0
+    for qn, ri, ci, sz in zip(sectors, rows, cols, sizes):
+        qs, rs = torch.linalg.qr(_block(a, ri, ci), mode="reduced")
+        rt = torch.as_tensor(ri, device=a.device)
+        ct = torch.as_tensor(ci, device=a.device)
+        q[rt, pos:pos + sz] = qs
+        r[pos:pos + sz, ct] = rs
+        qinterm[pos:pos + sz] = qn
+        pos += sz
+    return q, r, qinterm
+
+
+def block_sparse_svd(a, q0, q1):
+    """
+    Sector-wise thin SVD of a block-sparse matrix -> `(u, s, v, q)` with `s` a host
+    float64 array ordered sector-ascending, sigma-descending inside a sector (:244-319).
+    """
+    assert a.ndim == 2
+    q0 = np.asarray(q0); q1 = np.asarray(q1)
+    assert len(q0) == a.shape[0] and len(q1) == a.shape[1]
+    assert is_qsparse(a, [q0, -q1])
+    sectors, rows, cols = _sector_plan(q0, q1)
+    if len(sectors) == 0:
+        assert float(torch.linalg.norm(a)) == 0
+        u = torch.zeros((a.shape[0], 1), dtype=a.dtype, device=a.device)
+        v = torch.zeros((1, a.shape[1]), dtype=a.dtype, device=a.device)
+        if a.shape[0] > 0:
+            u[0, 0] = 1
+        return u, np.zeros(1), v, q0[:1]
+    sizes = [min(len(ri), len(ci)) for ri, ci in zip(rows, cols)]
+    nb = int(sum(sizes))
+    if len(sectors) == 1 and _is_identity_range(rows[0], a.shape[0]) and _is_identity_range(cols[0], a.shape[1]):
+        us, ss, vs = torch.linalg.svd(a, full_matrices=False, driver=_SVD_DRIVER)
+        return us, ss.cpu().numpy(), vs, np.full(nb, sectors[0], dtype=q0.dtype)
+    u = torch.zeros((a.shape[0], nb), dtype=a.dtype, device=a.device)
+    v = torch.zeros((nb, a.shape[1]), dtype=a.dtype, device=a.device)
+    s_dev = torch.zeros(nb, dtype=dev.F64, device=a.device)
+    q = np.zeros(nb, dtype=q0.dtype)
+    pos = 0
+    for qn, ri, ci, sz in zip(sectors, rows, cols, sizes):
+        us, ss, vs = torch.linalg.svd(_block(a, ri, ci), full_matrices=False, driver=_SVD_DRIVER)
+        rt = torch.as_tensor(ri, device=a.device)
+        ct = torch.as_tensor(ci, device=a.device)
+        u[rt, pos:pos + sz] = us
+        v[pos:pos + sz, ct] = vs
+        s_dev[pos:pos + sz] = ss
+        q[pos:pos + sz] = qn
+        pos += sz
+    return u, s_dev.cpu().numpy(), v, q

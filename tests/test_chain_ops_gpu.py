@@ -1,0 +1,147 @@
+"""GPU: the four chain contractions through the C ABI against the oracle and the
+golden fixtures of the reference.  Tolerance 1e-12 relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def rel(x, y):
+    n = np.linalg.norm(y)
+    return np.linalg.norm(np.asarray(x) - np.asarray(y)) / (n if n > 0 else 1.0)
+
+
+def rnd(rng, shape, cplx):
+    x = rng.normal(size=shape)
+    if cplx:
+        x = (x + 1j * rng.normal(size=shape)) / np.sqrt(2)
+    return x
+
+
+def cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def test_golden_fixtures_device_and_host_entry(cuda_lib, golden_dir):
+    import pytenet_b200 as ptb
+    z = np.load(os.path.join(golden_dir, "chain_ops.npz"))
+    for name in z["names"]:
+        g = lambda k: z[f"{name}/{k}"]      # noqa: E731
+        a, b, w, l, r, c, rb = (g(k) for k in "a b w l r c rb".split())
+        # device-resident entry
+        out = ptb.apply_local_hamiltonian(cu(a), cu(w), cu(l), cu(r))
+        assert isinstance(out, torch.Tensor) and out.is_cuda
+        assert rel(out.cpu().numpy(), g("ref_hv")) < TOL, name
+        assert rel(ptb.apply_local_bond_contraction(cu(c), cu(l), cu(rb)).cpu().numpy(), g("ref_bond")) < TOL, name
+        assert rel(ptb.contraction_operator_step_right(cu(a), cu(b), cu(w), cu(r)).cpu().numpy(), g("ref_sr")) < TOL
+        assert rel(ptb.contraction_operator_step_left(cu(a), cu(b), cu(w), cu(l)).cpu().numpy(), g("ref_sl")) < TOL
+        # host-buffer entry (NumPy in, NumPy out): the e2e call
+        out = ptb.apply_local_hamiltonian(a, w, l, r)
+        assert isinstance(out, np.ndarray) and out.dtype == g("ref_hv").dtype and out.shape == g("ref_hv").shape
+        assert rel(out, g("ref_hv")) < TOL
+
+
+SHAPES = [
+    # Dl, d, Dr, chil, chir, Dl', Dr'
+    (1, 2, 1, 1, 1, 1, 1),
+    (1, 2, 2, 1, 4, 1, 2),
+    (2, 2, 4, 4, 5, 2, 4),
+    (16, 2, 28, 5, 5, 16, 28),          # config 1 largest site
+    (28, 2, 16, 5, 5, 28, 16),
+    (31, 3, 17, 4, 6, 29, 19),
+    (64, 4, 64, 5, 5, 64, 64),          # two-site Heisenberg
+    (48, 16, 40, 6, 6, 48, 40),         # two-site Fermi-Hubbard
+    (96, 2, 96, 37, 41, 96, 96),        # large MPO bond (molecular-like)
+    (130, 2, 257, 5, 5, 131, 255),
+]
+
+
+@pytest.mark.parametrize("cplx_state", [True, False])
+@pytest.mark.parametrize("cplx_w", [False, True])
+def test_seeded_shapes_against_oracle(cuda_lib, cplx_state, cplx_w):
+    import pytenet_b200 as ptb
+    rng = np.random.default_rng(11 + 2 * cplx_state + cplx_w)
+    for (Dl, d, Dr, cl, cr, Dlp, Drp) in SHAPES:
+        a = rnd(rng, (Dl, d, Dr), cplx_state)
+        b = rnd(rng, (Dlp, d, Drp), cplx_state)
+        w = rnd(rng, (cl, d, d, cr), cplx_w)
+        w[rng.random(w.shape) < 0.7] = 0
+        l = rnd(rng, (Dl, cl, Dlp), cplx_state)
+        r = rnd(rng, (Dr, cr, Drp), cplx_state)
+        c = rnd(rng, (Dl, Dr), cplx_state)
+        rb = rnd(rng, (Dr, cl, Drp), cplx_state)
+        tag = (Dl, d, Dr, cl, cr, Dlp, Drp)
+        got = ptb.apply_local_hamiltonian(cu(a), cu(w), cu(l), cu(r)).cpu().numpy()
+        want = oracle.apply_local_hamiltonian(a, w, l, r)
+        assert got.dtype == want.dtype and got.shape == want.shape
+        assert rel(got, want) < TOL, ("hv", tag)
+        got = ptb.apply_local_bond_contraction(cu(c), cu(l), cu(rb)).cpu().numpy()
+        assert rel(got, oracle.apply_local_bond_contraction(c, l, rb)) < TOL, ("bond", tag)
+        got = ptb.contraction_operator_step_right(cu(a), cu(b), cu(w), cu(r)).cpu().numpy()
+        assert rel(got, oracle.contraction_operator_step_right(a, b, w, r)) < TOL, ("sr", tag)
+        got = ptb.contraction_operator_step_left(cu(a), cu(b), cu(w), cu(l)).cpu().numpy()
+        assert rel(got, oracle.contraction_operator_step_left(a, b, w, l)) < TOL, ("sl", tag)
+
+
+def test_integer_dummy_edge_block(cuda_lib):
+    """The reference seeds environments with the int64 block [[[1]]] (chain_ops.py:110)."""
+    import pytenet_b200 as ptb
+    rng = np.random.default_rng(3)
+    a = rnd(rng, (4, 2, 1), True); w = rnd(rng, (5, 2, 2, 1), False)
+    r = np.array([[[1]]])
+    got = ptb.contraction_operator_step_right(a, a, w, r)
+    want = oracle.contraction_operator_step_right(a, a, w, r)
+    assert got.shape == want.shape == (4, 5, 4) and rel(got, want) < TOL
+
+
+def test_block_sparse_mpo_inner_product(cuda_lib, golden_dir):
+    """reference test_chain_ops.py:32-65 pattern (a != b, quantum numbers), seeded fixture."""
+    import pytenet_b200 as ptb
+    z = np.load(os.path.join(golden_dir, "mpo_inner.npz"))
+    n = int(z["nsites"])
+    D = z[f"psi{n-1}"].shape[2]
+    t = torch.eye(D, dtype=torch.complex128, device="cuda").reshape(D, 1, D)
+    for i in reversed(range(n)):
+        t = ptb.contraction_operator_step_right(cu(z[f"psi{i}"]), cu(z[f"chi{i}"]), cu(z[f"op{i}"]), t)
+    assert tuple(t.shape) == (1, 1, 1)
+    val = t.reshape(-1)[0].item()
+    assert abs(val - complex(z["value"])) / abs(complex(z["value"])) < TOL
+
+
+def test_shape_errors_raise_like_the_reference(cuda_lib):
+    import pytenet_b200 as ptb
+    a = np.zeros((2, 2, 2)); w = np.zeros((3, 2, 2, 3)); l = np.zeros((2, 3, 2)); r = np.zeros((2, 3, 2))
+    with pytest.raises(AssertionError):
+        ptb.apply_local_hamiltonian(a[0], w, l, r)          # rank assert, chain_ops.py:268
+    with pytest.raises(AssertionError):
+        ptb.apply_local_hamiltonian(a, w, l, np.zeros((3, 3, 2)))
+
+
+def test_hermiticity_and_linearity_at_scale(cuda_lib):
+    """Size-independent properties at a bench-like size (D=512, d=4, chi=5): with
+    Hermitian environments / MPO the effective Hamiltonian is Hermitian, <x|H y> = <H x|y>,
+    and H(x + 2y) = Hx + 2Hy."""
+    import pytenet_b200 as ptb
+    D, d, chi = 512, 4, 5
+    g = torch.Generator(device="cuda").manual_seed(5)
+    def rc(*s):
+        return torch.randn(*s, dtype=torch.complex128, device="cuda", generator=g)
+    l = rc(D, chi, D); r = rc(D, chi, D)
+    l = l + l.conj().permute(2, 1, 0); r = r + r.conj().permute(2, 1, 0)
+    w = torch.randn(chi, d, d, chi, dtype=torch.float64, device="cuda", generator=g)
+    w = w + w.permute(0, 2, 1, 3)
+    x = rc(D, d, D); y = rc(D, d, D)
+    hx = ptb.apply_local_hamiltonian(x, w, l, r)
+    hy = ptb.apply_local_hamiltonian(y, w, l, r)
+    lhs = torch.vdot(x.reshape(-1), hy.reshape(-1))
+    rhs = torch.vdot(hx.reshape(-1), y.reshape(-1))
+    assert abs((lhs - rhs).item()) / abs(lhs.item()) < 1e-11
+    hxy = ptb.apply_local_hamiltonian(x + 2 * y, w, l, r)
+    assert (torch.linalg.norm(hxy - (hx + 2 * hy)) / torch.linalg.norm(hxy)).item() < 1e-13

@@ -1,0 +1,99 @@
+"""GPU: the DMMA GEMM engine (ptb_gemm) against NumPy on seeded inputs.
+Tolerance: 1e-13 relative (Frobenius) -- north_star asks 1e-12 for the contractions."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-13
+
+
+def rel(x, y):
+    n = np.linalg.norm(y)
+    return np.linalg.norm(x - y) / (n if n > 0 else 1.0)
+
+
+def rnd(rng, shape, cplx):
+    x = rng.normal(size=shape)
+    if cplx:
+        x = x + 1j * rng.normal(size=shape)
+    return x
+
+
+def run_gemm(lib, cplx, ta, tb, cj, M, N, K, rng, batch=1, accumulate=False, pad=(0, 0, 0)):
+    from pytenet_b200 import _lib
+    lda = (M if ta else K) + pad[0]
+    ldb = (K if tb else N) + pad[1]
+    ldc = N + pad[2]
+    A = rnd(rng, (batch, K if ta else M, lda), cplx)
+    B = rnd(rng, (batch, N if tb else K, ldb), cplx)
+    C0 = rnd(rng, (batch, M, ldc), cplx)
+    dA, dB, dC = (torch.from_numpy(x).cuda() for x in (A, B, C0))
+    st = lib.ptb_gemm(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, ta, tb, cj, M, N, K,
+                      dA.data_ptr(), lda, dB.data_ptr(), ldb, dC.data_ptr(), ldc, batch,
+                      A.shape[1] * lda, B.shape[1] * ldb, M * ldc, int(accumulate),
+                      torch.cuda.current_stream().cuda_stream)
+    assert st == 0, lib.ptb_status_string(st)
+    torch.cuda.synchronize()
+    got = dC.cpu().numpy()
+    opA = A[:, :, :M].transpose(0, 2, 1) if ta else A[:, :, :K]
+    opB = B[:, :, :K].transpose(0, 2, 1) if tb else B[:, :, :N]
+    if cj:
+        opB = opB.conj()
+    want = C0.copy()
+    prod = opA @ opB
+    want[:, :, :N] = prod + (C0[:, :, :N] if accumulate else 0)
+    # padding columns of C must be untouched
+    assert np.array_equal(got[:, :, N:], C0[:, :, N:])
+    return rel(got[:, :, :N], want[:, :, :N])
+
+
+SHAPES = [(1, 1, 1), (3, 5, 7), (8, 8, 4), (17, 9, 33), (128, 64, 8), (129, 65, 9), (130, 200, 77),
+          (64, 257, 19), (300, 70, 130), (1, 300, 5), (257, 1, 64), (256, 256, 256)]
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+@pytest.mark.parametrize("ta", [0, 1])
+@pytest.mark.parametrize("tb", [0, 1])
+def test_gemm_layouts_and_ragged_shapes(cuda_lib, cplx, ta, tb):
+    rng = np.random.default_rng(100 + 4 * cplx + 2 * ta + tb)
+    for (M, N, K) in SHAPES:
+        for cj in ([0, 1] if cplx else [0]):
+            e = run_gemm(cuda_lib, cplx, ta, tb, cj, M, N, K, rng)
+            assert e < TOL, (cplx, ta, tb, cj, M, N, K, e)
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+def test_gemm_batched_accumulate_and_leading_dims(cuda_lib, cplx):
+    rng = np.random.default_rng(7 + cplx)
+    # odd leading dimensions force the 8-byte copy path for float64
+    for pad in [(0, 0, 0), (1, 3, 5), (2, 2, 2)]:
+        for (ta, tb) in [(0, 0), (1, 0), (0, 1), (1, 1)]:
+            e = run_gemm(cuda_lib, cplx, ta, tb, 0, 37, 45, 29, rng, batch=5, accumulate=True, pad=pad)
+            assert e < TOL, (cplx, pad, ta, tb, e)
+    e = run_gemm(cuda_lib, cplx, 0, 0, 0, 10, 130, 10, rng, batch=300)
+    assert e < TOL
+
+
+def test_gemm_exact_zeros_preserved(cuda_lib):
+    """Structural zeros of block-sparse operands must give exactly 0.0 outputs (SURVEY.md headline 3)."""
+    from pytenet_b200 import _device as dev
+    rng = np.random.default_rng(5)
+    a = rnd(rng, (40, 30), True); b = rnd(rng, (30, 50), True)
+    a[:20, 15:] = 0; a[20:, :15] = 0
+    b[:15, 25:] = 0; b[15:, :25] = 0
+    c = dev.gemm(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy()
+    assert np.all(c[:20, 25:] == 0) and np.all(c[20:, :25] == 0)
+    assert rel(c, a @ b) < TOL
+
+
+def test_gemm_large_against_torch(cuda_lib):
+    """Full-size sanity (size-independent check): 2048 x 1280 x 1024 complex, T/N layout, vs torch fp64."""
+    from pytenet_b200 import _device as dev
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(1024, 2048, dtype=torch.complex128, device="cuda", generator=g)
+    b = torch.randn(1024, 1280, dtype=torch.complex128, device="cuda", generator=g)
+    c = dev.gemm(a, b, trans_a=True)
+    ref = a.T @ b
+    assert (torch.linalg.norm(c - ref) / torch.linalg.norm(ref)).item() < TOL
