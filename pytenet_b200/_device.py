@@ -45,17 +45,34 @@ def to_device(x, device=None):
 
 
 def to_host(x):
-    return x.detach().cpu().numpy()
+    """Device tensor -> fresh NumPy array.  The copy lands in pinned memory from torch's
+    caching host allocator (full-speed DMA); every call returns its own buffer, so results
+    never alias each other."""
+    x = x.detach()
+    if not x.is_cuda:
+        return x.numpy()
+    if x.numel() * x.element_size() < (1 << 20):
+        return x.cpu().numpy()
+    buf = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+    buf.copy_(x)
+    return buf.numpy()
+
+
+def dense(x):
+    """Materialised, C-contiguous tensor whose memory is exactly its values: torch marks
+    conjugation / negation lazily (bit flags on a view, e.g. on the factors returned by
+    torch.linalg.svd), which a raw data_ptr() consumer would silently ignore."""
+    return x.resolve_conj().resolve_neg().contiguous()
 
 
 def as_dtype(x, cplx):
-    """Contiguous float64 / complex128 view-or-copy of a device tensor."""
+    """Contiguous float64 / complex128 view-or-copy of a device tensor (safe to pass by pointer)."""
     want = C128 if cplx else F64
     if x.dtype != want:
         if x.dtype.is_complex and not cplx:
             raise TypeError("cannot demote a complex tensor to float64")
         x = x.to(want)
-    return x.contiguous()
+    return dense(x)
 
 
 def any_complex(*tensors):

@@ -54,4 +54,4 @@ def minimize_local_energy(w, l, r, a_start, numiter: int):
     ev, u_ritz = eigh_krylov(
         lambda x: apply_local_hamiltonian(x.reshape(shape), w, l, r).reshape(-1),
         a_start.reshape(-1), numiter, 1)
-    return ev[0], u_ritz[:, 0].contiguous().reshape(shape)
+    return ev[0], dev.dense(u_ritz[:, 0]).reshape(shape)

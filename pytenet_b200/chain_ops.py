@@ -62,7 +62,7 @@ def apply_local_hamiltonian(a, w, l, r, out=None):
     Dlp, Drp = l.shape[2], r.shape[2]
     a = dev.as_dtype(a, cplx); l = dev.as_dtype(l, cplx); r = dev.as_dtype(r, cplx)
     w_cplx = w.dtype.is_complex
-    w = w.contiguous()
+    w = dev.dense(w)
     dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
     if out is None:
         out = torch.empty((Dlp, dout, Drp), dtype=a.dtype, device=device)
@@ -123,7 +123,7 @@ def _env_step(which, a, b, w, env):
         oshape = (Dl, cl, Dlp)
     a = dev.as_dtype(a, cplx); b = dev.as_dtype(b, cplx); env = dev.as_dtype(env, cplx)
     w_cplx = w.dtype.is_complex
-    w = w.contiguous()
+    w = dev.dense(w)
     dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
     out = torch.empty(oshape, dtype=a.dtype, device=device)
     nbytes = lib.ptb_env_step_workspace_bytes(dt, Dl, d, Dr, cl, cr, dout, Dlp, Drp)

@@ -1,0 +1,442 @@
+// Warp-specialised persistent FP64 / complex128 GEMM for sm_100a (second-generation engine).
+//
+// Same contract and operand-layout flags as gemm_dmma.cuh (C = op(A) op(B), row-major C,
+// no operand is ever transposed in memory), but built the Hopper/Blackwell way:
+//
+//   * persistent grid: one CTA per SM walks the tile list; 16 consumer warps
+//     (4 per SM sub-partition) + 1 producer warp.
+//   * the producer stages operand tiles with the TMA unit and the bulk-copy engine:
+//       k-contiguous operand  -> cp.async.bulk.tensor (3-D tensor map, box = 4 k x MN rows;
+//                                out-of-range rows / columns are zero-filled by hardware)
+//       mn-contiguous operand -> one cp.async.bulk per k-row into a padded row
+//                                (conflict-free fragment reads need a 32 B row skew that a
+//                                dense TMA box cannot give)
+//     completion is tracked with mbarrier transaction counts; a STAGES-deep full/empty
+//     mbarrier ring replaces every __syncthreads of the first-generation kernel, and the
+//     producer runs ahead across tile boundaries, so the prologue of tile i+1 overlaps the
+//     epilogue of tile i.
+//   * consumers hold 32 x 16 complex (32 x 32 real) warp tiles = 32 FP64 accumulators per
+//     thread, which leaves room for 16 resident warps per SM; fragments are 16-byte LDS of
+//     interleaved (re, im); complex products are 4 real DMMA.8x8x4 with the sign folded into
+//     the instruction's operand-negate modifier.
+//
+// FP64 has no tcgen05 / TMEM path on Blackwell (the UMMA kinds are f16, tf32, i8, f8f6f4 and
+// the block-scaled formats), so the FP64 tensor pipe is driven by warp-level mma.sync.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm_dmma.cuh"
+
+namespace ptb {
+
+template <bool CPLX>
+struct WsCfg {
+    static constexpr int E = CPLX ? 2 : 1;
+    static constexpr int BM = 128;
+    static constexpr int BN = CPLX ? 64 : 128;
+    static constexpr int BK = 16;
+    static constexpr int WTM = 32;
+    static constexpr int WTN = CPLX ? 16 : 32;
+    static constexpr int MT = WTM / 8;
+    static constexpr int NT = WTN / 8;
+    static constexpr int PAD = CPLX ? 2 : 4;  // elements = 32 bytes
+    static constexpr int STAGES = CPLX ? 4 : 6;
+    static constexpr int CONSUMER_WARPS = 16;
+    static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+    static constexpr int SA = BK * (BM + PAD) * E;  // doubles per stage
+    static constexpr int SB = BK * (BN + PAD) * E;
+    static constexpr int SMEM_BYTES = STAGES * (SA + SB) * 8 + 2 * STAGES * 8 + 128;
+};
+
+struct WsParams {
+    const double* A;
+    const double* B;
+    double* C;
+    int M, N, K;
+    int64_t lda, ldb, ldc;
+    int64_t sA, sB, sC;
+    int batch;
+    int accumulate;
+    int tiles_m, tiles_n;
+    int batched_a, batched_b;  // 0 when the batch stride is 0 (operand shared by all batches)
+};
+
+// ---- mbarrier / TMA primitives ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error becomes a trap (reported as a launch failure) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s at 2 GHz
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Producer side for one operand tile of one k-tile.  Returns the transaction bytes that the
+// asynchronous copies will signal.  `issue` selects between the accounting pass (all lanes,
+// also zero-fills k-tail rows of mn-contiguous operands) and the copy pass (lane 0 only).
+template <bool CPLX, bool KC, int MN_T>
+__device__ __forceinline__ uint32_t producer_operand(bool issue, double* stage, const CUtensorMap* map,
+                                                     const double* g, int64_t ld, int mn0, int k0, int MN, int K,
+                                                     int bcoord, uint64_t* bar, int lane) {
+    using Cfg = WsCfg<CPLX>;
+    constexpr int E = Cfg::E, BK = Cfg::BK, PAD = Cfg::PAD;
+    if (KC) {
+        if (issue) {
+#pragma unroll
+            for (int c = 0; c < BK / 4; c++)
+                tma_load_3d(stage + c * MN_T * 4 * E, map, bar, (k0 + 4 * c) * E, mn0, bcoord);
+        }
+        return (uint32_t)(MN_T * BK * E * 8);
+    } else {
+        const int rows = min(BK, K - k0);
+        const int cols = min(MN_T, MN - mn0);
+        const uint32_t row_bytes = (uint32_t)(cols * E * 8);
+        if (issue) {
+            for (int r = 0; r < rows; r++)
+                bulk_load_1d(stage + r * (MN_T + PAD) * E, g + ((int64_t)(k0 + r) * ld + mn0) * E, row_bytes, bar);
+        } else if (rows < BK) {
+            // k-tail: rows beyond K must read as zeros (they multiply valid data of the other operand)
+            double2* z = reinterpret_cast<double2*>(stage + rows * (MN_T + PAD) * E);
+            const int n16 = (BK - rows) * (MN_T + PAD) * E / 2;
+            for (int i = lane; i < n16; i += 32) z[i] = make_double2(0.0, 0.0);
+        }
+        return (uint32_t)rows * row_bytes;
+    }
+}
+
+template <bool CPLX, bool A_KC, bool B_KC, bool CONJB>
+__global__ void __launch_bounds__(WsCfg<CPLX>::THREADS, 1)
+gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+    using Cfg = WsCfg<CPLX>;
+    constexpr int E = Cfg::E, BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK;
+    constexpr int MT = Cfg::MT, NT = Cfg::NT, PAD = Cfg::PAD, STAGES = Cfg::STAGES;
+    constexpr int SA = Cfg::SA, SB = Cfg::SB;
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    double* sA = reinterpret_cast<double*>(base);
+    double* sB = sA + STAGES * SA;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * SB);
+    uint64_t* empty = full + STAGES;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], Cfg::CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int KT = (p.K + BK - 1) / BK;
+    const int tiles_per_batch = p.tiles_m * p.tiles_n;
+    const long long total = (long long)tiles_per_batch * p.batch;
+    constexpr int GROUP = 8;
+    const int per_group = GROUP * p.tiles_n;
+
+    int stage = 0;
+    uint32_t phase = 0;
+
+    if (warp == Cfg::CONSUMER_WARPS) {
+        // ===================== producer warp =====================
+        for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+            const int bz = (int)(t / tiles_per_batch);
+            const int tile = (int)(t - (long long)bz * tiles_per_batch);
+            const int grp = tile / per_group;
+            const int first_m = grp * GROUP;
+            const int gsize = min(p.tiles_m - first_m, GROUP);
+            const int tm = first_m + (tile % per_group) % gsize;
+            const int tn = (tile % per_group) / gsize;
+            const int m0 = tm * BM, n0 = tn * BN;
+            const double* Ag = p.A + (int64_t)bz * p.sA * E;
+            const double* Bg = p.B + (int64_t)bz * p.sB * E;
+            const int ba = p.batched_a ? bz : 0, bb = p.batched_b ? bz : 0;
+            for (int kt = 0; kt < KT; kt++) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                double* a_st = sA + stage * SA;
+                double* b_st = sB + stage * SB;
+                const int k0 = kt * BK;
+                uint32_t bytes = producer_operand<CPLX, A_KC, BM>(false, a_st, &tmA, Ag, p.lda, m0, k0, p.M, p.K, ba,
+                                                                  &full[stage], lane);
+                bytes += producer_operand<CPLX, B_KC, BN>(false, b_st, &tmB, Bg, p.ldb, n0, k0, p.N, p.K, bb,
+                                                          &full[stage], lane);
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[stage], bytes);
+                    producer_operand<CPLX, A_KC, BM>(true, a_st, &tmA, Ag, p.lda, m0, k0, p.M, p.K, ba, &full[stage],
+                                                     lane);
+                    producer_operand<CPLX, B_KC, BN>(true, b_st, &tmB, Bg, p.ldb, n0, k0, p.N, p.K, bb, &full[stage],
+                                                     lane);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    const int g = lane >> 2, q = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int a_row = wm * Cfg::WTM + g;
+    const int b_col = wn * Cfg::WTN + g;
+    const int a_off = A_KC ? ((a_row << 2) + q) * E : (q * (BM + PAD) + a_row) * E;
+    const int b_off = B_KC ? ((b_col << 2) + q) * E : (q * (BN + PAD) + b_col) * E;
+    constexpr int A_KS = A_KC ? BM * 4 * E : 4 * (BM + PAD) * E;
+    constexpr int B_KS = B_KC ? BN * 4 * E : 4 * (BN + PAD) * E;
+    constexpr int A_MT = A_KC ? 8 * 4 * E : 8 * E;
+    constexpr int B_NT = B_KC ? 8 * 4 * E : 8 * E;
+
+    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+        const int bz = (int)(t / tiles_per_batch);
+        const int tile = (int)(t - (long long)bz * tiles_per_batch);
+        const int grp = tile / per_group;
+        const int first_m = grp * GROUP;
+        const int gsize = min(p.tiles_m - first_m, GROUP);
+        const int tm = first_m + (tile % per_group) % gsize;
+        const int tn = (tile % per_group) / gsize;
+        const int m0 = tm * BM, n0 = tn * BN;
+
+        double acc[MT][NT][2 * E];
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++)
+#pragma unroll
+                for (int e = 0; e < 2 * E; e++) acc[i][j][e] = 0.0;
+
+        for (int kt = 0; kt < KT; kt++) {
+            mbar_wait(&full[stage], phase);
+            const double* As = sA + stage * SA + a_off;
+            const double* Bs = sB + stage * SB + b_off;
+#pragma unroll
+            for (int ks = 0; ks < BK / 4; ks++) {
+                if constexpr (CPLX) {
+                    double2 af[MT], bf[NT];
+#pragma unroll
+                    for (int i = 0; i < MT; i++)
+                        af[i] = *reinterpret_cast<const double2*>(As + ks * A_KS + i * A_MT);
+#pragma unroll
+                    for (int j = 0; j < NT; j++)
+                        bf[j] = *reinterpret_cast<const double2*>(Bs + ks * B_KS + j * B_NT);
+#pragma unroll
+                    for (int i = 0; i < MT; i++)
+#pragma unroll
+                        for (int j = 0; j < NT; j++) {
+                            const double nbi = -bf[j].y;
+                            const double bi_re = CONJB ? bf[j].y : nbi;   // multiplies a.im into re
+                            const double bi_im = CONJB ? nbi : bf[j].y;   // multiplies a.re into im
+                            dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+                            dmma_8x8x4(acc[i][j][2], acc[i][j][3], af[i].x, bi_im);
+                            dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i].y, bi_re);
+                            dmma_8x8x4(acc[i][j][2], acc[i][j][3], af[i].y, bf[j].x);
+                        }
+                } else {
+                    double af[MT], bf[NT];
+#pragma unroll
+                    for (int i = 0; i < MT; i++) af[i] = As[ks * A_KS + i * A_MT];
+#pragma unroll
+                    for (int j = 0; j < NT; j++) bf[j] = Bs[ks * B_KS + j * B_NT];
+#pragma unroll
+                    for (int i = 0; i < MT; i++)
+#pragma unroll
+                        for (int j = 0; j < NT; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+
+        // epilogue (overlaps the producer's prefetch of the next tile)
+        double* __restrict__ Cg = p.C + (int64_t)bz * p.sC * E;
+#pragma unroll
+        for (int i = 0; i < MT; i++) {
+            const int row = m0 + wm * Cfg::WTM + i * 8 + g;
+            if (row >= p.M) continue;
+            double* crow = Cg + (int64_t)row * p.ldc * E;
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                const int col = n0 + wn * Cfg::WTN + j * 8 + 2 * q;
+                if constexpr (CPLX) {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        if (col + e < p.N) {
+                            double2* dst = reinterpret_cast<double2*>(crow + (int64_t)(col + e) * 2);
+                            double2 v = make_double2(acc[i][j][e], acc[i][j][2 + e]);
+                            if (p.accumulate) {
+                                const double2 old = *dst;
+                                v.x += old.x;
+                                v.y += old.y;
+                            }
+                            *dst = v;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        if (col + e < p.N) {
+                            double v = acc[i][j][e];
+                            if (p.accumulate) v += crow[col + e];
+                            crow[col + e] = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+// Tensor map over a k-contiguous operand X[mn][k] (leading dimension ld, batch stride sx, all in
+// elements): dims (fastest first) = {K*E doubles, MN rows, batches}; box = {4*E doubles, MN_T rows, 1}.
+template <bool CPLX>
+static bool make_kc_map(CUtensorMap* map, const double* ptr, int MN, int K, int64_t ld, int64_t sx, int batch,
+                        int mn_tile) {
+    constexpr int E = CPLX ? 2 : 1;
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    const bool batched = (sx != 0) && batch > 1;
+    cuuint64_t dims[3] = {(cuuint64_t)K * E, (cuuint64_t)MN, (cuuint64_t)(batched ? batch : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * E * 8, (cuuint64_t)(batched ? sx * E * 8 : (int64_t)ld * E * 8 * MN)};
+    if (strides[0] % 16 != 0 || strides[1] % 16 != 0) return false;
+    if (strides[0] >= (1ULL << 40) || strides[1] >= (1ULL << 40)) return false;
+    if (strides[1] == 0) strides[1] = 16;
+    cuuint32_t box[3] = {(cuuint32_t)(4 * E), (cuuint32_t)mn_tile, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <bool CPLX, bool A_KC, bool B_KC, bool CONJB>
+static int launch_ws_inst(const WsParams& p, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+    using Cfg = WsCfg<CPLX>;
+    auto kern = gemm_ws_kernel<CPLX, A_KC, B_KC, CONJB>;
+    static bool configured = false;
+    static int num_sms = 0;
+    if (!configured) {
+        PTB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        int devid = 0;
+        PTB_CUDA_TRY(cudaGetDevice(&devid));
+        PTB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid));
+        configured = true;
+    }
+    const long long total = (long long)p.tiles_m * p.tiles_n * p.batch;
+    const int grid = (int)(total < num_sms ? total : num_sms);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p, ta, tb);
+    return cuda_status(cudaGetLastError());
+}
+
+// Returns PTB_OK when launched, 1 when the fast path does not apply (caller falls back to the
+// first-generation kernel), or an error status.
+template <bool CPLX>
+static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp, cudaStream_t stream) {
+    using Cfg = WsCfg<CPLX>;
+    constexpr int E = Cfg::E;
+    const bool a_kc = (transA == 0), b_kc = (transB != 0);
+    // 16-byte granularity of the bulk / tensor copies
+    auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+    if (!al16(gp.A) || !al16(gp.B)) return 1;
+    if (!CPLX) {
+        if ((gp.lda | gp.ldb | gp.sA | gp.sB) & 1) return 1;
+        if (!a_kc && (gp.M & 1)) return 1;  // partial mn-rows must stay multiples of 16 bytes
+        if (!b_kc && (gp.N & 1)) return 1;
+    }
+    if (gp.K < 1) return 1;
+    WsParams p;
+    p.A = gp.A; p.B = gp.B; p.C = gp.C;
+    p.M = gp.M; p.N = gp.N; p.K = gp.K;
+    p.lda = gp.lda; p.ldb = gp.ldb; p.ldc = gp.ldc;
+    p.sA = gp.sA; p.sB = gp.sB; p.sC = gp.sC;
+    p.batch = gp.batch;
+    p.accumulate = gp.accumulate;
+    p.tiles_m = (gp.M + Cfg::BM - 1) / Cfg::BM;
+    p.tiles_n = (gp.N + Cfg::BN - 1) / Cfg::BN;
+    p.batched_a = (gp.sA != 0 && gp.batch > 1) ? 1 : 0;
+    p.batched_b = (gp.sB != 0 && gp.batch > 1) ? 1 : 0;
+    CUtensorMap ta, tb;
+    memset(&ta, 0, sizeof(ta));
+    memset(&tb, 0, sizeof(tb));
+    if (a_kc && !make_kc_map<CPLX>(&ta, gp.A, gp.M, gp.K, gp.lda, gp.sA, gp.batch, Cfg::BM)) return 1;
+    if (b_kc && !make_kc_map<CPLX>(&tb, gp.B, gp.N, gp.K, gp.ldb, gp.sB, gp.batch, Cfg::BN)) return 1;
+    (void)E;
+    const bool cj = CPLX && conjB;
+    const int sel = (a_kc ? 4 : 0) | (b_kc ? 2 : 0) | (cj ? 1 : 0);
+    switch (sel) {
+        case 0: return launch_ws_inst<CPLX, false, false, false>(p, ta, tb, stream);
+        case 1: return launch_ws_inst<CPLX, false, false, CPLX>(p, ta, tb, stream);
+        case 2: return launch_ws_inst<CPLX, false, true, false>(p, ta, tb, stream);
+        case 3: return launch_ws_inst<CPLX, false, true, CPLX>(p, ta, tb, stream);
+        case 4: return launch_ws_inst<CPLX, true, false, false>(p, ta, tb, stream);
+        case 5: return launch_ws_inst<CPLX, true, false, CPLX>(p, ta, tb, stream);
+        case 6: return launch_ws_inst<CPLX, true, true, false>(p, ta, tb, stream);
+        case 7: return launch_ws_inst<CPLX, true, true, CPLX>(p, ta, tb, stream);
+    }
+    return 1;
+}
+
+}  // namespace ptb

@@ -19,9 +19,10 @@ from .qnumber import encode_quantum_number_pair
 __all__ = ["heisenberg_xxz_1d_mpo", "ising_1d_mpo", "fermi_hubbard_1d_mpo"]
 
 
-def _chain_mpo(qsite, qbond, wbulk, nsites, first_row, last_col, device=None):
-    """Open chain from one bulk tensor: the first site keeps row `first_row`, the last
-    site column `last_col` of the operator-valued matrix."""
+def _chain_tensors(qbond, wbulk, nsites, first_row, last_col):
+    """Host tensors and bond quantum numbers of an open chain built from one bulk tensor:
+    the first site keeps row `first_row`, the last site column `last_col` of the
+    operator-valued matrix."""
     tensors = []
     qbonds = []
     for i in range(nsites):
@@ -35,15 +36,15 @@ def _chain_mpo(qsite, qbond, wbulk, nsites, first_row, last_col, device=None):
         tensors.append(np.ascontiguousarray(w))
         qbonds.append(np.asarray(ql))
     qbonds.append(np.asarray(qbond[last_col:last_col + 1]))
+    return tensors, qbonds
+
+
+def _chain_mpo(qsite, qbond, wbulk, nsites, first_row, last_col, device=None):
+    tensors, qbonds = _chain_tensors(qbond, wbulk, nsites, first_row, last_col)
     return MPO.from_tensors(qsite, qbonds, tensors, device=device)
 
 
-def heisenberg_xxz_1d_mpo(nsites: int, J: float, D: float, h: float, device=None) -> MPO:
-    """
-    XXZ Heisenberg chain `sum J (X X + Y Y) + D Z Z - h Z` (spin 1/2), MPO bond
-    dimension 5; physical quantum numbers are 2 Sz = (1, -1) as in
-    pytenet/hamiltonian/heisenberg.py:14-55.
-    """
+def _xxz_bulk(J, D, h):
     sup = np.array([[0., 1.], [0., 0.]])
     sdn = np.array([[0., 0.], [1., 0.]])
     sz = np.array([[0.5, 0.], [0., -0.5]])
@@ -59,14 +60,20 @@ def heisenberg_xxz_1d_mpo(nsites: int, J: float, D: float, h: float, device=None
     w[2, :, :, 4] = sup
     w[3, :, :, 4] = sz
     w[4, :, :, 4] = id2
-    return _chain_mpo([1, -1], np.array([0, 2, -2, 0, 0]), w, nsites, 0, 4, device)
+    return [1, -1], np.array([0, 2, -2, 0, 0]), w, 0, 4
 
 
-def ising_1d_mpo(nsites: int, J: float, h: float, g: float, device=None) -> MPO:
+def heisenberg_xxz_1d_mpo(nsites: int, J: float, D: float, h: float, device=None) -> MPO:
     """
-    Ising chain `sum J Z Z + h Z + g X` (Pauli matrices), MPO bond dimension 3, all
-    quantum numbers zero (pytenet/hamiltonian/ising.py:14-69).
+    XXZ Heisenberg chain `sum J (X X + Y Y) + D Z Z - h Z` (spin 1/2), MPO bond
+    dimension 5; physical quantum numbers are 2 Sz = (1, -1) as in
+    pytenet/hamiltonian/heisenberg.py:14-55.
     """
+    qsite, qb, w, first, last = _xxz_bulk(J, D, h)
+    return _chain_mpo(qsite, qb, w, nsites, first, last, device)
+
+
+def _ising_bulk(J, h, g):
     sx = np.array([[0., 1.], [1., 0.]])
     sz = np.array([[1., 0.], [0., -1.]])
     id2 = np.identity(2)
@@ -76,16 +83,19 @@ def ising_1d_mpo(nsites: int, J: float, h: float, g: float, device=None) -> MPO:
     w[0, :, :, 2] = h * sz + g * sx
     w[1, :, :, 2] = sz
     w[2, :, :, 2] = id2
-    return _chain_mpo([0, 0], np.zeros(3, dtype=int), w, nsites, 0, 2, device)
+    return [0, 0], np.zeros(3, dtype=int), w, 0, 2
 
 
-def fermi_hubbard_1d_mpo(nsites: int, t: float, u: float, mu: float, device=None) -> MPO:
+def ising_1d_mpo(nsites: int, J: float, h: float, g: float, device=None) -> MPO:
     """
-    Fermi-Hubbard chain with nearest-neighbour hopping `t`, interaction
-    `u (n_up - 1/2)(n_dn - 1/2)` and chemical potential `mu`, Jordan-Wigner ordered
-    (up, down) per site; MPO bond dimension 6; physical quantum numbers are
-    (particle number, spin) pairs (pytenet/hamiltonian/fermi_hubbard.py:14-85).
+    Ising chain `sum J Z Z + h Z + g X` (Pauli matrices), MPO bond dimension 3, all
+    quantum numbers zero (pytenet/hamiltonian/ising.py:14-69).
     """
+    qsite, qb, w, first, last = _ising_bulk(J, h, g)
+    return _chain_mpo(qsite, qb, w, nsites, first, last, device)
+
+
+def _fermi_hubbard_bulk(t, u, mu):
     qsite = [encode_quantum_number_pair(n, s) for n, s in zip([0, 1, 1, 2], [0, -1, 1, 0])]
     id2 = np.identity(2)
     cr = np.array([[0., 0.], [1., 0.]])      # creation
@@ -111,4 +121,15 @@ def fermi_hubbard_1d_mpo(nsites: int, t: float, u: float, mu: float, device=None
                    encode_quantum_number_pair(1, 1), encode_quantum_number_pair(-1, -1),
                    encode_quantum_number_pair(1, -1), encode_quantum_number_pair(-1, 1),
                    0])
-    return _chain_mpo(qsite, qb, w, nsites, 0, 5, device)
+    return qsite, qb, w, 0, 5
+
+
+def fermi_hubbard_1d_mpo(nsites: int, t: float, u: float, mu: float, device=None) -> MPO:
+    """
+    Fermi-Hubbard chain with nearest-neighbour hopping `t`, interaction
+    `u (n_up - 1/2)(n_dn - 1/2)` and chemical potential `mu`, Jordan-Wigner ordered
+    (up, down) per site; MPO bond dimension 6; physical quantum numbers are
+    (particle number, spin) pairs (pytenet/hamiltonian/fermi_hubbard.py:14-85).
+    """
+    qsite, qb, w, first, last = _fermi_hubbard_bulk(t, u, mu)
+    return _chain_mpo(qsite, qb, w, nsites, first, last, device)

@@ -56,8 +56,8 @@ def _lanczos_core(afunc, vstart, numiter):
         w = afunc(V[j]).reshape(-1)
         if w.dtype != V.dtype:
             w = w.to(V.dtype)
-        if not w.is_contiguous():
-            w = w.contiguous()
+        if not w.is_contiguous() or w.is_conj():
+            w = dev.dense(w)
         if w.data_ptr() == vj:
             w = w.clone()
         assert w.shape[0] == n

@@ -48,7 +48,7 @@ class MPO:
     def from_tensors(cls, qsite, qbonds, tensors, device=None):
         """Wrap host (NumPy) or device tensors, e.g. the output of a reference Hamiltonian builder."""
         op = cls(qsite, qbonds, fill="postpone", device=device)
-        op.a = [dev.to_device(t, op.device).contiguous() for t in tensors]
+        op.a = [dev.dense(dev.to_device(t, op.device)) for t in tensors]
         assert len(op.a) == len(op.qbonds) - 1
         return op
 
@@ -86,5 +86,5 @@ def mpo_merge_tensor_pair(a0, a1):
     b1b, p1, q1, b2 = a1.shape
     assert b1 == b1b
     t = dev.gemm(a0.reshape(b0 * p0 * q0, b1), a1.reshape(b1, p1 * q1 * b2))
-    t = t.reshape(b0, p0, q0, p1, q1, b2).permute(0, 1, 3, 2, 4, 5).contiguous()
+    t = dev.dense(t.reshape(b0, p0, q0, p1, q1, b2).permute(0, 1, 3, 2, 4, 5))
     return t.reshape(b0, p0 * p1, q0 * q1, b2)

@@ -97,7 +97,7 @@ class MPS:
     def from_tensors(cls, qsite, qbonds, tensors, device=None):
         """Wrap existing tensors (NumPy or torch), uploading them to the device."""
         psi = cls(qsite, qbonds, fill="postpone", device=device)
-        psi.a = [dev.to_device(t, psi.device).contiguous() for t in tensors]
+        psi.a = [dev.dense(dev.to_device(t, psi.device)) for t in tensors]
         assert len(psi.a) == len(psi.qbonds) - 1
         return psi
 
@@ -179,17 +179,17 @@ def mps_local_orthonormalize_left_qr(a, a_next, qsite, qbonds):
     s = a.shape
     assert len(s) == 3
     q, r, qbond = block_sparse_qr(a.reshape(s[0] * s[1], s[2]), qnumber_flatten((qbonds[0], qsite)), qbonds[1])
-    a = q.reshape(s[0], s[1], q.shape[1]).contiguous()
+    a = dev.dense(q.reshape(s[0], s[1], q.shape[1]))
     return a, _left_multiply(r, a_next), qbond
 
 
 def mps_local_orthonormalize_right_qr(a, a_prev, qsite, qbonds):
     """Right-orthonormalise `a` by QR of its bond-flipped matricisation (mps.py:476-491)."""
-    at = a.permute(2, 1, 0).contiguous()
+    at = dev.dense(a.permute(2, 1, 0))
     s = at.shape
     assert len(s) == 3
     q, r, qbond = block_sparse_qr(at.reshape(s[0] * s[1], s[2]), qnumber_flatten((-qbonds[1], qsite)), -qbonds[0])
-    a = q.reshape(s[0], s[1], q.shape[1]).permute(2, 1, 0).contiguous()
+    a = dev.dense(q.reshape(s[0], s[1], q.shape[1]).permute(2, 1, 0))
     return a, _right_multiply_t(a_prev, r), -qbond
 
 
@@ -228,4 +228,4 @@ def mps_split_tensor_svd(a, qsite0, qsite1, qbonds_outer, svd_distr: str, tol=0)
         v = v * rt[:, None]
     else:
         raise ValueError('`svd_distr` parameter must be "left", "right" or "sqrt".')
-    return u.reshape(b0, d0, nb).contiguous(), v.reshape(nb, d1, b2).contiguous(), qbond
+    return dev.dense(u.reshape(b0, d0, nb)), dev.dense(v.reshape(nb, d1, b2)), qbond

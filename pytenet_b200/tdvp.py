@@ -46,9 +46,9 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
             b0, d, b1 = psi.a[i].shape
             q, c, psi.qbonds[i + 1] = block_sparse_qr(
                 psi.a[i].reshape(b0 * d, b1), qnumber_flatten((psi.qbonds[i], psi.qsite)), psi.qbonds[i + 1])
-            psi.a[i] = q.reshape(b0, d, q.shape[1]).contiguous()
+            psi.a[i] = dev.dense(q.reshape(b0, d, q.shape[1]))
             lblocks[i + 1] = contraction_operator_step_left(psi.a[i], psi.a[i], ham[i], lblocks[i])
-            c = local_bond_step(lblocks[i + 1], rblocks[i], c.contiguous(), -0.5 * dt, k)
+            c = local_bond_step(lblocks[i + 1], rblocks[i], dev.dense(c), -0.5 * dt, k)
             nxt = psi.a[i + 1]
             psi.a[i + 1] = dev.gemm(c, nxt.reshape(nxt.shape[0], -1)).reshape((c.shape[0],) + tuple(nxt.shape[1:]))
 
@@ -58,14 +58,14 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
 
         # right -> left (tdvp.py:92-115)
         for i in reversed(range(1, nsites)):
-            at = psi.a[i].permute(2, 1, 0).contiguous()
+            at = dev.dense(psi.a[i].permute(2, 1, 0))
             b1, d, b0 = at.shape
             q, c, qbond = block_sparse_qr(
                 at.reshape(b1 * d, b0), qnumber_flatten((-psi.qbonds[i + 1], psi.qsite)), -psi.qbonds[i])
             psi.qbonds[i] = -qbond
-            psi.a[i] = q.reshape(b1, d, q.shape[1]).permute(2, 1, 0).contiguous()
+            psi.a[i] = dev.dense(q.reshape(b1, d, q.shape[1]).permute(2, 1, 0))
             rblocks[i - 1] = contraction_operator_step_right(psi.a[i], psi.a[i], ham[i], rblocks[i])
-            c = local_bond_step(lblocks[i], rblocks[i - 1], c.T.contiguous(), -0.5 * dt, k)
+            c = local_bond_step(lblocks[i], rblocks[i - 1], dev.dense(c.T), -0.5 * dt, k)
             prv = psi.a[i - 1]
             psi.a[i - 1] = dev.gemm(prv.reshape(-1, prv.shape[2]), c).reshape(tuple(prv.shape[:2]) + (c.shape[1],))
             psi.a[i - 1] = local_hamiltonian_step(

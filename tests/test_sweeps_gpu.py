@@ -1,0 +1,191 @@
+"""GPU: the four sweep drivers (device-resident) against the golden fixtures generated from
+the reference and against exact results, mirroring the reference's own tests
+(test/test_tdvp.py:7-119, test/test_dmrg.py:5-95).
+
+Tolerances: energies / observables 1e-10 (north_star); sector layouts (`qbonds`) and bond
+dimensions bit-exact; state vectors 1e-9 (gauge-invariant full vectors after many local steps)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+from scipy.linalg import expm
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(x, y):
+    n = np.linalg.norm(y)
+    return np.linalg.norm(np.asarray(x) - np.asarray(y)) / (n if n > 0 else 1.0)
+
+
+def load_mps(ptb, z, tag, n):
+    return ptb.MPS.from_tensors(z[f"{tag}/qsite"], [z[f"{tag}/qb{i}"] for i in range(n + 1)],
+                                [z[f"{tag}/a{i}"] for i in range(n)])
+
+
+def load_mpo(ptb, z, tag="h"):
+    n = int(z[f"{tag}/nsites"])
+    return ptb.MPO.from_tensors(z[f"{tag}/qsite"], [z[f"{tag}/qb{i}"] for i in range(n + 1)],
+                                [z[f"{tag}/w{i}"] for i in range(n)]), n
+
+
+def test_tdvp_readme_config(cuda_lib, golden_dir):
+    """BASELINE config 1 (README.rst:18-48): XXZ L=10, tdvp_singlesite dt=0.01-0.05j, k=5."""
+    import pytenet_b200 as ptb
+    z = np.load(os.path.join(golden_dir, "tdvp_xxz_L10.npz"))
+    h, n = load_mpo(ptb, z)
+    psi = load_mps(ptb, z, "psi0", n)
+    nrm = ptb.tdvp_singlesite(h, psi, complex(z["dt"]), int(z["nsteps"]), numiter_lanczos=int(z["k"]))
+    assert abs(nrm - float(z["single/nrm"])) < 1e-12
+    assert all(t.is_cuda for t in psi.a)
+    assert rel(psi.to_vector(), z["single/vec"]) < 1e-9
+    en = ptb.mpo_average(psi, h)
+    assert abs(en - complex(z["single/energy"])) < 1e-10
+    psi = load_mps(ptb, z, "psi0", n)
+    ptb.tdvp_twosite(h, psi, complex(z["dt"]), int(z["two/nsteps"]), numiter_lanczos=int(z["two/k"]),
+                     tol_split=float(z["two/tol"]))
+    assert psi.bond_dims == list(z["two/bond_dims"])
+    assert rel(psi.to_vector(), z["two/vec"]) < 1e-9
+
+
+def test_tdvp_quantum_numbers_bit_exact_sectors(cuda_lib, golden_dir):
+    import pytenet_b200 as ptb
+    z = np.load(os.path.join(golden_dir, "tdvp_xxz_qnum_L8.npz"))
+    h, n = load_mpo(ptb, z)
+    psi = load_mps(ptb, z, "psi0", n)
+    ptb.tdvp_twosite(h, psi, complex(z["dt"]), int(z["nsteps"]), numiter_lanczos=10)
+    for i in range(n + 1):
+        assert np.array_equal(psi.qbonds[i], z[f"two/qb{i}"]), f"sector layout of bond {i}"
+    assert rel(psi.to_vector(), z["two/vec"]) < 1e-9
+    for i in range(n):
+        assert ptb.is_qsparse(psi.a[i], [psi.qbonds[i], psi.qsite, -psi.qbonds[i + 1]])
+    psi = load_mps(ptb, z, "psi0", n)
+    ptb.tdvp_singlesite(h, psi, complex(z["dt"]), int(z["nsteps"]), numiter_lanczos=5)
+    for i in range(n + 1):
+        assert np.array_equal(psi.qbonds[i], z[f"single/qb{i}"])
+    assert rel(psi.to_vector(), z["single/vec"]) < 1e-9
+
+
+def test_dmrg_notebook_known_answer(cuda_lib, golden_dir):
+    """doc/dmrg.ipynb:130,140: e0 = -18.48435890403327, bond dims [1,4,16,30,16,4,1]."""
+    import pytenet_b200 as ptb
+    z = np.load(os.path.join(golden_dir, "dmrg_fermi_hubbard_L6.npz"))
+    h, n = load_mpo(ptb, z)
+    psi = load_mps(ptb, z, "psi0", n)
+    assert psi.a[0].dtype == torch.float64          # dtype="real" start (test_dmrg.py:24 pattern)
+    en = ptb.dmrg_twosite(h, psi, 4, tol_split=1e-8)
+    assert abs(en[-1] - (-18.48435890403327)) < 1e-10
+    assert np.max(np.abs(en - z["two/en"])) < 1e-10
+    assert psi.bond_dims == [1, 4, 16, 30, 16, 4, 1]
+    for i in range(n + 1):
+        assert np.array_equal(psi.qbonds[i], z[f"two/qb{i}"])
+    assert abs(np.linalg.norm(psi.to_vector()) - 1) < 1e-12
+    psi = load_mps(ptb, z, "psi1", n)
+    en1 = ptb.dmrg_singlesite(h, psi, 3)
+    assert np.max(np.abs(en1 - z["single/en"])) < 1e-10
+
+
+def test_basics_notebook_known_answer(cuda_lib, golden_dir):
+    """doc/basics.ipynb:256,530."""
+    import pytenet_b200 as ptb
+    z = np.load(os.path.join(golden_dir, "basics_notebook.npz"))
+    h, n = load_mpo(ptb, z)
+    psi = load_mps(ptb, z, "psi0", n)
+    nrm = psi.orthonormalize(mode="left")
+    assert abs(nrm - 0.008359386283800499) < 1e-15
+    avg = ptb.mpo_average(psi, h)
+    assert abs(avg.real - 9.188269028617416) < 1e-12 and abs(avg.imag) < 1e-12
+
+
+def test_same_seed_gives_reference_tensors(cuda_lib, golden_dir):
+    """MPS(..., fill="random", rng) draws the reference's exact tensors for a seed (mps.py:50-71)."""
+    import pytenet_b200 as ptb
+    z = np.load(os.path.join(golden_dir, "basics_notebook.npz"))
+    rng = np.random.default_rng(42)
+    b = [1, 4, 15, 13, 7, 1]
+    psi = ptb.MPS(np.zeros(3, dtype=int), [np.zeros(bi, dtype=int) for bi in b], fill="random", rng=rng)
+    for i in range(5):
+        assert np.array_equal(psi.a[i].cpu().numpy(), z[f"psi0/a{i}"])
+    z = np.load(os.path.join(golden_dir, "dmrg_fermi_hubbard_L6.npz"))
+    rng = np.random.default_rng(42)
+    psi = ptb.MPS.construct_random(6, z["h/qsite"], ptb.encode_quantum_number_pair(7, 1), max_vdim=18,
+                                   dtype="real", rng=rng)
+    for i in range(6):
+        assert np.array_equal(psi.a[i].cpu().numpy(), z[f"psi0/a{i}"])
+        assert np.array_equal(psi.qbonds[i], z[f"psi0/qb{i}"])
+
+
+def test_tdvp_against_exact_evolution(cuda_lib):
+    """reference test_tdvp.py:7-75 with a seed and this package's own input builder."""
+    import pytenet_b200 as ptb
+    rng = np.random.default_rng(17)
+    L = 8
+    dt = 0.02 - 0.05j
+    nsteps = 8
+    h = ptb.heisenberg_xxz_1d_mpo(L, 4.0 / 3, 5.0 / 13, -2.0 / 7)
+    spin_tot = 1
+    qbonds = [np.array([0])]
+    for _ in range(L - 1):
+        qbonds.append(np.sort(np.array([q + h.qsite for q in qbonds[-1]]).reshape(-1)))
+    qbonds.append(np.array([2 * spin_tot]))
+    psi = ptb.MPS(h.qsite, qbonds, fill="random", rng=rng)
+    psi.orthonormalize(mode="left")
+    psi.orthonormalize(mode="right")
+    for i in range(L):
+        psi.a[i][6:, :, :] = 0
+        psi.a[i][:, :, 6:] = 0
+    psi.orthonormalize(mode="left")
+    assert psi.qbonds[-1][0] == 2 * spin_tot
+    ref = expm(-dt * nsteps * h.to_matrix()) @ psi.to_vector()
+    p1 = copy.deepcopy(psi); p2 = copy.deepcopy(psi)
+    ptb.tdvp_singlesite(h, p1, dt, nsteps, numiter_lanczos=5)
+    ptb.tdvp_twosite(h, p2, dt, nsteps, numiter_lanczos=10)
+    assert np.allclose(p1.to_vector(), ref, atol=2e-5)
+    assert np.allclose(p2.to_vector(), ref, atol=1e-10)
+
+
+def test_tdvp_time_reversal_symmetry(cuda_lib):
+    """reference test_tdvp.py:78-119."""
+    import pytenet_b200 as ptb
+    rng = np.random.default_rng(23)
+    L = 8
+    h = ptb.heisenberg_xxz_1d_mpo(L, 4.0 / 3, 5.0 / 13, -2.0 / 7).zero_qnumbers()
+    qbonds = [np.array([0])] + [np.zeros(5, dtype=int) for _ in range(L - 1)] + [np.array([0])]
+    psi = ptb.MPS(h.qsite, qbonds, fill="random", rng=rng)
+    psi.orthonormalize(mode="left")
+    ref = psi.to_vector()
+    p1 = copy.deepcopy(psi)
+    ptb.tdvp_singlesite(h, p1, 0.5j, 1, numiter_lanczos=10)
+    ptb.tdvp_singlesite(h, p1, -0.5j, 1, numiter_lanczos=10)
+    assert np.allclose(p1.to_vector(), ref, atol=1e-10)
+    p2 = copy.deepcopy(psi)
+    ptb.tdvp_twosite(h, p2, 0.5j, 1, numiter_lanczos=10, tol_split=1e-10)
+    ptb.tdvp_twosite(h, p2, -0.5j, 1, numiter_lanczos=10, tol_split=1e-10)
+    assert np.allclose(p2.to_vector(), ref, atol=1e-6)
+
+
+def test_dmrg_against_exact_diagonalisation(cuda_lib):
+    """reference test_dmrg.py:5-95 (real start vector, bond growth in the two-site variant)."""
+    import pytenet_b200 as ptb
+    L = 8
+    h = ptb.heisenberg_xxz_1d_mpo(L, 4 / 5, 8 / 3, -2 / 7)
+    hm = h.to_matrix()
+    en_ref, v_ref = np.linalg.eigh(hm)
+    rng = np.random.default_rng(31)
+    psi = ptb.MPS.construct_random(L, h.qsite, 0, max_vdim=32, dtype="real", rng=rng)
+    e0 = ptb.dmrg_singlesite(h, psi, 4)[-1]
+    # lowest state within the Sz = 0 sector
+    sz = np.array([sum(1 if (i >> b) & 1 == 0 else -1 for b in range(L)) for i in range(2 ** L)])
+    sector = np.where(sz == 0)[0]
+    e_sec = np.linalg.eigvalsh(hm[np.ix_(sector, sector)])[0]
+    assert abs(e0 - e_sec) < 1e-12
+    vec = psi.to_vector()
+    assert np.allclose(hm @ vec, e0 * vec, atol=1e-7)
+    rng = np.random.default_rng(32)
+    psi = ptb.MPS.construct_random(L, h.qsite, 2, max_vdim=6, dtype="complex", rng=rng)
+    e2 = ptb.dmrg_twosite(h, psi, 3)[-1]
+    sector = np.where(sz == 2)[0]
+    assert abs(e2 - np.linalg.eigvalsh(hm[np.ix_(sector, sector)])[0]) < 1e-12
+    assert max(psi.bond_dims) > 6          # bonds must have grown
