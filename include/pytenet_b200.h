@@ -63,6 +63,12 @@ int ptb_gemm(int dtype, int trans_a, int trans_b, int conj_b,
              int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c,
              int accumulate, void* stream);
 
+/* Engine selection for every GEMM-shaped step (process-wide; for A/B measurements and tests):
+ *   0 = automatic: warp-specialised TMA/mbarrier kernel when operands meet its 16-byte
+ *       granularity, else the cp.async kernel;  1 = cp.async kernel only;
+ *   2 = warp-specialised kernel required (PTB_ERR_ALIGNMENT if it cannot run). */
+int ptb_set_gemm_engine(int engine);
+
 /* ---------------------------------------------------------------------------
  * apply_local_hamiltonian(a, w, l, r)            pytenet/chain_ops.py:237-279
  *   out[i',s',j'] = sum l[i,k,i'] w[k,s',s,kappa] a[i,s,j] r[j,kappa,j']

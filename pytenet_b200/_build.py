@@ -15,7 +15,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpytenet_b200.so")
 SOURCES = ["chain_ops.cu", "krylov.cu", "probe.cu"]
-HEADERS = ["common.cuh", "gemm_dmma.cuh", os.path.join("..", "..", "include", "pytenet_b200.h")]
+
+
+def _dependencies():
+    """Every file the library is compiled from (all of csrc/ plus the public header)."""
+    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    deps.append(os.path.join(HERE, "..", "include", "pytenet_b200.h"))
+    deps.append(os.path.abspath(__file__))
+    return deps
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -36,8 +43,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _dependencies())
 
 
 def build(force=False, verbose=False):

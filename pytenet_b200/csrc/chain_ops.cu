@@ -15,10 +15,13 @@
 // zgemm.
 #include "../../include/pytenet_b200.h"
 #include "gemm_dmma.cuh"
+#include "gemm_ws.cuh"
 
 using namespace ptb;
 
 namespace {
+
+int g_engine = 0;
 
 inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
@@ -49,6 +52,14 @@ int gemm(int ta, int tb, int cj, int64_t M, int64_t N, int64_t K, const void* A,
     p.batch = (int)batch;
     p.accumulate = acc;
     p.tiles_m = p.tiles_n = 0;
+    if (M == 0 || N == 0 || batch == 0) return PTB_OK;
+    // engine selection: 0 = auto (warp-specialised TMA kernel when it applies), 1 = first-generation
+    // cp.async kernel only, 2 = warp-specialised kernel required
+    if (g_engine != 1 && K > 0) {
+        const int rc = try_launch_ws<CPLX>(ta, tb, cj, p, st);
+        if (rc != 1) return rc;
+        if (g_engine == 2) return PTB_ERR_ALIGNMENT;
+    }
     return launch_gemm<CPLX>(ta, tb, cj, p, st);
 }
 
@@ -163,7 +174,13 @@ int step_left_impl(const void* a, const void* b, const void* w, bool w_cplx, con
 
 extern "C" {
 
-int ptb_version(void) { return 100; }
+int ptb_version(void) { return 101; }
+
+int ptb_set_gemm_engine(int engine) {
+    if (engine < 0 || engine > 2) return PTB_ERR_BAD_ARG;
+    g_engine = engine;
+    return PTB_OK;
+}
 
 const char* ptb_status_string(int status) {
     switch (status) {

@@ -43,7 +43,11 @@ struct WsCfg {
     static constexpr int PAD = CPLX ? 2 : 4;  // elements = 32 bytes
     static constexpr int STAGES = CPLX ? 4 : 6;
     static constexpr int CONSUMER_WARPS = 16;
-    static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+    // registers are granted per group of 4 warps: the producer gets its own warpgroup (one
+    // active warp) and hands most of its registers to the consumers with setmaxnreg
+    static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
+    static constexpr int PRODUCER_REGS = 24;
+    static constexpr int CONSUMER_REGS = 112;  // 16 x 512 extra registers <= the 72 x 128 the producer group releases
     static constexpr int SA = BK * (BM + PAD) * E;  // doubles per stage
     static constexpr int SB = BK * (BN + PAD) * E;
     static constexpr int SMEM_BYTES = STAGES * (SA + SB) * 8 + 2 * STAGES * 8 + 128;
@@ -91,7 +95,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s at 2 GHz
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
     }
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -180,8 +184,10 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
     int stage = 0;
     uint32_t phase = 0;
 
-    if (warp == Cfg::CONSUMER_WARPS) {
-        // ===================== producer warp =====================
+    if (warp >= Cfg::CONSUMER_WARPS) {
+        // ===================== producer warpgroup (one working warp) =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(Cfg::PRODUCER_REGS));
+        if (warp != Cfg::CONSUMER_WARPS) return;
         for (long long t = blockIdx.x; t < total; t += gridDim.x) {
             const int bz = (int)(t / tiles_per_batch);
             const int tile = (int)(t - (long long)bz * tiles_per_batch);
@@ -219,6 +225,7 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
     }
 
     // ===================== consumer warps =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(Cfg::CONSUMER_REGS));
     const int g = lane >> 2, q = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
     const int a_row = wm * Cfg::WTM + g;
@@ -401,6 +408,7 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     // 16-byte granularity of the bulk / tensor copies
     auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
     if (!al16(gp.A) || !al16(gp.B)) return 1;
+    if (CPLX && !al16(gp.C)) return 1;
     if (!CPLX) {
         if ((gp.lda | gp.ldb | gp.sA | gp.sB) & 1) return 1;
         if (!a_kc && (gp.M & 1)) return 1;  // partial mn-rows must stay multiples of 16 bytes

@@ -49,6 +49,14 @@ def run_gemm(lib, cplx, ta, tb, cj, M, N, K, rng, batch=1, accumulate=False, pad
     return rel(got[:, :, :N], want[:, :, :N])
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["engine-auto", "engine-cpasync", "engine-tma"])
+def engine(request, cuda_lib):
+    """Run every GEMM case on both kernel generations (2 = warp-specialised TMA kernel required)."""
+    assert cuda_lib.ptb_set_gemm_engine(request.param) == 0
+    yield request.param
+    cuda_lib.ptb_set_gemm_engine(0)
+
+
 SHAPES = [(1, 1, 1), (3, 5, 7), (8, 8, 4), (17, 9, 33), (128, 64, 8), (129, 65, 9), (130, 200, 77),
           (64, 257, 19), (300, 70, 130), (1, 300, 5), (257, 1, 64), (256, 256, 256)]
 
@@ -56,7 +64,9 @@ SHAPES = [(1, 1, 1), (3, 5, 7), (8, 8, 4), (17, 9, 33), (128, 64, 8), (129, 65, 
 @pytest.mark.parametrize("cplx", [True, False])
 @pytest.mark.parametrize("ta", [0, 1])
 @pytest.mark.parametrize("tb", [0, 1])
-def test_gemm_layouts_and_ragged_shapes(cuda_lib, cplx, ta, tb):
+def test_gemm_layouts_and_ragged_shapes(cuda_lib, engine, cplx, ta, tb):
+    if engine == 2 and not cplx:
+        pytest.skip("odd float64 extents are served by the cp.async kernel")
     rng = np.random.default_rng(100 + 4 * cplx + 2 * ta + tb)
     for (M, N, K) in SHAPES:
         for cj in ([0, 1] if cplx else [0]):
@@ -65,15 +75,22 @@ def test_gemm_layouts_and_ragged_shapes(cuda_lib, cplx, ta, tb):
 
 
 @pytest.mark.parametrize("cplx", [True, False])
-def test_gemm_batched_accumulate_and_leading_dims(cuda_lib, cplx):
+def test_gemm_batched_accumulate_and_leading_dims(cuda_lib, engine, cplx):
     rng = np.random.default_rng(7 + cplx)
     # odd leading dimensions force the 8-byte copy path for float64
-    for pad in [(0, 0, 0), (1, 3, 5), (2, 2, 2)]:
+    pads = [(0, 0, 0), (1, 3, 5), (2, 2, 2)] if (cplx or engine != 2) else []
+    for pad in pads:
         for (ta, tb) in [(0, 0), (1, 0), (0, 1), (1, 1)]:
             e = run_gemm(cuda_lib, cplx, ta, tb, 0, 37, 45, 29, rng, batch=5, accumulate=True, pad=pad)
             assert e < TOL, (cplx, pad, ta, tb, e)
     e = run_gemm(cuda_lib, cplx, 0, 0, 0, 10, 130, 10, rng, batch=300)
     assert e < TOL
+    # float64 with even extents is eligible for the TMA kernel in every layout
+    for (ta, tb) in [(0, 0), (1, 0), (0, 1), (1, 1)]:
+        e = run_gemm(cuda_lib, cplx, ta, tb, 0, 70, 36, 50, rng, batch=3, accumulate=True, pad=(2, 4, 6))
+        assert e < TOL, (cplx, ta, tb, e)
+        e = run_gemm(cuda_lib, cplx, ta, tb, 0, 200, 300, 40, rng)
+        assert e < TOL, (cplx, ta, tb, e)
 
 
 def test_gemm_exact_zeros_preserved(cuda_lib):
@@ -88,7 +105,7 @@ def test_gemm_exact_zeros_preserved(cuda_lib):
     assert rel(c, a @ b) < TOL
 
 
-def test_gemm_large_against_torch(cuda_lib):
+def test_gemm_large_against_torch(cuda_lib, engine):
     """Full-size sanity (size-independent check): 2048 x 1280 x 1024 complex, T/N layout, vs torch fp64."""
     from pytenet_b200 import _device as dev
     g = torch.Generator(device="cuda").manual_seed(1)

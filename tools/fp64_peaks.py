@@ -65,9 +65,10 @@ def main():
         ms = time_ms(lambda: lib.ptb_probe_fp64_pipe(use, blocks, 4000, out.data_ptr(), ctypes.byref(fl), st))
         res[name] = fl.value / ms / 1e9
 
-    # this repository's engine on the matvec shapes (D, d, chi)
+    # this repository's engines on the matvec shapes (D, d, chi): 1 = cp.async kernel, 2 = TMA kernel
     shapes = []
-    for (D, d, chi) in [(1024, 4, 5), (2048, 2, 5), (2048, 4, 5)]:
+    for eng, (D, d, chi) in [(e, s) for e in (1, 2) for s in [(1024, 4, 5), (2048, 2, 5), (2048, 4, 5)]]:
+        assert lib.ptb_set_gemm_engine(eng) == 0
         a = torch.randn(D * d, D, dtype=torch.complex128, device="cuda")
         r = torch.randn(D, chi * D, dtype=torch.complex128, device="cuda")
         t1 = torch.empty(D * d, chi * D, dtype=torch.complex128, device="cuda")
@@ -79,11 +80,20 @@ def main():
         f = 8.0 * D * d * D * chi * D
         cub1 = time_ms(lambda: torch.matmul(a, r, out=t1), warm=1, reps=3)
         cub3 = time_ms(lambda: torch.matmul(l.T, t2, out=o), warm=1, reps=3)
-        shapes.append({"D": D, "d": d, "chi": chi, "step1_NN_tflops": f / ms1 / 1e9, "step3_TN_tflops": f / ms3 / 1e9,
+        shapes.append({"engine": eng, "D": D, "d": d, "chi": chi, "step1_NN_tflops": f / ms1 / 1e9, "step3_TN_tflops": f / ms3 / 1e9,
                        "cublas_step1_tflops": f / cub1 / 1e9, "cublas_step3_tflops": f / cub3 / 1e9,
                        "step1_ms": ms1, "step3_ms": ms3})
         del a, r, t1, l, t2, o
     res["engine"] = shapes
+    for eng in (1, 2):
+        lib.ptb_set_gemm_engine(eng)
+        n = 8192
+        a = torch.randn(n, n, dtype=torch.float64, device="cuda"); b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        c = torch.empty(n, n, dtype=torch.float64, device="cuda")
+        ms = time_ms(lambda: dev.gemm(a, b, out=c), warm=1, reps=3)
+        res[f"engine{eng}_dgemm_8192_tflops"] = 2 * n ** 3 / ms / 1e9
+        del a, b, c
+    lib.ptb_set_gemm_engine(0)
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device="cuda"); b = torch.randn(n, n, dtype=torch.float64, device="cuda")
     c = torch.empty(n, n, dtype=torch.float64, device="cuda")
