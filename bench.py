@@ -311,7 +311,7 @@ def run_ours(args):
         except Exception:
             prof_traffic = None
     roofline = {
-        "bound": "tensor", "kernel": "gemm_dmma_kernel<complex128> (step 1 a.r NN / step 3 l^T.t2 TN)",
+        "bound": "tensor", "kernel": "gemm_ws_kernel<complex128> (TMA/mbarrier warp-specialised DMMA GEMM; step 1 a.r / step 3 l^T.t2)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": prof_traffic,
         "peak_source": "measured live in this run: max(cuBLAS ZGEMM 4096^3 via torch.matmul, register-resident "
                        "DMMA.8x8x4 probe); MEASURED_PEAKS.json has no FP64 entry",
