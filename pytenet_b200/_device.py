@@ -136,3 +136,17 @@ def gemm(a, b, trans_a=False, trans_b=False, conj_b=False, out=None):
                       1, 0, 0, 0, 0, stream_ptr(a.device))
     _lib.check(st, "ptb_gemm")
     return out
+
+
+def gemm_strided(cplx, trans_a, trans_b, conj_b, m, n, k, a, lda, b, ldb, c, ldc,
+                 batch=1, stride_a=0, stride_b=0, stride_c=0, accumulate=False):
+    """Thin call-through to ptb_gemm on tensors that are already dense device buffers of the
+    right dtype (float64 when `cplx` is False -- a complex tensor may be passed as its float64
+    view for the real-W trick -- or complex128).  Leading dimensions / strides in elements."""
+    lib = _lib.load()
+    st = lib.ptb_gemm(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, int(trans_a), int(trans_b), int(conj_b),
+                      int(m), int(n), int(k), a.data_ptr(), int(lda), b.data_ptr(), int(ldb), c.data_ptr(), int(ldc),
+                      int(batch), int(stride_a), int(stride_b), int(stride_c), int(bool(accumulate)),
+                      stream_ptr(c.device))
+    _lib.check(st, "ptb_gemm")
+    return c
