@@ -199,6 +199,42 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def sharded_block(torch, dist, device, world, rank, D=1024, d=2, cl=562, cr=501, reps=3):
+    """One effective-H matvec at the centre-site shape of the 32-orbital molecular MPO
+    (w (562,2,2,501) real, 16.8 % dense; a (1024,2,1024)), MPO bond split over all ranks:
+    fixed total work, so ms_per_matvec across N = 1, 2, 4, 8 is the strong-scaling curve."""
+    from pytenet_b200.sharded import ShardedEffectiveHamiltonian
+    heff = ShardedEffectiveHamiltonian.synthetic(D, d, D, cl, cr, density=0.168, seed=1, device=device)
+    x = torch.randn(D, d, D, dtype=torch.complex128, device=device) / np.sqrt(D * d * D)
+    for _ in range(2):
+        heff.matvec(x)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        heff.matvec(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    fa = 8.0 * (D * d * D * cr * D + cl * d * d * cr * D * D + D * D * cl * d * D)
+    gather, red = heff.exchange_bytes_per_rank()
+    blk = {"workload": f"molecular-shape heff matvec: a ({D},{d},{D}), w ({cl},{d},{d},{cr}) real 16.8% dense, "
+                       f"l ({D},{cl},{D}), r ({D},{cr},{D}); MPO bonds split over {world} rank(s)",
+           "scaling": "strong", "n_gpus": world, "ms_per_matvec": ms, "gflops_alg": fa / ms / 1e6,
+           "flops_alg": fa, "flops_exec_per_rank": heff.flops_per_rank(), "exchange": heff.exchange,
+           "allgather_bytes_per_rank": gather, "allreduce_bytes_per_rank": red}
+    del heff, x
+    torch.cuda.empty_cache()
+    return blk
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -267,6 +303,15 @@ def run_ours(args):
     h2d = a_h.nbytes + w_h.nbytes + l_h.nbytes + r_h.nbytes
     d2h = res.nbytes
     F = f_alg(D, d, chi)
+
+    # ---- MPO-bond-sharded matvec (BASELINE config 4 shape), STRONG scaling over the same N ranks ----
+    sharded = None
+    if os.environ.get("PTB_BENCH_SKIP_SHARDED") != "1":
+        del a, l, r, out, res
+        torch.cuda.empty_cache()
+        sharded = sharded_block(torch, dist, device, world, rank)
+        a = torch.from_numpy(a_h).to(device); l = torch.from_numpy(l_h).to(device); r = torch.from_numpy(r_h).to(device)
+        out = torch.empty((D, d, D), dtype=torch.complex128, device=device)
 
     if rank != 0:
         if world > 1:
@@ -337,6 +382,7 @@ def run_ours(args):
         "gpu_launches": 3 * steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "sharded": sharded,
     }
     print(json.dumps(line))
     if world > 1:

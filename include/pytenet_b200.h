@@ -63,6 +63,16 @@ int ptb_gemm(int dtype, int trans_a, int trans_b, int conj_b,
              int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c,
              int accumulate, void* stream);
 
+/* Fused GEMM + all-gather: C = op(A) op(B) is written to n_dst (1..8) output buffers of identical
+ * layout in the kernel's epilogue.  c_list is a HOST array of device pointers; entries beyond the
+ * first are typically peer-mapped buffers of the other GPUs of the box (CUDA IPC / symmetric
+ * memory), so the tiles travel over NVLink while the tensor pipe keeps working.  Used by the
+ * MPO-bond-sharded matvec (step 1 on each rank's kappa range lands in every rank's gathered t1).
+ * Needs 16-byte operand granularity (always true for complex128). */
+int ptb_gemm_multicast(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k,
+                       const void* a, int64_t lda, const void* b, int64_t ldb, void* const* c_list, int n_dst,
+                       int64_t ldc, void* stream);
+
 /* Engine selection for every GEMM-shaped step (process-wide; for A/B measurements and tests):
  *   0 = automatic: warp-specialised TMA/mbarrier kernel when operands meet its 16-byte
  *       granularity, else the cp.async kernel;  1 = cp.async kernel only;

@@ -212,6 +212,36 @@ int ptb_gemm(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t
     return PTB_ERR_BAD_DTYPE;
 }
 
+int ptb_gemm_multicast(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k, const void* a,
+                       int64_t lda, const void* b, int64_t ldb, void* const* c_list, int n_dst, int64_t ldc,
+                       void* stream) {
+    if (!a || !b || !c_list || n_dst < 1 || n_dst > 8) return PTB_ERR_BAD_ARG;
+    if (m <= 0 || n <= 0 || k <= 0 || !fits_int({m, n, k})) return PTB_ERR_BAD_ARG;
+    for (int i = 0; i < n_dst; i++)
+        if (!c_list[i]) return PTB_ERR_BAD_ARG;
+    GemmParams p;
+    p.A = static_cast<const double*>(a);
+    p.B = static_cast<const double*>(b);
+    p.C = static_cast<double*>(c_list[0]);
+    p.M = (int)m; p.N = (int)n; p.K = (int)k;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.sA = p.sB = p.sC = 0;
+    p.batch = 1;
+    p.accumulate = 0;
+    p.tiles_m = p.tiles_n = 0;
+    double* extra[7];
+    for (int i = 1; i < n_dst; i++) extra[i - 1] = static_cast<double*>(c_list[i]);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if (dtype == PTB_COMPLEX128)
+        rc = try_launch_ws<true>(trans_a, trans_b, conj_b, p, st, n_dst - 1, extra);
+    else if (dtype == PTB_REAL64)
+        rc = try_launch_ws<false>(trans_a, trans_b, 0, p, st, n_dst - 1, extra);
+    else
+        return PTB_ERR_BAD_DTYPE;
+    return rc == 1 ? PTB_ERR_ALIGNMENT : rc;   // the fused kernel exists only on the TMA engine
+}
+
 size_t ptb_apply_local_hamiltonian_workspace_bytes(int dtype, int64_t Dl, int64_t d_in, int64_t Dr, int64_t chi_l,
                                                    int64_t chi_r, int64_t d_out, int64_t Dlp, int64_t Drp) {
     (void)Dr; (void)Dlp;

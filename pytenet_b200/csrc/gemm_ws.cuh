@@ -64,6 +64,10 @@ struct WsParams {
     int accumulate;
     int tiles_m, tiles_n;
     int batched_a, batched_b;  // 0 when the batch stride is 0 (operand shared by all batches)
+    // fused all-gather: the epilogue also stores every C tile to `n_extra` further base pointers of
+    // identical layout -- peer-mapped buffers of the other GPUs, written over NVLink
+    int n_extra;
+    double* Cx[7];
 };
 
 // ---- mbarrier / TMA primitives ---------------------------------------------------------
@@ -298,37 +302,40 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
 
-        // epilogue (overlaps the producer's prefetch of the next tile)
-        double* __restrict__ Cg = p.C + (int64_t)bz * p.sC * E;
+        // epilogue (overlaps the producer's prefetch of the next tile); with n_extra > 0 the tile is
+        // also written to the peer GPUs' buffers (compute + all-gather in one kernel)
+        for (int dsti = 0; dsti <= p.n_extra; dsti++) {
+            double* __restrict__ Cg = (dsti == 0 ? p.C : p.Cx[dsti - 1]) + (int64_t)bz * p.sC * E;
 #pragma unroll
-        for (int i = 0; i < MT; i++) {
-            const int row = m0 + wm * Cfg::WTM + i * 8 + g;
-            if (row >= p.M) continue;
-            double* crow = Cg + (int64_t)row * p.ldc * E;
+            for (int i = 0; i < MT; i++) {
+                const int row = m0 + wm * Cfg::WTM + i * 8 + g;
+                if (row >= p.M) continue;
+                double* crow = Cg + (int64_t)row * p.ldc * E;
 #pragma unroll
-            for (int j = 0; j < NT; j++) {
-                const int col = n0 + wn * Cfg::WTN + j * 8 + 2 * q;
-                if constexpr (CPLX) {
+                for (int j = 0; j < NT; j++) {
+                    const int col = n0 + wn * Cfg::WTN + j * 8 + 2 * q;
+                    if constexpr (CPLX) {
 #pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        if (col + e < p.N) {
-                            double2* dst = reinterpret_cast<double2*>(crow + (int64_t)(col + e) * 2);
-                            double2 v = make_double2(acc[i][j][e], acc[i][j][2 + e]);
-                            if (p.accumulate) {
-                                const double2 old = *dst;
-                                v.x += old.x;
-                                v.y += old.y;
+                        for (int e = 0; e < 2; e++) {
+                            if (col + e < p.N) {
+                                double2* dst = reinterpret_cast<double2*>(crow + (int64_t)(col + e) * 2);
+                                double2 v = make_double2(acc[i][j][e], acc[i][j][2 + e]);
+                                if (p.accumulate) {
+                                    const double2 old = *dst;
+                                    v.x += old.x;
+                                    v.y += old.y;
+                                }
+                                *dst = v;
                             }
-                            *dst = v;
                         }
-                    }
-                } else {
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        if (col + e < p.N) {
-                            double v = acc[i][j][e];
-                            if (p.accumulate) v += crow[col + e];
-                            crow[col + e] = v;
+                        for (int e = 0; e < 2; e++) {
+                            if (col + e < p.N) {
+                                double v = acc[i][j][e];
+                                if (p.accumulate) v += crow[col + e];
+                                crow[col + e] = v;
+                            }
                         }
                     }
                 }
@@ -401,7 +408,8 @@ static int launch_ws_inst(const WsParams& p, const CUtensorMap& ta, const CUtens
 // Returns PTB_OK when launched, 1 when the fast path does not apply (caller falls back to the
 // first-generation kernel), or an error status.
 template <bool CPLX>
-static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp, cudaStream_t stream) {
+static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp, cudaStream_t stream,
+                         int n_extra = 0, double* const* extra = nullptr) {
     using Cfg = WsCfg<CPLX>;
     constexpr int E = Cfg::E;
     const bool a_kc = (transA == 0), b_kc = (transB != 0);
@@ -426,6 +434,16 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     p.tiles_n = (gp.N + Cfg::BN - 1) / Cfg::BN;
     p.batched_a = (gp.sA != 0 && gp.batch > 1) ? 1 : 0;
     p.batched_b = (gp.sB != 0 && gp.batch > 1) ? 1 : 0;
+    p.n_extra = 0;
+    for (int i = 0; i < 7; i++) p.Cx[i] = nullptr;
+    if (n_extra > 0) {
+        if (n_extra > 7 || gp.accumulate || !extra) return PTB_ERR_BAD_ARG;
+        for (int i = 0; i < n_extra; i++) {
+            if (!extra[i] || !al16(extra[i])) return PTB_ERR_ALIGNMENT;
+            p.Cx[i] = extra[i];
+        }
+        p.n_extra = n_extra;
+    }
     CUtensorMap ta, tb;
     memset(&ta, 0, sizeof(ta));
     memset(&tb, 0, sizeof(tb));

@@ -55,6 +55,22 @@ class _CudaOps:
         return dev.gemm(a2d, r2d, out=out)
 
     @staticmethod
+    def step1_multicast(a2d, r2d, dst_ptrs):
+        """Fused GEMM + all-gather: the product is stored to every pointer of `dst_ptrs` (this rank's
+        slot in each rank's gathered buffer; peers are reached over NVLink) by the kernel's epilogue."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        m, k = a2d.shape
+        n = r2d.shape[1]
+        arr = (ctypes.c_void_p * len(dst_ptrs))(*dst_ptrs)
+        cplx = a2d.dtype.is_complex
+        st = lib.ptb_gemm_multicast(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, 0, 0, 0, m, n, k,
+                                    a2d.data_ptr(), k, r2d.data_ptr(), n, arr, len(dst_ptrs), n,
+                                    dev.stream_ptr(a2d.device))
+        _lib.check(st, "ptb_gemm_multicast")
+
+    @staticmethod
     def wapply(wblk, tin, tout, accumulate):
         """tout[i] (+)= wblk @ tin[i]  for all i.  wblk (R_out, R_in) real or complex;
         tin (B, R_in, Drp), tout (B, R_out, Drp) complex128 or float64, dense."""
@@ -85,7 +101,13 @@ class ShardedEffectiveHamiltonian:
         ptn.eigh_krylov(lambda x: heff.matvec(x.reshape(shape)).reshape(-1), a.reshape(-1), k, 1)
     """
 
-    def __init__(self, w_blocks, l_shard, r_shard, dims, group=None, ops=None):
+    def __init__(self, w_blocks, l_shard, r_shard, dims, group=None, ops=None, exchange="auto"):
+        # exchange: "fused"  = step-1 GEMM writes its tiles straight into every rank's gathered buffer
+        #                      (peer memory over NVLink, torch symmetric memory for the mapping);
+        #           "nccl"   = step-1 GEMM followed by an NCCL all-gather;
+        #           "auto"   = fused on CUDA with more than one rank when peer mapping is available
+        self.exchange = exchange
+        self._symm = None
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -97,7 +119,7 @@ class ShardedEffectiveHamiltonian:
         self._t1 = self._gathered = self._t2 = None
 
     @classmethod
-    def from_full(cls, w, l, r, group=None, ops=None, device=None):
+    def from_full(cls, w, l, r, group=None, ops=None, device=None, exchange="auto"):
         """Slice the full tensors (same on every rank) into this rank's shards."""
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -132,10 +154,12 @@ class ShardedEffectiveHamiltonian:
             if p1 > p0:
                 blk[:, :, :, :p1 - p0] = w_t[k0:k1, :, :, p0:p1]
             w_blocks.append(blk.reshape(kg * dout, din * P).contiguous())
-        return cls(w_blocks, l_shard, r_pad, (Dl, din, Dr, dout, Dlp, Drp, kg, P), group=group, ops=ops)
+        return cls(w_blocks, l_shard, r_pad, (Dl, din, Dr, dout, Dlp, Drp, kg, P), group=group, ops=ops,
+                   exchange=exchange)
 
     @classmethod
-    def synthetic(cls, Dl, d, Dr, cl, cr, density=0.168, seed=0, device=None, group=None, dtype=torch.complex128):
+    def synthetic(cls, Dl, d, Dr, cl, cr, density=0.168, seed=0, device=None, group=None, dtype=torch.complex128,
+                  exchange="auto"):
         """Random shards of the given global shape generated directly on this rank (benchmark input:
         no rank ever materialises the full environments).  `density` is the fraction of non-zero
         MPO-tensor entries (16.8 % at the centre of the 32-orbital molecular MPO)."""
@@ -161,14 +185,43 @@ class ShardedEffectiveHamiltonian:
             if p1 < P:
                 blk[:, :, :, max(p1, 0):] = 0
             w_blocks.append(blk.reshape(kg * d, d * P).contiguous())
-        return cls(w_blocks, l_shard, r_shard, (Dl, d, Dr, d, Dl, Dr, kg, P), group=group)
+        return cls(w_blocks, l_shard, r_shard, (Dl, d, Dr, d, Dl, Dr, kg, P), group=group, exchange=exchange)
 
     def _buffers(self, like):
         n1 = (self.Dl, self.d_in * self.P, self.Drp)
         if self._t1 is None or self._t1.dtype != like.dtype:
-            self._t1 = torch.empty(n1, dtype=like.dtype, device=like.device)
-            self._gathered = torch.empty((self.world,) + n1, dtype=like.dtype, device=like.device)
             self._t2 = torch.empty((self.Dl, self.kg * self.d_out, self.Drp), dtype=like.dtype, device=like.device)
+            want_fused = (self.exchange in ("auto", "fused") and self.world > 1 and like.is_cuda
+                          and hasattr(self.ops, "step1_multicast"))
+            if want_fused:
+                try:
+                    import torch.distributed._symmetric_memory as symm_mem
+                    grp = self.group if self.group is not None else dist.group.WORLD
+                    # allocated as float64 (complex128 = interleaved pairs) so the peer mapping does
+                    # not depend on complex-dtype support of the symmetric-memory allocator
+                    if like.dtype.is_complex:
+                        raw = symm_mem.empty((self.world,) + n1 + (2,), dtype=torch.float64, device=like.device)
+                        self._gathered = torch.view_as_complex(raw)
+                    else:
+                        raw = symm_mem.empty((self.world,) + n1, dtype=like.dtype, device=like.device)
+                        self._gathered = raw
+                    self._symm = symm_mem.rendezvous(raw, group=grp)
+                    slot = int(np.prod(n1)) * like.element_size()
+                    self._dst_ptrs = [int(self._symm.buffer_ptrs[p]) + self.rank * slot for p in range(self.world)]
+                    # own slot first: it is the kernel's primary output
+                    self._dst_ptrs = [self._dst_ptrs[self.rank]] + [q for i, q in enumerate(self._dst_ptrs)
+                                                                    if i != self.rank]
+                    self._t1 = self._gathered[self.rank]
+                    self.exchange = "fused"
+                except Exception as exc:            # peer mapping unavailable: fall back to the NCCL exchange
+                    if self.exchange == "fused":
+                        raise
+                    self._symm = None
+                    self._exchange_note = f"symmetric memory unavailable ({type(exc).__name__}: {exc})"
+            if self._symm is None:
+                self.exchange = "nccl" if self.world > 1 else "local"
+                self._t1 = torch.empty(n1, dtype=like.dtype, device=like.device)
+                self._gathered = torch.empty((self.world,) + n1, dtype=like.dtype, device=like.device)
         return self._t1, self._gathered, self._t2
 
     def matvec(self, a):
@@ -177,14 +230,23 @@ class ShardedEffectiveHamiltonian:
         a = a.to(self.l_shard.dtype) if a.dtype != self.l_shard.dtype else a
         a = a.contiguous()
         t1, gathered, t2 = self._buffers(a)
-        # step 1 on this rank's kappa range:  t1[(i,s),(kappa_loc,j')] = a r_g
-        self.ops.step1(a.reshape(self.Dl * self.d_in, self.Dr), self.r_shard.reshape(self.Dr, self.P * self.Drp),
-                       t1.reshape(self.Dl * self.d_in, self.P * self.Drp))
-        # exchange: every rank receives all kappa ranges of t1
-        if self.world > 1:
-            dist.all_gather_into_tensor(_flat_real(gathered), _flat_real(t1), group=self.group)
+        a2d = a.reshape(self.Dl * self.d_in, self.Dr)
+        r2d = self.r_shard.reshape(self.Dr, self.P * self.Drp)
+        if self._symm is not None:
+            # step 1 fused with the exchange: tiles of t1_g land in every rank's gathered buffer over
+            # NVLink from the GEMM epilogue; the barrier makes all ranks' contributions visible.
+            # (The all-reduce that ended the previous matvec already ordered this overwrite after every
+            # rank's last read of its gathered buffer.)
+            self.ops.step1_multicast(a2d, r2d, self._dst_ptrs)
+            self._symm.barrier(channel=0)
         else:
-            gathered = t1.reshape((1,) + tuple(t1.shape))
+            # step 1 on this rank's kappa range:  t1[(i,s),(kappa_loc,j')] = a r_g
+            self.ops.step1(a2d, r2d, t1.reshape(self.Dl * self.d_in, self.P * self.Drp))
+            # exchange: every rank receives all kappa ranges of t1
+            if self.world > 1:
+                dist.all_gather_into_tensor(_flat_real(gathered), _flat_real(t1), group=self.group)
+            else:
+                gathered = t1.reshape((1,) + tuple(t1.shape))
         # step 2 on this rank's k range, accumulating over the source ranges
         for gp in range(self.world):
             # gathered[gp] is [i, (s, kappa_loc), j'] because t1 rows are (i, s) and columns (kappa_loc, j')
