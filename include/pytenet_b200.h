@@ -63,6 +63,15 @@ int ptb_gemm(int dtype, int trans_a, int trans_b, int conj_b,
              int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c,
              int accumulate, void* stream);
 
+/* ptb_gemm with split-K: when the output has too few tiles to fill the 148 SMs, every tile is
+ * computed by `split_k` work units over disjoint k ranges (partials in `workspace`, at least
+ * batch*split_k*m*n elements) and summed in fixed order by a second kernel (deterministic).
+ * split_k = 0 chooses the factor automatically (1..8), 1 disables splitting. */
+int ptb_gemm_splitk(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k,
+                    const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc,
+                    int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c, int accumulate,
+                    int split_k, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fused GEMM + all-gather: C = op(A) op(B) is written to n_dst (1..8) output buffers of identical
  * layout in the kernel's epilogue.  c_list is a HOST array of device pointers; entries beyond the
  * first are typically peer-mapped buffers of the other GPUs of the box (CUDA IPC / symmetric

@@ -37,10 +37,11 @@ inline bool fits_int(std::initializer_list<int64_t> v) {
     return true;
 }
 
+// split_k: 1 = never split; 0 = choose automatically when `part_ws` is given; >1 = forced
 template <bool CPLX>
 int gemm(int ta, int tb, int cj, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
          int64_t ldb, void* C, int64_t ldc, int64_t batch, int64_t sA, int64_t sB, int64_t sC, int acc,
-         cudaStream_t st) {
+         cudaStream_t st, int split_k = 1, void* part_ws = nullptr, size_t part_ws_bytes = 0) {
     if (!fits_int({M, N, K, batch})) return PTB_ERR_TOO_LARGE;
     GemmParams p;
     p.A = static_cast<const double*>(A);
@@ -56,7 +57,7 @@ int gemm(int ta, int tb, int cj, int64_t M, int64_t N, int64_t K, const void* A,
     // engine selection: 0 = auto (warp-specialised TMA kernel when it applies), 1 = first-generation
     // cp.async kernel only, 2 = warp-specialised kernel required
     if (g_engine != 1 && K > 0) {
-        const int rc = try_launch_ws<CPLX>(ta, tb, cj, p, st);
+        const int rc = try_launch_ws<CPLX>(ta, tb, cj, p, st, 0, nullptr, split_k, part_ws, part_ws_bytes);
         if (rc != 1) return rc;
         if (g_engine == 2) return PTB_ERR_ALIGNMENT;
     }
@@ -77,9 +78,13 @@ int apply_w(bool w_cplx, int trans_w, int64_t rows_out, int64_t rows_in, int64_t
                       rows_in * Drp, rows_out * Drp, 0, st);
 }
 
-size_t two_buffers(int dtype, int64_t n1, int64_t n2) {
+// Workspace = intermediate 1 | intermediate 2 | split-K partial tiles of the last GEMM (up to
+// MAX_SPLIT copies of the output; used when the output has too few tiles to fill 148 SMs).
+constexpr int MAX_SPLIT = 8;
+
+size_t two_buffers(int dtype, int64_t n1, int64_t n2, int64_t nout = 0) {
     const size_t es = dtype == PTB_COMPLEX128 ? 16 : 8;
-    return align16((size_t)n1 * es) + align16((size_t)n2 * es);
+    return align16((size_t)n1 * es) + align16((size_t)n2 * es) + align16((size_t)nout * es * MAX_SPLIT);
 }
 
 template <bool CPLX>
@@ -95,6 +100,8 @@ int apply_local_hamiltonian_impl(const void* a, const void* w, bool w_cplx, cons
     if (reinterpret_cast<uintptr_t>(ws) % 16) return PTB_ERR_ALIGNMENT;
     char* t1 = static_cast<char*>(ws);
     char* t2 = t1 + align16(n1 * es);
+    char* part = t2 + align16(n2 * es);
+    const size_t part_bytes = ws_bytes - (size_t)(part - t1);
     int rc;
     // (1) t1[(i,s),(kappa,j')] = a[(i,s),j] r[j,(kappa,j')]                 chain_ops.py:273
     rc = gemm<CPLX>(0, 0, 0, Dl * d, cr * Drp, Dr, a, Dr, r, cr * Drp, t1, cr * Drp, 1, 0, 0, 0, 0, st);
@@ -103,7 +110,8 @@ int apply_local_hamiltonian_impl(const void* a, const void* w, bool w_cplx, cons
     rc = apply_w<CPLX>(w_cplx, 0, cl * dout, d * cr, d * cr, Drp, w, t1, t2, Dl, st);
     if (rc) return rc;
     // (3) out[i',(s',j')] = l[(i,k),i']^T t2[(i,k),(s',j')]                 chain_ops.py:278
-    return gemm<CPLX>(1, 0, 0, Dlp, dout * Drp, Dl * cl, l, Dlp, t2, dout * Drp, out, dout * Drp, 1, 0, 0, 0, 0, st);
+    return gemm<CPLX>(1, 0, 0, Dlp, dout * Drp, Dl * cl, l, Dlp, t2, dout * Drp, out, dout * Drp, 1, 0, 0, 0, 0, st,
+                      0, part, part_bytes);
 }
 
 template <bool CPLX>
@@ -119,7 +127,10 @@ int bond_impl(const void* c, const void* l, const void* r, void* out, int64_t Dl
     int rc = gemm<CPLX>(0, 0, 0, Dl, chi * Drp, Dr, c, Dr, r, chi * Drp, ws, chi * Drp, 1, 0, 0, 0, 0, st);
     if (rc) return rc;
     // (2) out[i',j'] = l[(i,k),i']^T t[(i,k),j']                            chain_ops.py:316
-    return gemm<CPLX>(1, 0, 0, Dlp, Drp, Dl * chi, l, Dlp, ws, Drp, out, Drp, 1, 0, 0, 0, 0, st);
+    char* part = static_cast<char*>(ws) + align16(n1 * es);
+    const size_t part_bytes = ws_bytes - align16(n1 * es);
+    return gemm<CPLX>(1, 0, 0, Dlp, Drp, Dl * chi, l, Dlp, ws, Drp, out, Drp, 1, 0, 0, 0, 0, st, 0, part,
+                      part_bytes);
 }
 
 template <bool CPLX>
@@ -142,8 +153,9 @@ int step_right_impl(const void* a, const void* b, const void* w, bool w_cplx, co
     rc = apply_w<CPLX>(w_cplx, 0, cl * dout, d * cr, d * cr, Drp, w, t1, t2, Dl, st);
     if (rc) return rc;
     // (3) r_next[(i,k),i'] = t2[(i,k),(s',j')] conj(b[i',(s',j')])^T         chain_ops.py:56
+    char* part = t2 + align16(n2 * es);
     return gemm<CPLX>(0, 1, 1, Dl * cl, Dlp, dout * Drp, t2, dout * Drp, b, dout * Drp, r_next, Dlp, 1, 0, 0, 0, 0,
-                      st);
+                      st, 0, part, ws_bytes - (size_t)(part - t1));
 }
 
 template <bool CPLX>
@@ -167,7 +179,9 @@ int step_left_impl(const void* a, const void* b, const void* w, bool w_cplx, con
     rc = apply_w<CPLX>(w_cplx, 1, d * cr, cl * dout, d * cr, Drp, w, t, t2, Dl, st);
     if (rc) return rc;
     // (3) l_next[j,(kappa,j')] = a[(i,s),j]^T t2[(i,s),(kappa,j')]           chain_ops.py:98
-    return gemm<CPLX>(1, 0, 0, Dr, cr * Drp, Dl * d, a, Dr, t2, cr * Drp, l_next, cr * Drp, 1, 0, 0, 0, 0, st);
+    char* part = t2 + align16(n2 * es);
+    return gemm<CPLX>(1, 0, 0, Dr, cr * Drp, Dl * d, a, Dr, t2, cr * Drp, l_next, cr * Drp, 1, 0, 0, 0, 0, st, 0,
+                      part, ws_bytes - (size_t)(part - t));
 }
 
 }  // namespace
@@ -212,6 +226,22 @@ int ptb_gemm(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t
     return PTB_ERR_BAD_DTYPE;
 }
 
+int ptb_gemm_splitk(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k, const void* a,
+                    int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t batch, int64_t stride_a,
+                    int64_t stride_b, int64_t stride_c, int accumulate, int split_k, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    if (!a || !b || !c) return PTB_ERR_BAD_ARG;
+    if (m < 0 || n < 0 || k < 0 || batch < 0 || split_k < 0 || split_k > 64) return PTB_ERR_BAD_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == PTB_COMPLEX128)
+        return gemm<true>(trans_a, trans_b, conj_b, m, n, k, a, lda, b, ldb, c, ldc, batch, stride_a, stride_b,
+                          stride_c, accumulate, st, split_k, workspace, workspace_bytes);
+    if (dtype == PTB_REAL64)
+        return gemm<false>(trans_a, trans_b, 0, m, n, k, a, lda, b, ldb, c, ldc, batch, stride_a, stride_b,
+                           stride_c, accumulate, st, split_k, workspace, workspace_bytes);
+    return PTB_ERR_BAD_DTYPE;
+}
+
 int ptb_gemm_multicast(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k, const void* a,
                        int64_t lda, const void* b, int64_t ldb, void* const* c_list, int n_dst, int64_t ldc,
                        void* stream) {
@@ -244,8 +274,8 @@ int ptb_gemm_multicast(int dtype, int trans_a, int trans_b, int conj_b, int64_t 
 
 size_t ptb_apply_local_hamiltonian_workspace_bytes(int dtype, int64_t Dl, int64_t d_in, int64_t Dr, int64_t chi_l,
                                                    int64_t chi_r, int64_t d_out, int64_t Dlp, int64_t Drp) {
-    (void)Dr; (void)Dlp;
-    return two_buffers(dtype, Dl * d_in * chi_r * Drp, Dl * chi_l * d_out * Drp);
+    (void)Dr;
+    return two_buffers(dtype, Dl * d_in * chi_r * Drp, Dl * chi_l * d_out * Drp, Dlp * d_out * Drp);
 }
 
 int ptb_apply_local_hamiltonian_z(const void* a, const void* w, int w_is_complex, const void* l, const void* r,
@@ -267,8 +297,8 @@ int ptb_apply_local_hamiltonian_d(const void* a, const void* w, const void* l, c
 
 size_t ptb_apply_local_bond_contraction_workspace_bytes(int dtype, int64_t Dl, int64_t Dr, int64_t chi,
                                                         int64_t Dlp, int64_t Drp) {
-    (void)Dr; (void)Dlp;
-    return two_buffers(dtype, Dl * chi * Drp, 0);
+    (void)Dr;
+    return two_buffers(dtype, Dl * chi * Drp, 0, Dlp * Drp);
 }
 
 int ptb_apply_local_bond_contraction_z(const void* c, const void* l, const void* r, void* out, int64_t Dl,
@@ -287,8 +317,9 @@ int ptb_apply_local_bond_contraction_d(const void* c, const void* l, const void*
 
 size_t ptb_env_step_workspace_bytes(int dtype, int64_t Dl, int64_t d_in, int64_t Dr, int64_t chi_l, int64_t chi_r,
                                     int64_t d_out, int64_t Dlp, int64_t Drp) {
-    (void)Dr; (void)Dlp;
-    return two_buffers(dtype, Dl * d_in * chi_r * Drp, Dl * chi_l * d_out * Drp);
+    // the final GEMM writes (Dr, chi_r, Drp) for step_left and (Dl, chi_l, Dlp) for step_right
+    const int64_t o1 = Dr * chi_r * Drp, o2 = Dl * chi_l * Dlp;
+    return two_buffers(dtype, Dl * d_in * chi_r * Drp, Dl * chi_l * d_out * Drp, o1 > o2 ? o1 : o2);
 }
 
 int ptb_env_step_left_z(const void* a, const void* b, const void* w, int w_is_complex, const void* l, void* l_next,

@@ -68,6 +68,10 @@ struct WsParams {
     // identical layout -- peer-mapped buffers of the other GPUs, written over NVLink
     int n_extra;
     double* Cx[7];
+    // split-K: every output tile is computed by `split_k` work units over disjoint k ranges that write
+    // partial tiles to Cpart ([batch][split][M][N], dense); a second kernel sums them in fixed order
+    int split_k;
+    double* Cpart;
 };
 
 // ---- mbarrier / TMA primitives ---------------------------------------------------------
@@ -179,9 +183,10 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
     }
     __syncthreads();
 
-    const int KT = (p.K + BK - 1) / BK;
+    const int KT_all = (p.K + BK - 1) / BK;
     const int tiles_per_batch = p.tiles_m * p.tiles_n;
-    const long long total = (long long)tiles_per_batch * p.batch;
+    const int SK = p.split_k;
+    const long long total = (long long)tiles_per_batch * p.batch * SK;
     constexpr int GROUP = 8;
     const int per_group = GROUP * p.tiles_n;
 
@@ -192,7 +197,11 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
         // ===================== producer warpgroup (one working warp) =====================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(Cfg::PRODUCER_REGS));
         if (warp != Cfg::CONSUMER_WARPS) return;
-        for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+        for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+            const long long t = u / SK;
+            const int sk = (int)(u - t * SK);
+            const int kt_begin = (int)(((long long)KT_all * sk) / SK);
+            const int kt_end = (int)(((long long)KT_all * (sk + 1)) / SK);
             const int bz = (int)(t / tiles_per_batch);
             const int tile = (int)(t - (long long)bz * tiles_per_batch);
             const int grp = tile / per_group;
@@ -204,7 +213,7 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
             const double* Ag = p.A + (int64_t)bz * p.sA * E;
             const double* Bg = p.B + (int64_t)bz * p.sB * E;
             const int ba = p.batched_a ? bz : 0, bb = p.batched_b ? bz : 0;
-            for (int kt = 0; kt < KT; kt++) {
+            for (int kt = kt_begin; kt < kt_end; kt++) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 double* a_st = sA + stage * SA;
                 double* b_st = sB + stage * SB;
@@ -241,7 +250,11 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
     constexpr int A_MT = A_KC ? 8 * 4 * E : 8 * E;
     constexpr int B_NT = B_KC ? 8 * 4 * E : 8 * E;
 
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const long long t = u / SK;
+        const int sk = (int)(u - t * SK);
+        const int kt_begin = (int)(((long long)KT_all * sk) / SK);
+        const int kt_end = (int)(((long long)KT_all * (sk + 1)) / SK);
         const int bz = (int)(t / tiles_per_batch);
         const int tile = (int)(t - (long long)bz * tiles_per_batch);
         const int grp = tile / per_group;
@@ -259,7 +272,7 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
 #pragma unroll
                 for (int e = 0; e < 2 * E; e++) acc[i][j][e] = 0.0;
 
-        for (int kt = 0; kt < KT; kt++) {
+        for (int kt = kt_begin; kt < kt_end; kt++) {
             mbar_wait(&full[stage], phase);
             const double* As = sA + stage * SA + a_off;
             const double* Bs = sB + stage * SB + b_off;
@@ -304,13 +317,18 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
 
         // epilogue (overlaps the producer's prefetch of the next tile); with n_extra > 0 the tile is
         // also written to the peer GPUs' buffers (compute + all-gather in one kernel)
+        const bool partial = SK > 1;
+        const int64_t ldc_eff = partial ? (int64_t)p.N : p.ldc;
+        const bool accum = !partial && p.accumulate;
         for (int dsti = 0; dsti <= p.n_extra; dsti++) {
-            double* __restrict__ Cg = (dsti == 0 ? p.C : p.Cx[dsti - 1]) + (int64_t)bz * p.sC * E;
+            double* __restrict__ Cg =
+                partial ? p.Cpart + ((int64_t)bz * SK + sk) * (int64_t)p.M * p.N * E
+                        : (dsti == 0 ? p.C : p.Cx[dsti - 1]) + (int64_t)bz * p.sC * E;
 #pragma unroll
             for (int i = 0; i < MT; i++) {
                 const int row = m0 + wm * Cfg::WTM + i * 8 + g;
                 if (row >= p.M) continue;
-                double* crow = Cg + (int64_t)row * p.ldc * E;
+                double* crow = Cg + (int64_t)row * ldc_eff * E;
 #pragma unroll
                 for (int j = 0; j < NT; j++) {
                     const int col = n0 + wn * Cfg::WTN + j * 8 + 2 * q;
@@ -320,7 +338,7 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
                             if (col + e < p.N) {
                                 double2* dst = reinterpret_cast<double2*>(crow + (int64_t)(col + e) * 2);
                                 double2 v = make_double2(acc[i][j][e], acc[i][j][2 + e]);
-                                if (p.accumulate) {
+                                if (accum) {
                                     const double2 old = *dst;
                                     v.x += old.x;
                                     v.y += old.y;
@@ -333,7 +351,7 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
                         for (int e = 0; e < 2; e++) {
                             if (col + e < p.N) {
                                 double v = acc[i][j][e];
-                                if (p.accumulate) v += crow[col + e];
+                                if (accum) v += crow[col + e];
                                 crow[col + e] = v;
                             }
                         }
@@ -341,6 +359,27 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
                 }
             }
         }
+    }
+}
+
+// Sum the split-K partial tiles in fixed order: C[b][m][n] (+)= sum_s part[b][s][m][n]  (doubles; a complex
+// matrix is 2N doubles per row).
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const double* __restrict__ part, double* __restrict__ C,
+                                                            int M, int ND, int64_t ldcD, int64_t sCD, int SK,
+                                                            int accumulate) {
+    const int64_t per = (int64_t)M * ND;
+    const int b = blockIdx.y;
+    const double* pb = part + (int64_t)b * SK * per;
+    double* cb = C + (int64_t)b * sCD;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < per;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = idx / ND;
+        const int64_t nd = idx - m * ND;
+        double acc = 0.0;
+        for (int sidx = 0; sidx < SK; sidx++) acc += pb[(int64_t)sidx * per + idx];
+        double* dst = cb + m * ldcD + nd;
+        if (accumulate) acc += *dst;
+        *dst = acc;
     }
 }
 
@@ -399,17 +438,45 @@ static int launch_ws_inst(const WsParams& p, const CUtensorMap& ta, const CUtens
         PTB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid));
         configured = true;
     }
-    const long long total = (long long)p.tiles_m * p.tiles_n * p.batch;
+    const long long total = (long long)p.tiles_m * p.tiles_n * p.batch * p.split_k;
     const int grid = (int)(total < num_sms ? total : num_sms);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p, ta, tb);
-    return cuda_status(cudaGetLastError());
+    PTB_CUDA_TRY(cudaGetLastError());
+    if (p.split_k > 1) {
+        const int ND = p.N * Cfg::E;
+        const int64_t per = (int64_t)p.M * ND;
+        int gx = (int)((per + 255) / 256);
+        if (gx > 148 * 8) gx = 148 * 8;
+        if (gx < 1) gx = 1;
+        splitk_reduce_kernel<<<dim3(gx, p.batch), 256, 0, stream>>>(p.Cpart, p.C, p.M, ND, p.ldc * Cfg::E,
+                                                                     p.sC * Cfg::E, p.split_k, p.accumulate);
+        PTB_CUDA_TRY(cudaGetLastError());
+    }
+    return PTB_OK;
+}
+
+// Split factor that fills the 148-SM persistent grid best: maximise units / (waves * SMs) over
+// S in {1..8}, keeping at least 8 k-tiles per unit.  Returns 1 when splitting does not help.
+static int choose_split_k(long long tiles, int KT, int num_sms = 148) {
+    if (tiles >= 6LL * num_sms) return 1;
+    double best_eff = 0.0;
+    int best = 1;
+    for (int sk = 1; sk <= 8; sk++) {
+        if (sk > 1 && KT / sk < 8) break;
+        const long long units = tiles * sk;
+        const long long waves = (units + num_sms - 1) / num_sms;
+        const double eff = (double)units / (double)(waves * num_sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = sk; }
+    }
+    return best;
 }
 
 // Returns PTB_OK when launched, 1 when the fast path does not apply (caller falls back to the
 // first-generation kernel), or an error status.
 template <bool CPLX>
 static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp, cudaStream_t stream,
-                         int n_extra = 0, double* const* extra = nullptr) {
+                         int n_extra = 0, double* const* extra = nullptr, int split_k = 1, void* part_ws = nullptr,
+                         size_t part_ws_bytes = 0) {
     using Cfg = WsCfg<CPLX>;
     constexpr int E = Cfg::E;
     const bool a_kc = (transA == 0), b_kc = (transB != 0);
@@ -436,6 +503,18 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     p.batched_b = (gp.sB != 0 && gp.batch > 1) ? 1 : 0;
     p.n_extra = 0;
     for (int i = 0; i < 7; i++) p.Cx[i] = nullptr;
+    p.split_k = 1;
+    p.Cpart = nullptr;
+    if (split_k != 1 && n_extra == 0 && part_ws != nullptr) {
+        const int KT = (gp.K + Cfg::BK - 1) / Cfg::BK;
+        int sk = split_k > 1 ? split_k : choose_split_k((long long)p.tiles_m * p.tiles_n * p.batch, KT);
+        if (sk > KT) sk = KT;
+        const size_t need = (size_t)p.batch * sk * p.M * p.N * E * 8;
+        if (sk > 1 && need <= part_ws_bytes && al16(part_ws)) {
+            p.split_k = sk;
+            p.Cpart = static_cast<double*>(part_ws);
+        }
+    }
     if (n_extra > 0) {
         if (n_extra > 7 || gp.accumulate || !extra) return PTB_ERR_BAD_ARG;
         for (int i = 0; i < n_extra; i++) {

@@ -27,7 +27,7 @@ import torch.distributed as dist
 
 from . import _device as dev
 
-__all__ = ["ShardedEffectiveHamiltonian", "bond_partition"]
+__all__ = ["ShardedEffectiveHamiltonian", "PrecontractedShardedHamiltonian", "bond_partition"]
 
 
 def bond_partition(chi, nparts):
@@ -89,6 +89,37 @@ class _CudaOps:
     @staticmethod
     def step3(l2d, t2d, out):
         return dev.gemm(l2d, t2d, trans_a=True, out=out)
+
+    @staticmethod
+    def precontract(w3, l, out):
+        """out[i] = w3 @ l[i]:  w3 (R, chi_l) real or complex, l (Dl, chi_l, Dlp), out (Dl, R, Dlp)."""
+        nb, cl, dlp = l.shape
+        rows = w3.shape[0]
+        if l.dtype.is_complex and not w3.dtype.is_complex:
+            dev.gemm_strided(False, 0, 0, 0, rows, 2 * dlp, cl, w3, cl, torch.view_as_real(l), 2 * dlp,
+                             torch.view_as_real(out), 2 * dlp, nb, 0, 2 * cl * dlp, 2 * rows * dlp)
+        else:
+            cplx = l.dtype.is_complex
+            dev.gemm_strided(cplx, 0, 0, 0, rows, dlp, cl, dev.as_dtype(w3, cplx), cl, l, dlp, out, dlp,
+                             nb, 0, cl * dlp, rows * dlp)
+        return out
+
+    @staticmethod
+    def contract_lw(lw, t1, out):
+        """out[i',s',j'] = sum_K lw[K, s', i'] t1[K, j']  (K = (i, s, kappa_loc)): one GEMM batched over s'
+        with the contraction index split over work units (split-K) because the output has few tiles."""
+        from . import _lib
+        lib = _lib.load()
+        kk, dout, dlp = lw.shape
+        drp = t1.shape[1]
+        cplx = lw.dtype.is_complex
+        es = 16 if cplx else 8
+        ws = dev.workspace(8 * dout * dlp * drp * es, lw.device, tag="splitk")
+        st = lib.ptb_gemm_splitk(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, 1, 0, 0, dlp, drp, kk,
+                                 lw.data_ptr(), dout * dlp, t1.data_ptr(), drp, out.data_ptr(), dout * drp,
+                                 dout, dlp, 0, drp, 0, 0, ws.data_ptr(), ws.numel(), dev.stream_ptr(lw.device))
+        _lib.check(st, "ptb_gemm_splitk")
+        return out
 
 
 class ShardedEffectiveHamiltonian:
@@ -276,3 +307,132 @@ class ShardedEffectiveHamiltonian:
         gather = (self.world - 1) * self.Dl * self.d_in * self.P * self.Drp * es
         reduce_ = 2.0 * (self.world - 1) / max(self.world, 1) * self.Dlp * self.d_out * self.Drp * es
         return gather, reduce_
+
+
+class PrecontractedShardedHamiltonian:
+    r"""
+    MPO-bond-sharded effective Hamiltonian whose only communication is the all-reduce of the result.
+
+    The right MPO bond is split into G ranges.  Once per site (environments and MPO tensor are fixed
+    during a Lanczos run) rank g contracts the left environment with its slice of the MPO tensor,
+
+        LW_g[i, s, kappa, s', i'] = sum_k  w[k, s', s, kappa] l[i, k, i']        (kappa in range g),
+
+    and every matvec is then two GEMMs on that rank followed by one all-reduce:
+
+        t1_g[(i,s,kappa), j'] = a[(i,s), j] r[j, (kappa, j')]                    (kappa in range g)
+        out_g[i', s', j']     = sum_{(i,s,kappa)} LW_g[(i,s,kappa), s', i'] t1_g[(i,s,kappa), j']
+        out                   = all-reduce(sum_g out_g)                           (D*d*D elements)
+
+    Per-rank flops are 8 (Dl d Dr P Dr' + Dl' d' Dr' Dl d P) with P = chi_r / G: both GEMMs scale with
+    1/G and no intermediate ever crosses NVLink.  Compared with the three-step contraction this trades
+    the W step for a d-times larger final GEMM (about 12 % more flops at the 32-orbital molecular
+    shape), which is why the one-GPU path keeps the three-step form and the sharded path uses this one.
+    """
+
+    def __init__(self, lw, r_shard, dims, group=None, ops=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.ops = ops if ops is not None else _CudaOps()
+        self.lw = lw                      # (Dl * d_in * P, d_out, Dlp)
+        self.r_shard = r_shard            # (Dr, P, Drp), zero padded
+        (self.Dl, self.d_in, self.Dr, self.d_out, self.Dlp, self.Drp, self.P) = dims
+        self._t1 = None
+        self.exchange = "allreduce-only"
+
+    @staticmethod
+    def _w3(w_t, rank, P, cr):
+        """W3[(s, kappa_loc, s'), k] = w[k, s', s, kappa] for this rank's zero-padded kappa range."""
+        cl, dout, din, _ = w_t.shape
+        q0, q1 = rank * P, min((rank + 1) * P, cr)
+        blk = torch.zeros((din, P, dout, cl), dtype=w_t.dtype, device=w_t.device)
+        if q1 > q0:
+            blk[:, :q1 - q0] = w_t[:, :, :, q0:q1].permute(2, 3, 1, 0)
+        return blk.reshape(din * P * dout, cl).contiguous()
+
+    @classmethod
+    def from_full(cls, w, l, r, group=None, ops=None, device=None):
+        """Every rank passes the full (w, l, r); the rank keeps r[:, kappa_g, :] and builds LW_g."""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        ops = ops if ops is not None else _CudaOps()
+
+        def tens(x):
+            x = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            return x.to(device) if device is not None else x
+
+        w_t, l_t, r_t = tens(w), tens(l), tens(r)
+        w_t = w_t.to(l_t.device)
+        cl, dout, din, cr = w_t.shape
+        Dl, _, Dlp = l_t.shape
+        Dr, _, Drp = r_t.shape
+        cplx = l_t.dtype.is_complex or r_t.dtype.is_complex or w_t.dtype.is_complex
+        dt = torch.complex128 if cplx else torch.float64
+        l_t = l_t.to(dt).contiguous()
+        P = -(-cr // world)
+        r_pad = torch.zeros((Dr, P, Drp), dtype=dt, device=l_t.device)
+        q0, q1 = rank * P, min((rank + 1) * P, cr)
+        if q1 > q0:
+            r_pad[:, :q1 - q0, :] = r_t[:, q0:q1, :].to(dt)
+        w3 = cls._w3(w_t, rank, P, cr)
+        lw = torch.empty((Dl, din * P * dout, Dlp), dtype=dt, device=l_t.device)
+        ops.precontract(w3, l_t, lw)
+        return cls(lw.reshape(Dl * din * P, dout, Dlp), r_pad, (Dl, din, Dr, dout, Dlp, Drp, P), group=group, ops=ops)
+
+    @classmethod
+    def synthetic(cls, Dl, d, Dr, cl, cr, density=0.168, seed=0, device=None, group=None, dtype=torch.complex128):
+        """Random shards generated on this rank (benchmark input): the left environment is drawn in
+        full (it is what a site update would hold after its all-gather), LW_g is built from it by the
+        same precontraction GEMM a real run uses.  Returns (operator, precontraction milliseconds)."""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        device = device if device is not None else dev.default_device()
+        gen = torch.Generator(device=device).manual_seed(seed + 7919 * rank)
+        P = -(-cr // world)
+        scale = 1.0 / np.sqrt(Dl)
+        l_full = torch.randn((Dl, cl, Dl), dtype=dtype, device=device, generator=gen) * scale
+        r_shard = torch.randn((Dr, P, Dr), dtype=dtype, device=device, generator=gen) * scale
+        q1 = min((rank + 1) * P, cr) - rank * P
+        if q1 < P:
+            r_shard[:, max(q1, 0):, :] = 0
+        w3 = torch.randn((d * P * d, cl), dtype=torch.float64, device=device, generator=gen)
+        w3 = w3 * (torch.rand((d * P * d, cl), device=device, generator=gen) < density)
+        if q1 < P:
+            w3.reshape(d, P, d, cl)[:, max(q1, 0):] = 0
+        ops = _CudaOps()
+        lw = torch.empty((Dl, d * P * d, Dl), dtype=dtype, device=device)
+        torch.cuda.synchronize(device)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.precontract(w3.contiguous(), l_full, lw)
+        e1.record()
+        torch.cuda.synchronize(device)
+        setup_ms = e0.elapsed_time(e1)
+        del l_full
+        return cls(lw.reshape(Dl * d * P, d, Dl), r_shard, (Dl, d, Dr, d, Dl, Dr, P), group=group, ops=ops), setup_ms
+
+    def matvec(self, a):
+        """Apply the sharded effective Hamiltonian to `a` (Dl, d, Dr); every rank gets the full result."""
+        assert tuple(a.shape) == (self.Dl, self.d_in, self.Dr)
+        a = a.to(self.lw.dtype) if a.dtype != self.lw.dtype else a
+        a = a.contiguous()
+        rows = self.Dl * self.d_in
+        if self._t1 is None or self._t1.dtype != a.dtype:
+            self._t1 = torch.empty((rows, self.P * self.Drp), dtype=a.dtype, device=a.device)
+        # step 1 on this rank's kappa range; its row-major memory is also [(i, s, kappa_loc), j']
+        self.ops.step1(a.reshape(rows, self.Dr), self.r_shard.reshape(self.Dr, self.P * self.Drp), self._t1)
+        out = torch.empty((self.Dlp, self.d_out, self.Drp), dtype=a.dtype, device=a.device)
+        self.ops.contract_lw(self.lw, self._t1.reshape(rows * self.P, self.Drp), out)
+        if self.world > 1:
+            dist.all_reduce(_flat_real(out), op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def flops_per_rank(self):
+        s1 = self.Dl * self.d_in * self.Dr * self.P * self.Drp
+        s2 = self.Dlp * self.d_out * self.Drp * self.Dl * self.d_in * self.P
+        return 8.0 * (s1 + s2)
+
+    def exchange_bytes_per_rank(self):
+        es = self.lw.element_size()
+        return 0, 2.0 * (self.world - 1) / max(self.world, 1) * self.Dlp * self.d_out * self.Drp * es

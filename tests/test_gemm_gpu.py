@@ -114,3 +114,27 @@ def test_gemm_large_against_torch(cuda_lib, engine):
     c = dev.gemm(a, b, trans_a=True)
     ref = a.T @ b
     assert (torch.linalg.norm(c - ref) / torch.linalg.norm(ref)).item() < TOL
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+def test_gemm_split_k(cuda_lib, cplx):
+    """Split-K (partial tiles + ordered reduction) against NumPy: forced factors, automatic choice,
+    ragged K, batches and accumulate."""
+    from pytenet_b200 import _lib
+    rng = np.random.default_rng(21 + cplx)
+    lib = cuda_lib
+    for (M, N, K, batch, split, acc, ta) in [(130, 70, 1000, 1, 2, False, 0), (128, 64, 777, 1, 3, True, 1),
+                                             (256, 128, 4096, 2, 4, False, 1), (100, 60, 2048, 1, 0, False, 1),
+                                             (64, 64, 50, 1, 8, False, 0)]:
+        A = rnd(rng, (batch, K, M) if ta else (batch, M, K), cplx)
+        B = rnd(rng, (batch, K, N), cplx)
+        C0 = rnd(rng, (batch, M, N), cplx)
+        dA, dB, dC = (torch.from_numpy(x).cuda() for x in (A, B, C0))
+        ws = torch.empty(batch * 8 * M * N * (2 if cplx else 1), dtype=torch.float64, device="cuda")
+        st = lib.ptb_gemm_splitk(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, ta, 0, 0, M, N, K,
+                                 dA.data_ptr(), M if ta else K, dB.data_ptr(), N, dC.data_ptr(), N, batch,
+                                 M * K, K * N, M * N, int(acc), split, ws.data_ptr(), ws.numel() * 8,
+                                 torch.cuda.current_stream().cuda_stream)
+        assert st == 0, lib.ptb_status_string(st)
+        want = (A.transpose(0, 2, 1) if ta else A) @ B + (C0 if acc else 0)
+        assert rel(dC.cpu().numpy(), want) < TOL, (M, N, K, batch, split, acc, ta)

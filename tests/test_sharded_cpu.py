@@ -35,6 +35,16 @@ class CpuOps:
         out.copy_(l2d.T @ t2d)
         return out
 
+    @staticmethod
+    def precontract(w3, l, out):
+        out.copy_(torch.matmul(w3.to(l.dtype), l))
+        return out
+
+    @staticmethod
+    def contract_lw(lw, t1, out):
+        out.copy_(torch.einsum("ksm,kn->msn", lw, t1))
+        return out
+
 
 def _free_port():
     s = socket.socket()
@@ -65,7 +75,12 @@ def _worker(rank, world, port, shapes, seed, results):
         # second call reuses the buffers
         out2 = heff.matvec(torch.from_numpy(2 * a)).numpy()
         err2 = np.linalg.norm(out2 - 2 * ref) / np.linalg.norm(ref)
-        results[rank] = max(err, err2)
+        # the all-reduce-only (precontracted) variant
+        from pytenet_b200.sharded import PrecontractedShardedHamiltonian
+        hpre = PrecontractedShardedHamiltonian.from_full(w, torch.from_numpy(l), torch.from_numpy(r), ops=CpuOps())
+        out3 = hpre.matvec(torch.from_numpy(a)).numpy()
+        err3 = np.linalg.norm(out3 - ref) / np.linalg.norm(ref)
+        results[rank] = max(err, err2, err3)
     finally:
         dist.destroy_process_group()
 

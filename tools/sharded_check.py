@@ -13,12 +13,13 @@ import numpy as np
 import torch
 import torch.distributed as dist
 import pytenet_b200 as ptb
-from pytenet_b200.sharded import ShardedEffectiveHamiltonian
+from pytenet_b200.sharded import ShardedEffectiveHamiltonian, PrecontractedShardedHamiltonian
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--D", type=int, default=1024)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--exchange", default="auto")
+ap.add_argument("--mode", default="precontract", choices=["precontract", "exchange"])
 args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -35,14 +36,18 @@ l = torch.randn(Dl, cl, Dl, dtype=torch.complex128, device=device, generator=g)
 r = torch.randn(Dr, cr, Dr, dtype=torch.complex128, device=device, generator=g)
 w = torch.randn(cl, d, d, cr, dtype=torch.float64, device=device, generator=g)
 w = w * (torch.rand(cl, d, d, cr, device=device, generator=g) < 0.2)
-heff = ShardedEffectiveHamiltonian.from_full(w, l, r, exchange=args.exchange)
+if args.mode == "precontract":
+    make = lambda w_, l_, r_: PrecontractedShardedHamiltonian.from_full(w_, l_, r_)
+else:
+    make = lambda w_, l_, r_: ShardedEffectiveHamiltonian.from_full(w_, l_, r_, exchange=args.exchange)
+heff = make(w, l, r)
 out = heff.matvec(a)
 ref = ptb.apply_local_hamiltonian(a, w, l, r)
 err = (torch.linalg.norm(out - ref) / torch.linalg.norm(ref)).item()
 assert err < 1e-12, err
 # Lanczos on the sharded operator gives the same Ritz value on every rank
 lh = l + l.conj().permute(2, 1, 0); rh = r + r.conj().permute(2, 1, 0); wh = w + w.permute(0, 2, 1, 3)
-hs = ShardedEffectiveHamiltonian.from_full(wh, lh, rh, exchange=args.exchange)
+hs = make(wh, lh, rh)
 ev, _ = ptb.eigh_krylov(lambda x: hs.matvec(x.reshape(Dl, d, Dr)).reshape(-1), a.reshape(-1), 12, 1)
 ev_ref, _ = ptb.eigh_krylov(lambda x: ptb.apply_local_hamiltonian(x.reshape(Dl, d, Dr), wh, lh, rh).reshape(-1),
                             a.reshape(-1), 12, 1)
@@ -56,8 +61,12 @@ del heff, hs, l, r, w, lh, rh, wh
 # ---- 2. timing at the molecular-like shape --------------------------------------------------
 D = args.D
 cl, cr, d = 562, 501, 2
-heff = ShardedEffectiveHamiltonian.synthetic(D, d, D, cl, cr, density=0.168, seed=1, device=device,
-                                             exchange=args.exchange)
+setup_ms = 0.0
+if args.mode == "precontract":
+    heff, setup_ms = PrecontractedShardedHamiltonian.synthetic(D, d, D, cl, cr, density=0.168, seed=1, device=device)
+else:
+    heff = ShardedEffectiveHamiltonian.synthetic(D, d, D, cl, cr, density=0.168, seed=1, device=device,
+                                                 exchange=args.exchange)
 a = torch.randn(D, d, D, dtype=torch.complex128, device=device) / np.sqrt(D * d * D)
 for _ in range(2):
     heff.matvec(a)
@@ -79,7 +88,8 @@ f_alg = 8.0 * (D * d * D * cr * D + cl * d * d * cr * D * D + D * D * cl * d * D
 gather, red = heff.exchange_bytes_per_rank()
 if rank == 0:
     print(json.dumps({"sharded_matvec": {"n_gpus": world, "exchange": heff.exchange,
-                                         "note": getattr(heff, "_exchange_note", ""), "D": D, "chi_l": cl, "chi_r": cr, "d": d,
+                                         "note": getattr(heff, "_exchange_note", ""), "mode": args.mode,
+                                         "precontract_ms_per_site": setup_ms, "D": D, "chi_l": cl, "chi_r": cr, "d": d,
                                          "ms_per_matvec": t.item(), "gflops_alg": f_alg / t.item() / 1e6,
                                          "allgather_bytes_per_rank": gather, "allreduce_bytes_per_rank": red,
                                          "flops_exec_per_rank": heff.flops_per_rank()}}), flush=True)
