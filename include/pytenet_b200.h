@@ -72,6 +72,18 @@ int ptb_gemm_splitk(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, 
                     int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c, int accumulate,
                     int split_k, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Sector-banded GEMM (quantum-number block sparsity): like ptb_gemm, but every output tile only
+ * visits the k-tiles in [ktab[2*t], ktab[2*t+1]) where t = (batch * tiles_m + tile_m) * tiles_n + tile_n
+ * (device array of int32 pairs, tile shape from ptb_gemm_tile_shape).  The caller derives the ranges
+ * from the quantum numbers of the operand indices: contributions outside them are exact zeros
+ * (pytenet/block_sparse_util.py:47-53), so the result equals the dense product.  An empty range
+ * leaves the tile zero (or untouched when accumulating).  TMA engine only. */
+int ptb_gemm_banded(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k,
+                    const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc,
+                    int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c, int accumulate,
+                    const int32_t* ktab, void* stream);
+int ptb_gemm_tile_shape(int dtype, int* bm, int* bn, int* bk);
+
 /* Fused GEMM + all-gather: C = op(A) op(B) is written to n_dst (1..8) output buffers of identical
  * layout in the kernel's epilogue.  c_list is a HOST array of device pointers; entries beyond the
  * first are typically peer-mapped buffers of the other GPUs of the box (CUDA IPC / symmetric

@@ -26,6 +26,9 @@ SIGNATURES = {
     "ptb_set_gemm_engine": (_int, [_int]),
     "ptb_gemm_splitk": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                                _i64, _i64, _i64, _i64, _int, _int, _ptr, _sz, _ptr]),
+    "ptb_gemm_banded": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
+                               _i64, _i64, _i64, _i64, _int, _ptr, _ptr]),
+    "ptb_gemm_tile_shape": (_int, [_int, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     "ptb_gemm_multicast": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64,
                                   ctypes.POINTER(_ptr), _int, _i64, _ptr]),
     "ptb_gemm": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,

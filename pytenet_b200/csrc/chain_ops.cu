@@ -242,6 +242,39 @@ int ptb_gemm_splitk(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, 
     return PTB_ERR_BAD_DTYPE;
 }
 
+int ptb_gemm_banded(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k, const void* a,
+                    int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t batch, int64_t stride_a,
+                    int64_t stride_b, int64_t stride_c, int accumulate, const int32_t* ktab, void* stream) {
+    if (!a || !b || !c || !ktab) return PTB_ERR_BAD_ARG;
+    if (m <= 0 || n <= 0 || k <= 0 || batch <= 0 || !fits_int({m, n, k, batch})) return PTB_ERR_BAD_ARG;
+    GemmParams p;
+    p.A = static_cast<const double*>(a);
+    p.B = static_cast<const double*>(b);
+    p.C = static_cast<double*>(c);
+    p.M = (int)m; p.N = (int)n; p.K = (int)k;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.sA = stride_a; p.sB = stride_b; p.sC = stride_c;
+    p.batch = (int)batch;
+    p.accumulate = accumulate;
+    p.tiles_m = p.tiles_n = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if (dtype == PTB_COMPLEX128)
+        rc = try_launch_ws<true>(trans_a, trans_b, conj_b, p, st, 0, nullptr, 1, nullptr, 0, ktab);
+    else if (dtype == PTB_REAL64)
+        rc = try_launch_ws<false>(trans_a, trans_b, 0, p, st, 0, nullptr, 1, nullptr, 0, ktab);
+    else
+        return PTB_ERR_BAD_DTYPE;
+    return rc == 1 ? PTB_ERR_ALIGNMENT : rc;
+}
+
+int ptb_gemm_tile_shape(int dtype, int* bm, int* bn, int* bk) {
+    if (!bm || !bn || !bk) return PTB_ERR_BAD_ARG;
+    if (dtype == PTB_COMPLEX128) { *bm = WsCfg<true>::BM; *bn = WsCfg<true>::BN; *bk = WsCfg<true>::BK; return PTB_OK; }
+    if (dtype == PTB_REAL64) { *bm = WsCfg<false>::BM; *bn = WsCfg<false>::BN; *bk = WsCfg<false>::BK; return PTB_OK; }
+    return PTB_ERR_BAD_DTYPE;
+}
+
 int ptb_gemm_multicast(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k, const void* a,
                        int64_t lda, const void* b, int64_t ldb, void* const* c_list, int n_dst, int64_t ldc,
                        void* stream) {

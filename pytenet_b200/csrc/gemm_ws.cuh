@@ -72,6 +72,9 @@ struct WsParams {
     // partial tiles to Cpart ([batch][split][M][N], dense); a second kernel sums them in fixed order
     int split_k;
     double* Cpart;
+    // sector-banded GEMM: per (batch, tile) range [lo, hi) of k-tiles that can be non-zero given the
+    // quantum-number sectors of the operands (nullptr = full range); hi <= lo skips the tile's main loop
+    const int2* ktab;
 };
 
 // ---- mbarrier / TMA primitives ---------------------------------------------------------
@@ -200,8 +203,8 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
         for (long long u = blockIdx.x; u < total; u += gridDim.x) {
             const long long t = u / SK;
             const int sk = (int)(u - t * SK);
-            const int kt_begin = (int)(((long long)KT_all * sk) / SK);
-            const int kt_end = (int)(((long long)KT_all * (sk + 1)) / SK);
+            int kt_begin = (int)(((long long)KT_all * sk) / SK);
+            int kt_end = (int)(((long long)KT_all * (sk + 1)) / SK);
             const int bz = (int)(t / tiles_per_batch);
             const int tile = (int)(t - (long long)bz * tiles_per_batch);
             const int grp = tile / per_group;
@@ -210,6 +213,11 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
             const int tm = first_m + (tile % per_group) % gsize;
             const int tn = (tile % per_group) / gsize;
             const int m0 = tm * BM, n0 = tn * BN;
+            if (p.ktab != nullptr) {
+                const int2 kr = p.ktab[(long long)bz * tiles_per_batch + (long long)tm * p.tiles_n + tn];
+                kt_begin = max(kr.x, 0);
+                kt_end = min(kr.y, KT_all);
+            }
             const double* Ag = p.A + (int64_t)bz * p.sA * E;
             const double* Bg = p.B + (int64_t)bz * p.sB * E;
             const int ba = p.batched_a ? bz : 0, bb = p.batched_b ? bz : 0;
@@ -253,8 +261,8 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
     for (long long u = blockIdx.x; u < total; u += gridDim.x) {
         const long long t = u / SK;
         const int sk = (int)(u - t * SK);
-        const int kt_begin = (int)(((long long)KT_all * sk) / SK);
-        const int kt_end = (int)(((long long)KT_all * (sk + 1)) / SK);
+        int kt_begin = (int)(((long long)KT_all * sk) / SK);
+        int kt_end = (int)(((long long)KT_all * (sk + 1)) / SK);
         const int bz = (int)(t / tiles_per_batch);
         const int tile = (int)(t - (long long)bz * tiles_per_batch);
         const int grp = tile / per_group;
@@ -263,6 +271,11 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
         const int tm = first_m + (tile % per_group) % gsize;
         const int tn = (tile % per_group) / gsize;
         const int m0 = tm * BM, n0 = tn * BN;
+        if (p.ktab != nullptr) {
+            const int2 kr = p.ktab[(long long)bz * tiles_per_batch + (long long)tm * p.tiles_n + tn];
+            kt_begin = max(kr.x, 0);
+            kt_end = min(kr.y, KT_all);
+        }
 
         double acc[MT][NT][2 * E];
 #pragma unroll
@@ -476,7 +489,7 @@ static int choose_split_k(long long tiles, int KT, int num_sms = 148) {
 template <bool CPLX>
 static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp, cudaStream_t stream,
                          int n_extra = 0, double* const* extra = nullptr, int split_k = 1, void* part_ws = nullptr,
-                         size_t part_ws_bytes = 0) {
+                         size_t part_ws_bytes = 0, const int32_t* ktab = nullptr) {
     using Cfg = WsCfg<CPLX>;
     constexpr int E = Cfg::E;
     const bool a_kc = (transA == 0), b_kc = (transB != 0);
@@ -505,7 +518,9 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     for (int i = 0; i < 7; i++) p.Cx[i] = nullptr;
     p.split_k = 1;
     p.Cpart = nullptr;
-    if (split_k != 1 && n_extra == 0 && part_ws != nullptr) {
+    p.ktab = reinterpret_cast<const int2*>(ktab);
+    if (ktab != nullptr && (reinterpret_cast<uintptr_t>(ktab) % 8) != 0) return PTB_ERR_ALIGNMENT;
+    if (split_k != 1 && n_extra == 0 && part_ws != nullptr && ktab == nullptr) {
         const int KT = (gp.K + Cfg::BK - 1) / Cfg::BK;
         int sk = split_k > 1 ? split_k : choose_split_k((long long)p.tiles_m * p.tiles_n * p.batch, KT);
         if (sk > KT) sk = KT;

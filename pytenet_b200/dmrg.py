@@ -13,7 +13,8 @@ from .mps import (MPS, mps_local_orthonormalize_left_qr, mps_local_orthonormaliz
                   mps_merge_tensor_pair, mps_split_tensor_svd)
 from .mpo import MPO, mpo_merge_tensor_pair
 from .chain_ops import contraction_operator_step_right, contraction_operator_step_left
-from ._sweep import prepare_environments, minimize_local_energy
+from ._sweep import prepare_environments, minimize_local_energy, sector_plan
+from .block_sparse_util import qnumber_flatten
 
 __all__ = ["dmrg_singlesite", "dmrg_twosite"]
 
@@ -36,17 +37,21 @@ def dmrg_singlesite(hamiltonian: MPO, psi: MPS, numsweeps: int, numiter_lanczos:
     nsites = hamiltonian.nsites
     _, lblocks, rblocks = prepare_environments(hamiltonian, psi)
     ham, k = hamiltonian.a, numiter_lanczos
+    qh = hamiltonian.qbonds
     en_min = np.zeros(numsweeps)
+
+    def site_plan(i):
+        return sector_plan(psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], qh[i], qh[i + 1], psi.a[i])
 
     for n in range(numsweeps):
         en = 0
         for i in range(nsites - 1):                                          # dmrg.py:65-73
-            en, psi.a[i] = minimize_local_energy(ham[i], lblocks[i], rblocks[i], psi.a[i], k)
+            en, psi.a[i] = minimize_local_energy(ham[i], lblocks[i], rblocks[i], psi.a[i], k, site_plan(i))
             psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_local_orthonormalize_left_qr(
                 psi.a[i], psi.a[i + 1], psi.qsite, psi.qbonds[i:i + 2])
             lblocks[i + 1] = contraction_operator_step_left(psi.a[i], psi.a[i], ham[i], lblocks[i])
         for i in reversed(range(1, nsites)):                                 # dmrg.py:76-84
-            en, psi.a[i] = minimize_local_energy(ham[i], lblocks[i], rblocks[i], psi.a[i], k)
+            en, psi.a[i] = minimize_local_energy(ham[i], lblocks[i], rblocks[i], psi.a[i], k, site_plan(i))
             psi.a[i], psi.a[i - 1], psi.qbonds[i] = mps_local_orthonormalize_right_qr(
                 psi.a[i], psi.a[i - 1], psi.qsite, psi.qbonds[i:i + 2])
             rblocks[i - 1] = contraction_operator_step_right(psi.a[i], psi.a[i], ham[i], rblocks[i])
@@ -70,9 +75,13 @@ def dmrg_twosite(hamiltonian: MPO, psi: MPS, numsweeps: int, numiter_lanczos: in
     en_min = np.zeros(numsweeps)
     h2 = [mpo_merge_tensor_pair(ham[i], ham[i + 1]) for i in range(nsites - 1)]       # dmrg.py:135
 
+    qh = hamiltonian.qbonds
+    qs2 = qnumber_flatten([qs, qs])                   # quantum numbers of the merged physical index
+
     def optimize_pair(i, distr):
         merged = mps_merge_tensor_pair(psi.a[i], psi.a[i + 1])
-        en, merged = minimize_local_energy(h2[i], lblocks[i], rblocks[i + 1], merged, k)
+        plan = sector_plan(psi.qbonds[i], qs2, psi.qbonds[i + 2], qh[i], qh[i + 2], merged)
+        en, merged = minimize_local_energy(h2[i], lblocks[i], rblocks[i + 1], merged, k, plan)
         psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_split_tensor_svd(
             merged, qs, qs, [psi.qbonds[i], psi.qbonds[i + 2]], distr, tol=tol_split)
         return en

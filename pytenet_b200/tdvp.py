@@ -16,7 +16,7 @@ from .mps import MPS, mps_merge_tensor_pair, mps_split_tensor_svd
 from .mpo import MPO, mpo_merge_tensor_pair
 from .chain_ops import contraction_operator_step_right, contraction_operator_step_left
 from .block_sparse_util import qnumber_flatten, block_sparse_qr
-from ._sweep import prepare_environments, local_hamiltonian_step, local_bond_step
+from ._sweep import prepare_environments, local_hamiltonian_step, local_bond_step, sector_plan
 
 __all__ = ["tdvp_singlesite", "tdvp_twosite"]
 
@@ -38,11 +38,15 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
     nsites = hamiltonian.nsites
     nrm, lblocks, rblocks = prepare_environments(hamiltonian, psi)
     ham, k = hamiltonian.a, numiter_lanczos
+    qh = hamiltonian.qbonds
+
+    def site_plan(i):
+        return sector_plan(psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], qh[i], qh[i + 1], psi.a[i])
 
     for _ in range(numsteps):
         # left -> right: half step on each site, backward half step on each bond (tdvp.py:68-84)
         for i in range(nsites - 1):
-            psi.a[i] = local_hamiltonian_step(lblocks[i], rblocks[i], ham[i], psi.a[i], 0.5 * dt, k)
+            psi.a[i] = local_hamiltonian_step(lblocks[i], rblocks[i], ham[i], psi.a[i], 0.5 * dt, k, site_plan(i))
             b0, d, b1 = psi.a[i].shape
             q, c, psi.qbonds[i + 1] = block_sparse_qr(
                 psi.a[i].reshape(b0 * d, b1), qnumber_flatten((psi.qbonds[i], psi.qsite)), psi.qbonds[i + 1])
@@ -54,7 +58,7 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
 
         # full step on the last site (tdvp.py:87-89)
         i = nsites - 1
-        psi.a[i] = local_hamiltonian_step(lblocks[i], rblocks[i], ham[i], psi.a[i], dt, k)
+        psi.a[i] = local_hamiltonian_step(lblocks[i], rblocks[i], ham[i], psi.a[i], dt, k, site_plan(i))
 
         # right -> left (tdvp.py:92-115)
         for i in reversed(range(1, nsites)):
@@ -69,7 +73,7 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
             prv = psi.a[i - 1]
             psi.a[i - 1] = dev.gemm(prv.reshape(-1, prv.shape[2]), c).reshape(tuple(prv.shape[:2]) + (c.shape[1],))
             psi.a[i - 1] = local_hamiltonian_step(
-                lblocks[i - 1], rblocks[i - 1], ham[i - 1], psi.a[i - 1], 0.5 * dt, k)
+                lblocks[i - 1], rblocks[i - 1], ham[i - 1], psi.a[i - 1], 0.5 * dt, k, site_plan(i - 1))
 
     return nrm
 
@@ -95,14 +99,19 @@ def tdvp_twosite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lanczos:
     ham, k, qs = hamiltonian.a, numiter_lanczos, psi.qsite
     h2 = [mpo_merge_tensor_pair(ham[i], ham[i + 1]) for i in range(nsites - 1)]       # tdvp.py:163
 
+    qh = hamiltonian.qbonds
+    qs2 = qnumber_flatten([qs, qs])                   # quantum numbers of the merged physical index
+
     def evolve_pair(i, tau, distr):
         merged = mps_merge_tensor_pair(psi.a[i], psi.a[i + 1])
-        merged = local_hamiltonian_step(lblocks[i], rblocks[i + 1], h2[i], merged, tau, k)
+        plan = sector_plan(psi.qbonds[i], qs2, psi.qbonds[i + 2], qh[i], qh[i + 2], merged)
+        merged = local_hamiltonian_step(lblocks[i], rblocks[i + 1], h2[i], merged, tau, k, plan)
         psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_split_tensor_svd(
             merged, qs, qs, (psi.qbonds[i], psi.qbonds[i + 2]), distr, tol=tol_split)
 
     def backward_site(i):
-        psi.a[i] = local_hamiltonian_step(lblocks[i], rblocks[i], ham[i], psi.a[i], -0.5 * dt, k)
+        plan = sector_plan(psi.qbonds[i], qs, psi.qbonds[i + 1], qh[i], qh[i + 1], psi.a[i])
+        psi.a[i] = local_hamiltonian_step(lblocks[i], rblocks[i], ham[i], psi.a[i], -0.5 * dt, k, plan)
 
     for _ in range(numsteps):
         # left -> right (tdvp.py:168-184)

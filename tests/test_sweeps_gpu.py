@@ -189,3 +189,56 @@ def test_dmrg_against_exact_diagonalisation(cuda_lib):
     sector = np.where(sz == 2)[0]
     assert abs(e2 - np.linalg.eigvalsh(hm[np.ix_(sector, sector)])[0]) < 1e-12
     assert max(psi.bond_dims) > 6          # bonds must have grown
+
+
+def test_sector_banded_matvec_matches_dense(cuda_lib):
+    """Block-sparse path: HeffSectorPlan.apply == dense device matvec == oracle on block-sparse inputs
+    (sorted and unsorted bonds), and it actually skips work for sorted sectors."""
+    import oracle
+    import oracle.blocksparse as ob
+    import pytenet_b200 as ptb
+    from pytenet_b200.sectors import HeffSectorPlan
+    rng = np.random.default_rng(77)
+    for (Dl, d, Dr, cl, cr, sort) in [(300, 2, 260, 5, 5, True), (150, 4, 330, 6, 6, True), (200, 3, 129, 4, 5, False)]:
+        qs = rng.integers(-1, 2, size=d)
+        ql = rng.integers(-2, 3, size=Dl); qr = rng.integers(-2, 3, size=Dr)
+        if sort:
+            ql = np.sort(ql); qr = np.sort(qr)
+        qwl = rng.integers(-1, 2, size=cl); qwr = rng.integers(-1, 2, size=cr)
+        a = rng.normal(size=(Dl, d, Dr)) + 1j * rng.normal(size=(Dl, d, Dr)); ob.enforce_qsparsity(a, [ql, qs, -qr])
+        l = rng.normal(size=(Dl, cl, Dl)) + 1j * rng.normal(size=(Dl, cl, Dl)); ob.enforce_qsparsity(l, [ql, qwl, -ql])
+        r = rng.normal(size=(Dr, cr, Dr)) + 1j * rng.normal(size=(Dr, cr, Dr)); ob.enforce_qsparsity(r, [qr, qwr, -qr])
+        w = rng.normal(size=(cl, d, d, cr)); ob.enforce_qsparsity(w, [qwl, qs, -qs, -qwr])
+        plan = HeffSectorPlan(ql, qs, qr, qwl, qwr, cplx=True)
+        cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        got = plan.apply(cu(a), cu(w), cu(l), cu(r)).cpu().numpy()
+        ref = oracle.apply_local_hamiltonian(a, w, l, r)
+        dense = ptb.apply_local_hamiltonian(cu(a), cu(w), cu(l), cu(r)).cpu().numpy()
+        assert rel(got, ref) < 1e-12 and rel(got, dense) < 1e-13
+        # forbidden entries of the output stay exactly zero (SURVEY.md headline 3)
+        mask = ob.qnumber_outer_sum([ql, qs, -qr]) != 0
+        assert np.all(got[mask] == 0)
+
+
+def test_sweeps_with_forced_sector_plans(cuda_lib, golden_dir, monkeypatch):
+    """The sweeps give the same energies / sector layouts when every local problem goes through the
+    sector-banded matvec (forced; by default it is only used for bonds >= 256)."""
+    import pytenet_b200 as ptb
+    from pytenet_b200 import _sweep
+    monkeypatch.setattr(_sweep, "_SECTOR_MODE", "1")
+    z = np.load(os.path.join(golden_dir, "dmrg_fermi_hubbard_L6.npz"))
+    h, n = load_mpo(ptb, z)
+    psi = load_mps(ptb, z, "psi0", n)
+    en = ptb.dmrg_twosite(h, psi, 4, tol_split=1e-8)
+    assert abs(en[-1] - (-18.48435890403327)) < 1e-10
+    assert psi.bond_dims == [1, 4, 16, 30, 16, 4, 1]
+    for i in range(n + 1):
+        assert np.array_equal(psi.qbonds[i], z[f"two/qb{i}"])
+    z = np.load(os.path.join(golden_dir, "tdvp_xxz_qnum_L8.npz"))
+    h, n = load_mpo(ptb, z)
+    psi = load_mps(ptb, z, "psi0", n)
+    ptb.tdvp_twosite(h, psi, complex(z["dt"]), int(z["nsteps"]), numiter_lanczos=10)
+    assert rel(psi.to_vector(), z["two/vec"]) < 1e-9
+    psi = load_mps(ptb, z, "psi0", n)
+    ptb.tdvp_singlesite(h, psi, complex(z["dt"]), int(z["nsteps"]), numiter_lanczos=5)
+    assert rel(psi.to_vector(), z["single/vec"]) < 1e-9
