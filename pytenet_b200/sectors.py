@@ -107,6 +107,9 @@ class HeffSectorPlan:
         cl, cr, dout = len(self.qwl), len(self.qwr), len(self.qs_out)
         Dlp, Drp = len(self.qlp), len(self.qrp)
         self.dims = (Dl, d, Dr, cl, cr, dout, Dlp, Drp)
+        # the banded kernel is the TMA engine: float64 operands need even extents (16-byte granularity);
+        # complex128 always qualifies.  Otherwise apply() uses the dense device path.
+        self.supported = cplx or (Dr % 2 == 0 and Drp % 2 == 0 and Dlp % 2 == 0)
 
         # step 1, batched over s:  t1[i, s, (K, j')] = sum_j a[i, s, j] r[j, (K, j')]
         #   row i (batch s) needs  qr[j] = ql[i] + qs[s];  column (K, j') needs  qr[j] = qr'[j'] - qwr[K]
@@ -158,6 +161,9 @@ class HeffSectorPlan:
         Dl, d, Dr, cl, cr, dout, Dlp, Drp = self.dims
         cplx = dev.any_complex(a, l, r, w)
         assert cplx == self.cplx, "plan was built for a different dtype (tile shape differs)"
+        if not self.supported:
+            from .chain_ops import apply_local_hamiltonian
+            return apply_local_hamiltonian(a, w, l, r, out=out)
         a = dev.as_dtype(a, cplx); l = dev.as_dtype(l, cplx); r = dev.as_dtype(r, cplx)
         w = dev.dense(w)
         assert tuple(a.shape) == (Dl, d, Dr) and tuple(w.shape) == (cl, dout, d, cr)
