@@ -70,6 +70,58 @@ def host_inputs(D, d, chi, seed, pinned=False):
     return a, w, l, r
 
 
+def host_inputs_onesite(D, chi, seed):
+    """One-site XXZ inputs: a (D,2,D), bulk MPO tensor (5,2,2,5)."""
+    from pytenet_b200 import hamiltonian as ham
+    rng = np.random.default_rng(seed)
+
+    def crandn(shape):
+        return (rng.normal(size=shape) + 1j * rng.normal(size=shape)) / np.sqrt(2)
+
+    _, _, w, _, _ = ham._xxz_bulk(1.0, 0.8, -0.1)
+    return (crandn((D, 2, D)) / np.sqrt(2 * D * D), np.ascontiguousarray(w), crandn((D, chi, D)) / np.sqrt(D),
+            crandn((D, chi, D)) / np.sqrt(D))
+
+
+def block_sparse_block(torch, ptb, device, time_ms, D=2048):
+    """BASELINE config 3 shape (two-site Fermi-Hubbard, (N,Sz) sectors, bonds grouped by sector as the sweeps
+    leave them): dense device matvec vs the sector-banded matvec (HeffSectorPlan / ptb_gemm_banded)."""
+    from pytenet_b200 import hamiltonian as ham
+    from pytenet_b200.sectors import HeffSectorPlan
+    qsite, qb, wbulk, _, _ = ham._fermi_hubbard_bulk(1.0, 4.0, 0.0)
+    qsite = np.array(qsite); qb = np.array(qb)
+    d1 = len(qsite)
+    qs2 = np.add.outer(qsite, qsite).reshape(-1)
+    w2 = np.einsum("kpqm,mrsn->kprqsn", wbulk, wbulk).reshape(6, d1 * d1, d1 * d1, 6)
+    cand = [(dn, ds) for dn in range(-4, 5) for ds in range(-4, 5) if (dn + ds) % 2 == 0]
+    wts = np.array([np.exp(-(dn ** 2 + ds ** 2) / (2 * 1.6 ** 2)) for dn, ds in cand])
+    sizes = np.floor(wts / wts.sum() * D).astype(int)
+    sizes[np.argmax(sizes)] += D - sizes.sum()
+    q = np.sort(np.concatenate([np.full(sz, ptb.encode_quantum_number_pair(32 + dn, ds))
+                                for (dn, ds), sz in zip(cand, sizes)]))
+    g = torch.Generator(device=device).manual_seed(1)
+
+    def crand(*shape):
+        return torch.randn(*shape, dtype=torch.complex128, device=device, generator=g)
+
+    a = crand(D, d1 * d1, D); ptb.enforce_qsparsity(a, [q, qs2, -q])
+    l = crand(D, 6, D); ptb.enforce_qsparsity(l, [q, qb, -q])
+    r = crand(D, 6, D); ptb.enforce_qsparsity(r, [q, qb, -q])
+    w = torch.from_numpy(w2).to(device)
+    plan = HeffSectorPlan(q, qs2, q, qb, qb, cplx=True)
+    dense = ptb.apply_local_hamiltonian(a, w, l, r)
+    banded = plan.apply(a, w, l, r)
+    err = (torch.linalg.norm(banded - dense) / torch.linalg.norm(dense)).item()
+    ms_d = time_ms(lambda: ptb.apply_local_hamiltonian(a, w, l, r), reps=2)
+    ms_b = time_ms(lambda: plan.apply(a, w, l, r), reps=5)
+    fa = f_alg(D, d1 * d1, 6)
+    return {"workload": f"two-site Fermi-Hubbard heff matvec a ({D},16,{D}), h2 (6,16,16,6), {int((sizes > 0).sum())} "
+                        f"(N,Sz) sectors (Gaussian size profile, max {int(sizes.max())})",
+            "tensor_fill": float((a != 0).double().mean().item()), "ms_dense": ms_d, "ms_sector_banded": ms_b,
+            "speedup": ms_d / ms_b, "gflops_alg_dense_path": fa / ms_d / 1e6, "gflops_alg_banded_path": fa / ms_b / 1e6,
+            "rel_diff_banded_vs_dense": err, "k_tile_visit_fraction": list(plan.visit_fraction)}
+
+
 # ----------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement of the reference on the host cores
 # ----------------------------------------------------------------------------------------
@@ -376,6 +428,20 @@ def run_ours(args):
     # PTB_BENCH_SKIP_CPU=1 only for runs under a profiler (numbers taken there are never bench values)
     cpu = None if os.environ.get("PTB_BENCH_SKIP_CPU") == "1" else cpu_baseline_block()
 
+    # ---- other shapes of the same path (device-resident, CUDA events) ----
+    del t1, t2
+    torch.cuda.empty_cache()
+    other = []
+    for (Do, do, tag) in [(1024, 4, "config 2 two-site (1024,4,1024)"), (2048, 2, "one-site (2048,2,2048)")]:
+        ao, wo, lo, ro = host_inputs(Do, do, chi, seed=7) if do == d_HEAD else host_inputs_onesite(Do, chi, seed=7)
+        ad, wd, ld, rd = (torch.from_numpy(x).to(device) for x in (ao, wo, lo, ro))
+        mso = time_ms(lambda: ptb.apply_local_hamiltonian(ad, wd, ld, rd), reps=5)
+        other.append({"shape": tag, "ms_per_matvec": mso, "gflops": f_alg(Do, do, chi) / mso / 1e6})
+        del ad, wd, ld, rd
+    block_sparse = None
+    if os.environ.get("PTB_BENCH_SKIP_SECTORS") != "1":
+        block_sparse = block_sparse_block(torch, ptb, device, time_ms)
+
     line = {
         "metric": METRIC, "value": world * F / (ms / 1e3) / 1e9, "unit": "GFLOP/s", "n_gpus": world,
         "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -391,6 +457,8 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "sharded": sharded,
+        "other_shapes": other,
+        "block_sparse": block_sparse,
     }
     print(json.dumps(line))
     if world > 1:

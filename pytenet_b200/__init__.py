@@ -18,5 +18,6 @@ from .krylov import *             # noqa: F401,F403
 from .tdvp import *               # noqa: F401,F403
 from .dmrg import *               # noqa: F401,F403
 from .hamiltonian import *        # noqa: F401,F403
+from .metts import *              # noqa: F401,F403
 
 __version__ = "0.1.0"
