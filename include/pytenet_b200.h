@@ -118,6 +118,26 @@ int ptb_apply_local_hamiltonian_d(const void* a, const void* w, const void* l, c
                                   int64_t d_out, int64_t Dlp, int64_t Drp, void* workspace,
                                   size_t workspace_bytes, void* stream);
 
+/* Same contraction with the MPO tensor given in CSR form: W = w reshaped to (chi_l*d_out) x (d_in*chi_r),
+ * row pointers / column indices as device int32 arrays, values float64 (or complex128 when
+ * w_is_complex).  MPO tensors of local Hamiltonians are 5-17 % dense, so the W step becomes the
+ * HBM-bound sparse kernel below instead of a small dense GEMM.  Workspace as above. */
+int ptb_apply_local_hamiltonian_csr_z(const void* a, const int32_t* w_rowptr, const int32_t* w_col, const void* w_val,
+                                      int w_is_complex, const void* l, const void* r, void* out, int64_t Dl,
+                                      int64_t d_in, int64_t Dr, int64_t chi_l, int64_t chi_r, int64_t d_out,
+                                      int64_t Dlp, int64_t Drp, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+int ptb_apply_local_hamiltonian_csr_d(const void* a, const int32_t* w_rowptr, const int32_t* w_col, const void* w_val,
+                                      const void* l, const void* r, void* out, int64_t Dl, int64_t d_in, int64_t Dr,
+                                      int64_t chi_l, int64_t chi_r, int64_t d_out, int64_t Dlp, int64_t Drp,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* W step alone (pytenet/chain_ops.py:276, :52, :96):  t_out[b, m, n] = sum_c W[m, c] t_in[b, c, n],
+ * W in CSR form (r_out rows), t_in (batch, r_in, n_cols), t_out (batch, r_out, n_cols) dense, dtype
+ * t_dtype.  One pass over t_in and t_out: algorithmic bytes = elem_size (r_in + r_out) n_cols batch. */
+int ptb_wapply_csr(int t_dtype, int w_is_complex, int64_t r_out, int64_t r_in, int64_t n_cols, const int32_t* rowptr,
+                   const int32_t* col, const void* val, const void* t_in, void* t_out, int64_t batch, void* stream);
+
 /* ---------------------------------------------------------------------------
  * apply_local_bond_contraction(c, l, r)          pytenet/chain_ops.py:282-317
  *   out[i',j'] = sum l[i,k,i'] c[i,j] r[j,k,j']

@@ -150,3 +150,32 @@ def gemm_strided(cplx, trans_a, trans_b, conj_b, m, n, k, a, lda, b, ldb, c, ldc
                       stream_ptr(c.device))
     _lib.check(st, "ptb_gemm")
     return c
+
+
+# ---- CSR form of small sparse MPO tensors (cached per tensor version) ---------------------------
+_csr_cache = {}
+_CSR_MAX_NNZ = 4096          # beyond this the dense GEMM W step is the better kernel
+
+
+def w_csr(w):
+    """(rowptr, col, val, nnz) device arrays of w reshaped to (chi_l*d_out) x (d_in*chi_r), or None when w
+    is too dense / large for the sparse W kernel.  Built once per tensor (one small device->host copy of w)."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), w.dtype)
+    hit = _csr_cache.get(key)
+    if hit is not None:
+        return hit[0]
+    cl, dout, din, cr = w.shape
+    mat = w.detach().reshape(cl * dout, din * cr).cpu().numpy()
+    rows, cols = np.nonzero(mat)
+    result = None
+    if len(rows) <= _CSR_MAX_NNZ:
+        rowptr = np.zeros(cl * dout + 1, dtype=np.int32)
+        np.add.at(rowptr, rows + 1, 1)
+        rowptr = np.cumsum(rowptr, dtype=np.int64).astype(np.int32)
+        vals = np.ascontiguousarray(mat[rows, cols])
+        result = (torch.from_numpy(rowptr).to(w.device), torch.from_numpy(cols.astype(np.int32)).to(w.device),
+                  torch.from_numpy(vals).to(w.device), len(rows))
+    if len(_csr_cache) > 256:
+        _csr_cache.clear()
+    _csr_cache[key] = (result, w)           # keep `w` alive so the data_ptr key cannot be recycled
+    return result

@@ -71,12 +71,23 @@ def apply_local_hamiltonian(a, w, l, r, out=None):
     nbytes = lib.ptb_apply_local_hamiltonian_workspace_bytes(dt, Dl, d, Dr, cl, cr, dout, Dlp, Drp)
     ws = dev.workspace(nbytes, device)
     dims = (Dl, d, Dr, cl, cr, dout, Dlp, Drp)
-    if cplx:
+    tail = (ws.data_ptr(), nbytes, dev.stream_ptr(device))
+    csr = dev.w_csr(w) if (cplx or not w_cplx) else None     # sparse W kernel for 5-17 % dense MPO tensors
+    if csr is not None:
+        rowptr, col, val, _ = csr
+        if cplx:
+            st = lib.ptb_apply_local_hamiltonian_csr_z(a.data_ptr(), rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                                       int(w_cplx), l.data_ptr(), r.data_ptr(), out.data_ptr(),
+                                                       *dims, *tail)
+        else:
+            st = lib.ptb_apply_local_hamiltonian_csr_d(a.data_ptr(), rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                                       l.data_ptr(), r.data_ptr(), out.data_ptr(), *dims, *tail)
+    elif cplx:
         st = lib.ptb_apply_local_hamiltonian_z(a.data_ptr(), w.data_ptr(), int(w_cplx), l.data_ptr(), r.data_ptr(),
-                                               out.data_ptr(), *dims, ws.data_ptr(), nbytes, dev.stream_ptr(device))
+                                               out.data_ptr(), *dims, *tail)
     else:
         st = lib.ptb_apply_local_hamiltonian_d(a.data_ptr(), w.data_ptr(), l.data_ptr(), r.data_ptr(),
-                                               out.data_ptr(), *dims, ws.data_ptr(), nbytes, dev.stream_ptr(device))
+                                               out.data_ptr(), *dims, *tail)
     _lib.check(st, "apply_local_hamiltonian")
     return _finish(out, host_mode)
 

@@ -114,6 +114,33 @@ int apply_local_hamiltonian_impl(const void* a, const void* w, bool w_cplx, cons
                       0, part, part_bytes);
 }
 
+// Same contraction with the W step done by the sparse CSR kernel (csrc/wapply.cu): for the 5-17 % dense MPO
+// tensors of local Hamiltonians step 2 is then pure data movement (read t1, write t2 once).
+template <bool CPLX>
+int apply_local_hamiltonian_csr_impl(const void* a, const int32_t* w_rowptr, const int32_t* w_col, const void* w_val,
+                                     bool w_cplx, const void* l, const void* r, void* out, int64_t Dl, int64_t d,
+                                     int64_t Dr, int64_t cl, int64_t cr, int64_t dout, int64_t Dlp, int64_t Drp,
+                                     void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!a || !w_rowptr || !w_col || !w_val || !l || !r || !out) return PTB_ERR_BAD_ARG;
+    if (bad_dims({Dl, d, Dr, cl, cr, dout, Dlp, Drp})) return PTB_ERR_BAD_ARG;
+    if (!CPLX && w_cplx) return PTB_ERR_BAD_DTYPE;
+    const size_t es = CPLX ? 16 : 8;
+    const size_t n1 = (size_t)Dl * d * cr * Drp, n2 = (size_t)Dl * cl * dout * Drp;
+    if (ws_bytes < align16(n1 * es) + align16(n2 * es) || !ws) return PTB_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(ws) % 16) return PTB_ERR_ALIGNMENT;
+    char* t1 = static_cast<char*>(ws);
+    char* t2 = t1 + align16(n1 * es);
+    char* part = t2 + align16(n2 * es);
+    const size_t part_bytes = ws_bytes - (size_t)(part - t1);
+    int rc = gemm<CPLX>(0, 0, 0, Dl * d, cr * Drp, Dr, a, Dr, r, cr * Drp, t1, cr * Drp, 1, 0, 0, 0, 0, st);
+    if (rc) return rc;
+    rc = ptb_wapply_csr(CPLX ? PTB_COMPLEX128 : PTB_REAL64, w_cplx ? 1 : 0, cl * dout, d * cr, Drp, w_rowptr, w_col,
+                        w_val, t1, t2, Dl, st);
+    if (rc) return rc;
+    return gemm<CPLX>(1, 0, 0, Dlp, dout * Drp, Dl * cl, l, Dlp, t2, dout * Drp, out, dout * Drp, 1, 0, 0, 0, 0, st,
+                      0, part, part_bytes);
+}
+
 template <bool CPLX>
 int bond_impl(const void* c, const void* l, const void* r, void* out, int64_t Dl, int64_t Dr, int64_t chi,
               int64_t Dlp, int64_t Drp, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -326,6 +353,25 @@ int ptb_apply_local_hamiltonian_d(const void* a, const void* w, const void* l, c
                                   size_t workspace_bytes, void* stream) {
     return apply_local_hamiltonian_impl<false>(a, w, false, l, r, out, Dl, d_in, Dr, chi_l, chi_r, d_out, Dlp, Drp,
                                                workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int ptb_apply_local_hamiltonian_csr_z(const void* a, const int32_t* w_rowptr, const int32_t* w_col, const void* w_val,
+                                      int w_is_complex, const void* l, const void* r, void* out, int64_t Dl,
+                                      int64_t d_in, int64_t Dr, int64_t chi_l, int64_t chi_r, int64_t d_out,
+                                      int64_t Dlp, int64_t Drp, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+    return apply_local_hamiltonian_csr_impl<true>(a, w_rowptr, w_col, w_val, w_is_complex != 0, l, r, out, Dl, d_in, Dr,
+                                                  chi_l, chi_r, d_out, Dlp, Drp, workspace, workspace_bytes,
+                                                  static_cast<cudaStream_t>(stream));
+}
+
+int ptb_apply_local_hamiltonian_csr_d(const void* a, const int32_t* w_rowptr, const int32_t* w_col, const void* w_val,
+                                      const void* l, const void* r, void* out, int64_t Dl, int64_t d_in, int64_t Dr,
+                                      int64_t chi_l, int64_t chi_r, int64_t d_out, int64_t Dlp, int64_t Drp,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    return apply_local_hamiltonian_csr_impl<false>(a, w_rowptr, w_col, w_val, false, l, r, out, Dl, d_in, Dr, chi_l,
+                                                   chi_r, d_out, Dlp, Drp, workspace, workspace_bytes,
+                                                   static_cast<cudaStream_t>(stream));
 }
 
 size_t ptb_apply_local_bond_contraction_workspace_bytes(int dtype, int64_t Dl, int64_t Dr, int64_t chi,

@@ -185,8 +185,15 @@ class HeffSectorPlan:
         st = lib.ptb_gemm_banded(dt, 0, 0, 0, Dl, cr * Drp, Dr, a.data_ptr(), d * Dr, r.data_ptr(), cr * Drp,
                                  t1.data_ptr(), d * cr * Drp, d, Dr, 0, cr * Drp, 0, self.tab1.data_ptr(), stream)
         _lib.check(st, "ptb_gemm_banded(step 1)")
-        # (2) W step, dense small GEMM batched over i (t1[i] is (d*cr) x Drp, t2[i] is (cl*dout) x Drp)
-        if cplx and not w.dtype.is_complex:
+        # (2) W step batched over i (t1[i] is (d*cr) x Drp, t2[i] is (cl*dout) x Drp): sparse CSR kernel for
+        #     the usual sparse MPO tensors, dense small GEMM otherwise
+        csr = dev.w_csr(w) if (cplx or not w.dtype.is_complex) else None
+        if csr is not None:
+            rowptr, col, val, _ = csr
+            st = lib.ptb_wapply_csr(dt, int(w.dtype.is_complex), cl * dout, d * cr, Drp, rowptr.data_ptr(),
+                                    col.data_ptr(), val.data_ptr(), t1.data_ptr(), t2.data_ptr(), Dl, stream)
+            _lib.check(st, "ptb_wapply_csr")
+        elif cplx and not w.dtype.is_complex:
             dev.gemm_strided(False, 0, 0, 0, cl * dout, 2 * Drp, d * cr, w, d * cr, torch.view_as_real(t1), 2 * Drp,
                              torch.view_as_real(t2), 2 * Drp, Dl, 0, 2 * d * cr * Drp, 2 * cl * dout * Drp)
         else:

@@ -145,3 +145,33 @@ def test_hermiticity_and_linearity_at_scale(cuda_lib):
     assert abs((lhs - rhs).item()) / abs(lhs.item()) < 1e-11
     hxy = ptb.apply_local_hamiltonian(x + 2 * y, w, l, r)
     assert (torch.linalg.norm(hxy - (hx + 2 * hy)) / torch.linalg.norm(hxy)).item() < 1e-13
+
+
+def test_sparse_and_dense_w_step_agree(cuda_lib):
+    """The CSR W kernel (sparse MPO tensors) and the GEMM W step (dense / large MPO tensors) give the same
+    matvec; both against the oracle.  The dense path is forced by lowering the CSR threshold."""
+    import pytenet_b200 as ptb
+    from pytenet_b200 import _device as dev
+    rng = np.random.default_rng(41)
+    Dl, d, Dr, cl, cr = 70, 3, 66, 9, 8
+    a = rnd(rng, (Dl, d, Dr), True); l = rnd(rng, (Dl, cl, Dl), True); r = rnd(rng, (Dr, cr, Dr), True)
+    for cplx_w in (False, True):
+        w = rnd(rng, (cl, d, d, cr), cplx_w)
+        w[rng.random(w.shape) < 0.85] = 0
+        want = oracle.apply_local_hamiltonian(a, w, l, r)
+        assert dev.w_csr(cu(w)) is not None
+        got_sparse = ptb.apply_local_hamiltonian(cu(a), cu(w), cu(l), cu(r)).cpu().numpy()
+        old = dev._CSR_MAX_NNZ
+        try:
+            dev._CSR_MAX_NNZ = 0
+            dev._csr_cache.clear()
+            got_dense = ptb.apply_local_hamiltonian(cu(a), cu(w), cu(l), cu(r)).cpu().numpy()
+        finally:
+            dev._CSR_MAX_NNZ = old
+            dev._csr_cache.clear()
+        assert rel(got_sparse, want) < TOL and rel(got_dense, want) < TOL
+    # real state with a real sparse W
+    ar, lr, rr = rnd(rng, (Dl, d, Dr), False), rnd(rng, (Dl, cl, Dl), False), rnd(rng, (Dr, cr, Dr), False)
+    w = rnd(rng, (cl, d, d, cr), False); w[rng.random(w.shape) < 0.85] = 0
+    got = ptb.apply_local_hamiltonian(cu(ar), cu(w), cu(lr), cu(rr)).cpu().numpy()
+    assert got.dtype == np.float64 and rel(got, oracle.apply_local_hamiltonian(ar, w, lr, rr)) < TOL
