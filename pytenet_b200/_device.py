@@ -173,6 +173,9 @@ def w_csr(w):
         np.add.at(rowptr, rows + 1, 1)
         rowptr = np.cumsum(rowptr, dtype=np.int64).astype(np.int32)
         vals = np.ascontiguousarray(mat[rows, cols])
+        if len(rows) == 0:                       # all-zero MPO tensor: keep the arrays non-empty (non-null pointers)
+            cols = np.zeros(1, dtype=np.int64)
+            vals = np.zeros(1, dtype=mat.dtype)
         result = (torch.from_numpy(rowptr).to(w.device), torch.from_numpy(cols.astype(np.int32)).to(w.device),
                   torch.from_numpy(vals).to(w.device), len(rows))
     if len(_csr_cache) > 256:
