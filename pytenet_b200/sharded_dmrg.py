@@ -1,0 +1,210 @@
+"""
+Single-site DMRG with the MPO virtual bond split across GPUs (BASELINE config 4: molecular
+Hamiltonians, MPO bond dimension O(N^2)).
+
+Every environment block is stored sharded over its MPO-bond index: rank g of G holds the contiguous
+range g of bond b (zero padded to P_b = ceil(chi_b / G)), so the environment lists cost 1/G of the
+reference's memory per GPU (the reference keeps both full lists, dmrg.py:49-51).  The state `psi` and
+the MPO are replicated.  One site of a left-to-right sweep is
+
+  1. all-gather of the left block l_i  (once per site; the only bulk transfer, ~1 % of the site's time)
+  2. LW_g = sum_k w[k, :, :, kappa_g] l_i[:, k, :]                       precontraction, 1/G of the W flops
+  3. Lanczos on  x -> all-reduce( LW_g^T (x r_{i,g}) )                   two GEMMs + one all-reduce per matvec
+  4. QR of the optimised tensor (replicated, cuSOLVER)
+  5. l_{i+1,g} = a^T (LW_g conj(a))                                      two GEMMs, no communication: the new block
+                                                                          is born sharded over the right MPO bond
+
+and the right-to-left sweep is the mirror image, obtained by transposing the site / MPO tensors
+(`_mirror_*`) so that the same left-form kernels serve both directions.  All ranks execute the same
+Lanczos recursion on identical data (the all-reduce returns identical results everywhere), so psi stays
+bit-identical across ranks without further synchronisation.
+
+The arithmetic goes through an `ops` object (default: the CUDA engine, pytenet_b200/sharded.py); the
+multi-rank logic of the environment update is covered on CPU/gloo with a test-only ops object.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _device as dev
+from .mps import MPS, mps_local_orthonormalize_left_qr, mps_local_orthonormalize_right_qr
+from .mpo import MPO
+from .krylov import eigh_krylov
+from .sharded import _CudaOps, _flat_real
+
+__all__ = ["dmrg_singlesite_sharded", "ShardedSite", "shard_env", "gather_env"]
+
+
+def _world(group):
+    if dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def shard_env(block, group=None):
+    """This rank's zero-padded MPO-bond range of a full environment block (D, chi, D')."""
+    world, rank = _world(group)
+    D, chi, Dp = block.shape
+    P = -(-chi // world)
+    out = torch.zeros((D, P, Dp), dtype=block.dtype, device=block.device)
+    q0, q1 = rank * P, min((rank + 1) * P, chi)
+    if q1 > q0:
+        out[:, :q1 - q0, :] = block[:, q0:q1, :]
+    return out
+
+
+def gather_env(shard, chi, group=None):
+    """Full environment block (D, chi, D') from the per-rank shards (D, P, D')."""
+    world, _ = _world(group)
+    D, P, Dp = shard.shape
+    if world == 1:
+        return shard[:, :chi, :].contiguous()
+    buf = torch.empty((world, D, P, Dp), dtype=shard.dtype, device=shard.device)
+    dist.all_gather_into_tensor(_flat_real(buf), _flat_real(shard.contiguous()), group=group)
+    return buf.permute(1, 0, 2, 3).reshape(D, world * P, Dp)[:, :chi, :].contiguous()
+
+
+def _mirror_site(a):
+    return dev.dense(a.permute(2, 1, 0))
+
+
+def _mirror_w(w):
+    return dev.dense(w.permute(3, 1, 2, 0))
+
+
+class ShardedSite:
+    """
+    Left-form sharded local problem: the full "left-like" block `lfull` (D, chi_l, D') is contracted with this
+    rank's range of the MPO tensor's right bond; `r_shard` (Dr, P, Dr') is this rank's range of the
+    "right-like" block.  Serves the matvec and the environment update of one site.
+    """
+
+    def __init__(self, w, lfull, r_shard, group=None, ops=None):
+        self.group = group
+        self.world, self.rank = _world(group)
+        self.ops = ops if ops is not None else _CudaOps()
+        cl, dout, din, cr = w.shape
+        Dl, cl2, Dlp = lfull.shape
+        assert cl2 == cl
+        P = -(-cr // self.world)
+        assert r_shard.shape[1] == P
+        self.dims = (Dl, din, r_shard.shape[0], dout, Dlp, r_shard.shape[2], P)
+        cplx = lfull.dtype.is_complex or r_shard.dtype.is_complex or w.dtype.is_complex
+        self.dtype = torch.complex128 if cplx else torch.float64
+        lfull = lfull.to(self.dtype).contiguous()
+        self.r_shard = r_shard.to(self.dtype).contiguous()
+        # W3[(s, kappa_loc, s'), k] = w[k, s', s, kappa] on this rank's zero-padded kappa range
+        q0, q1 = self.rank * P, min((self.rank + 1) * P, cr)
+        w3 = torch.zeros((din, P, dout, cl), dtype=w.dtype, device=lfull.device)
+        if q1 > q0:
+            w3[:, :q1 - q0] = w[:, :, :, q0:q1].permute(2, 3, 1, 0)
+        lw = torch.empty((Dl, din * P * dout, Dlp), dtype=self.dtype, device=lfull.device)
+        self.ops.precontract(w3.reshape(din * P * dout, cl).contiguous(), lfull, lw)
+        self.lw = lw.reshape(Dl * din * P, dout, Dlp)          # [(i, s, kappa_loc), s', i']
+        self._t1 = None
+
+    def matvec(self, a):
+        """out[i',s',j'] (full, identical on every rank) = L.W.A.R applied to a (Dl, d, Dr)."""
+        Dl, d, Dr, dout, Dlp, Drp, P = self.dims
+        a = a.to(self.dtype).contiguous()
+        if self._t1 is None:
+            self._t1 = torch.empty((Dl * d, P * Drp), dtype=self.dtype, device=a.device)
+        self.ops.step1(a.reshape(Dl * d, Dr), self.r_shard.reshape(Dr, P * Drp), self._t1)
+        out = torch.empty((Dlp, dout, Drp), dtype=self.dtype, device=a.device)
+        self.ops.contract_lw(self.lw, self._t1.reshape(Dl * d * P, Drp), out)
+        if self.world > 1:
+            dist.all_reduce(_flat_real(out), op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def next_env_shard(self, a, b=None):
+        """This rank's range of the next block:  l_next[j, kappa, j'] = sum l[i,k,i'] conj(b[i',s',j'])
+        w[k,s',s,kappa] a[i,s,j]  (pytenet/chain_ops.py:60-99) for kappa in the rank's range; no communication."""
+        Dl, d, Dr, dout, Dlp, Drp, P = self.dims
+        b = a if b is None else b
+        a = a.to(self.dtype).contiguous()
+        # conj(b) with rows ordered (s', i') to match the column order of LW
+        b2 = dev.dense(b.to(self.dtype).permute(1, 0, 2)).reshape(dout * Dlp, b.shape[2])
+        x = torch.empty((Dl * d * P, b.shape[2]), dtype=self.dtype, device=a.device)
+        self.ops.env_x(self.lw.reshape(Dl * d * P, dout * Dlp), b2, x)           # X = LW conj(B)
+        nxt = torch.empty((Dr, P * b.shape[2]), dtype=self.dtype, device=a.device)
+        self.ops.step3(a.reshape(Dl * d, Dr), x.reshape(Dl * d, P * b.shape[2]), nxt)   # a^T X
+        return nxt.reshape(Dr, P, b.shape[2])
+
+
+def _ensure_env_ops(ops):
+    """The CUDA ops gain the conj-B GEMM used by the environment update."""
+    if not hasattr(ops, "env_x"):
+        def env_x(lw2d, b2, out):
+            return dev.gemm(lw2d, b2, conj_b=True, out=out)
+        ops.env_x = env_x
+    return ops
+
+
+def dmrg_singlesite_sharded(hamiltonian: MPO, psi: MPS, numsweeps: int, numiter_lanczos: int = 25, group=None,
+                            ops=None):
+    """
+    Single-site DMRG (same semantics and return value as `dmrg_singlesite`, pytenet/dmrg.py:22-93) with every
+    environment block sharded over its MPO-bond index across the ranks of `group`.  `psi` and `hamiltonian`
+    must be identical on all ranks; `psi` is updated in place (identically on every rank).
+    """
+    ops = _ensure_env_ops(ops if ops is not None else _CudaOps())
+    nsites = hamiltonian.nsites
+    assert nsites == psi.nsites
+    ham = hamiltonian.a
+    chi = hamiltonian.bond_dims
+    k = numiter_lanczos
+    psi.orthonormalize(mode="right")
+    device = psi.a[0].device
+    one = torch.ones((1, 1, 1), dtype=dev.F64, device=device)
+
+    # right blocks, right to left (chain_ops.py:102-113), each born sharded over bond i + 1
+    rshards = [None] * nsites
+    rshards[nsites - 1] = shard_env(one, group)
+    for i in reversed(range(nsites - 1)):
+        rfull = gather_env(rshards[i + 1], chi[i + 2], group)
+        # mirrored left form: "left-like" block = r_{i+1}, "right-like" = dummy; only the update is needed
+        site = ShardedSite(_mirror_w(ham[i + 1]), rfull, _dummy_right(psi.a[i + 1].shape[0], chi[i + 1], group,
+                                                                     rfull.dtype, device), group, ops)
+        rshards[i] = site.next_env_shard(_mirror_site(psi.a[i + 1]))
+    lshards = [None] * nsites
+    lshards[0] = shard_env(one, group)
+
+    def minimize(site, a_start, mirrored):
+        shape = tuple(a_start.shape)
+
+        def afunc(x):
+            t = x.reshape(shape)
+            if mirrored:
+                return _mirror_site(site.matvec(_mirror_site(t))).reshape(-1)
+            return site.matvec(t).reshape(-1)
+
+        ev, u = eigh_krylov(afunc, a_start.reshape(-1), k, 1)
+        return ev[0], dev.dense(u[:, 0]).reshape(shape)
+
+    en_min = np.zeros(numsweeps)
+    for n in range(numsweeps):
+        en = 0
+        for i in range(nsites - 1):                                            # dmrg.py:65-73
+            lfull = gather_env(lshards[i], chi[i], group)
+            site = ShardedSite(ham[i], lfull, rshards[i], group, ops)
+            en, psi.a[i] = minimize(site, psi.a[i], mirrored=False)
+            psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_local_orthonormalize_left_qr(
+                psi.a[i], psi.a[i + 1], psi.qsite, psi.qbonds[i:i + 2])
+            lshards[i + 1] = site.next_env_shard(psi.a[i])
+        for i in reversed(range(1, nsites)):                                   # dmrg.py:76-84
+            rfull = gather_env(rshards[i], chi[i + 1], group)
+            site = ShardedSite(_mirror_w(ham[i]), rfull, lshards[i], group, ops)
+            en, psi.a[i] = minimize(site, psi.a[i], mirrored=True)
+            psi.a[i], psi.a[i - 1], psi.qbonds[i] = mps_local_orthonormalize_right_qr(
+                psi.a[i], psi.a[i - 1], psi.qsite, psi.qbonds[i:i + 2])
+            rshards[i - 1] = site.next_env_shard(_mirror_site(psi.a[i]))
+        psi.a[0], _, psi.qbonds[0] = mps_local_orthonormalize_right_qr(psi.a[0], one, psi.qsite, psi.qbonds[:2])
+        en_min[n] = en
+    return en_min
+
+
+def _dummy_right(D, chi, group, dtype, device):
+    """Placeholder right-like shard of the correct shape for sites where only the environment update is used."""
+    world, _ = _world(group)
+    P = -(-chi // world)
+    return torch.zeros((D, P, D), dtype=dtype, device=device)

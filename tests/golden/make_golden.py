@@ -351,6 +351,37 @@ def basics_notebook_case():
     print("basics_notebook.npz: norm", nrm, "average", avg)
 
 
+def molecular_dmrg_case():
+    """BASELINE config 4 at CPU scale: molecular_hamiltonian_mpo from random symmetric integrals
+    (8 spin-less orbitals, optimize=False), dmrg_singlesite in the 4-particle sector."""
+    rng = np.random.default_rng(2026)
+    n = 8
+    tkin = rng.normal(size=(n, n)); tkin = 0.5 * (tkin + tkin.T)
+    vint = rng.normal(size=(n, n, n, n))
+    vint = 0.5 * (vint + vint.transpose(1, 0, 3, 2))
+    vint = 0.5 * (vint + vint.transpose(2, 3, 0, 1))
+    h = ptn.molecular_hamiltonian_mpo(tkin, vint, optimize=False)
+    assert np.allclose(h.to_matrix(), h.to_matrix().conj().T)
+    out = {}
+    save_mpo(out, "h", h)
+    psi = ptn.MPS.construct_random(n, h.qsite, 4, max_vdim=20, dtype="complex", rng=rng)
+    save_mps(out, "psi0", psi)
+    p = copy.deepcopy(psi); o = to_chain(psi)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        en = ptn.dmrg_singlesite(h, p, 3, numiter_lanczos=12)
+        en_o = osw.dmrg_singlesite(h.a, h.qbonds, o, 3, numiter_lanczos=12)
+    assert np.max(np.abs(en - en_o)) < 1e-10
+    hm = h.to_matrix()
+    nocc = np.array([bin(i).count("1") for i in range(2 ** n)])
+    sec = np.where(nocc == 4)[0]
+    e_ed = np.linalg.eigvalsh(hm[np.ix_(sec, sec)])[0]
+    out["single/en"] = en; out["ed_e0_sector"] = np.array(e_ed); out["k"] = np.array(12)
+    out["mpo_bond_dims"] = np.array(h.bond_dims)
+    np.savez_compressed(os.path.join(HERE, "dmrg_molecular_N8.npz"), **out)
+    print("dmrg_molecular_N8.npz: MPO bonds", h.bond_dims, "energies", en, "ED (sector)", e_ed)
+
+
 if __name__ == "__main__":
     chain_ops_cases()
     mpo_inner_case()
@@ -359,4 +390,5 @@ if __name__ == "__main__":
     tdvp_qnumber_case()
     dmrg_notebook_case()
     basics_notebook_case()
+    molecular_dmrg_case()
     print("all golden fixtures written to", HERE)

@@ -54,3 +54,31 @@ def test_precontracted_single_rank_matches_oracle(cuda_lib):
     x = torch.randn(64, 2, 64, dtype=torch.complex128, device="cuda")
     y = h.matvec(x)
     assert (torch.linalg.norm(h.matvec(3 * x) - 3 * y) / torch.linalg.norm(y)).item() < 1e-13
+
+
+def _load(ptb, z, tag, n):
+    return ptb.MPS.from_tensors(z[f"{tag}/qsite"], [z[f"{tag}/qb{i}"] for i in range(n + 1)],
+                                [z[f"{tag}/a{i}"] for i in range(n)])
+
+
+def test_sharded_dmrg_singlesite_molecular_fixture(cuda_lib, golden_dir):
+    """BASELINE config 4 at CPU scale: molecular_hamiltonian_mpo (8 orbitals, MPO bonds up to 46) built by the
+    reference, dmrg_singlesite energies from the reference -- through the unsharded device driver and through
+    the MPO-bond-sharded driver (one rank here; 2 and 8 ranks in tools/sharded_dmrg_check.py)."""
+    import os
+    import pytenet_b200 as ptb
+    from pytenet_b200.sharded_dmrg import dmrg_singlesite_sharded
+    z = np.load(os.path.join(golden_dir, "dmrg_molecular_N8.npz"))
+    n = int(z["h/nsites"])
+    h = ptb.MPO.from_tensors(z["h/qsite"], [z[f"h/qb{i}"] for i in range(n + 1)], [z[f"h/w{i}"] for i in range(n)])
+    assert h.bond_dims == list(z["mpo_bond_dims"])
+    psi = _load(ptb, z, "psi0", n)
+    en = ptb.dmrg_singlesite(h, psi, 3, numiter_lanczos=int(z["k"]))
+    assert np.max(np.abs(en - z["single/en"])) < 1e-10
+    assert abs(en[-1] - float(z["ed_e0_sector"])) < 1e-9
+    psi = _load(ptb, z, "psi0", n)
+    en_s = dmrg_singlesite_sharded(h, psi, 3, numiter_lanczos=int(z["k"]))
+    assert np.max(np.abs(en_s - z["single/en"])) < 1e-10
+    assert abs(np.linalg.norm(psi.to_vector()) - 1) < 1e-12
+    for i in range(n + 1):
+        assert len(psi.qbonds[i]) == psi.bond_dims[i]
