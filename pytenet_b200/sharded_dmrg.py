@@ -79,7 +79,7 @@ class ShardedSite:
     "right-like" block.  Serves the matvec and the environment update of one site.
     """
 
-    def __init__(self, w, lfull, r_shard, group=None, ops=None):
+    def __init__(self, w, lfull, r_shard, group=None, ops=None, cplx=None):
         self.group = group
         self.world, self.rank = _world(group)
         self.ops = ops if ops is not None else _CudaOps()
@@ -89,7 +89,8 @@ class ShardedSite:
         P = -(-cr // self.world)
         assert r_shard.shape[1] == P
         self.dims = (Dl, din, r_shard.shape[0], dout, Dlp, r_shard.shape[2], P)
-        cplx = lfull.dtype.is_complex or r_shard.dtype.is_complex or w.dtype.is_complex
+        # `cplx` = dtype of the state the site will act on (environments start as the real dummy block)
+        cplx = bool(cplx) or lfull.dtype.is_complex or r_shard.dtype.is_complex or w.dtype.is_complex
         self.dtype = torch.complex128 if cplx else torch.float64
         lfull = lfull.to(self.dtype).contiguous()
         self.r_shard = r_shard.to(self.dtype).contiguous()
@@ -153,6 +154,7 @@ def dmrg_singlesite_sharded(hamiltonian: MPO, psi: MPS, numsweeps: int, numiter_
     ham = hamiltonian.a
     chi = hamiltonian.bond_dims
     k = numiter_lanczos
+    cplx = any(t.dtype.is_complex for t in psi.a) or any(t.dtype.is_complex for t in ham)
     psi.orthonormalize(mode="right")
     device = psi.a[0].device
     one = torch.ones((1, 1, 1), dtype=dev.F64, device=device)
@@ -164,7 +166,7 @@ def dmrg_singlesite_sharded(hamiltonian: MPO, psi: MPS, numsweeps: int, numiter_
         rfull = gather_env(rshards[i + 1], chi[i + 2], group)
         # mirrored left form: "left-like" block = r_{i+1}, "right-like" = dummy; only the update is needed
         site = ShardedSite(_mirror_w(ham[i + 1]), rfull, _dummy_right(psi.a[i + 1].shape[0], chi[i + 1], group,
-                                                                     rfull.dtype, device), group, ops)
+                                                                     rfull.dtype, device), group, ops, cplx)
         rshards[i] = site.next_env_shard(_mirror_site(psi.a[i + 1]))
     lshards = [None] * nsites
     lshards[0] = shard_env(one, group)
@@ -186,14 +188,14 @@ def dmrg_singlesite_sharded(hamiltonian: MPO, psi: MPS, numsweeps: int, numiter_
         en = 0
         for i in range(nsites - 1):                                            # dmrg.py:65-73
             lfull = gather_env(lshards[i], chi[i], group)
-            site = ShardedSite(ham[i], lfull, rshards[i], group, ops)
+            site = ShardedSite(ham[i], lfull, rshards[i], group, ops, cplx)
             en, psi.a[i] = minimize(site, psi.a[i], mirrored=False)
             psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_local_orthonormalize_left_qr(
                 psi.a[i], psi.a[i + 1], psi.qsite, psi.qbonds[i:i + 2])
             lshards[i + 1] = site.next_env_shard(psi.a[i])
         for i in reversed(range(1, nsites)):                                   # dmrg.py:76-84
             rfull = gather_env(rshards[i], chi[i + 1], group)
-            site = ShardedSite(_mirror_w(ham[i]), rfull, lshards[i], group, ops)
+            site = ShardedSite(_mirror_w(ham[i]), rfull, lshards[i], group, ops, cplx)
             en, psi.a[i] = minimize(site, psi.a[i], mirrored=True)
             psi.a[i], psi.a[i - 1], psi.qbonds[i] = mps_local_orthonormalize_right_qr(
                 psi.a[i], psi.a[i - 1], psi.qsite, psi.qbonds[i:i + 2])
