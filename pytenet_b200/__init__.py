@@ -19,5 +19,8 @@ from .tdvp import *               # noqa: F401,F403
 from .dmrg import *               # noqa: F401,F403
 from .hamiltonian import *        # noqa: F401,F403
 from .metts import *              # noqa: F401,F403
+from .sectors import *            # noqa: F401,F403
+from .sharded import *            # noqa: F401,F403
+from .sharded_dmrg import *       # noqa: F401,F403
 
 __version__ = "0.1.0"
