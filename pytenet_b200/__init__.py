@@ -7,8 +7,7 @@ The public names mirror pytenet's flat namespace (pytenet/__init__.py:10-36) for
 the modules on that path.  All arithmetic runs in hand-written sm_100a CUDA
 kernels behind the C ABI of include/pytenet_b200.h; there is no CPU fallback.
 """
-from .qnumber import *            # noqa: F401,F403
-from .util import *               # noqa: F401,F403
+from .scalars import *            # noqa: F401,F403
 from .block_sparse_util import *  # noqa: F401,F403
 from .bond_ops import *           # noqa: F401,F403
 from .mps import *                # noqa: F401,F403

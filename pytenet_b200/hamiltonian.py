@@ -14,7 +14,7 @@ checkout.  MPO tensors produced by the reference itself can be wrapped with
 import numpy as np
 
 from .mpo import MPO
-from .qnumber import encode_quantum_number_pair
+from .scalars import encode_quantum_number_pair
 
 __all__ = ["heisenberg_xxz_1d_mpo", "ising_1d_mpo", "fermi_hubbard_1d_mpo"]
 

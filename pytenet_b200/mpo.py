@@ -27,7 +27,7 @@ class MPO:
         if isinstance(fill, (int, float, complex)) and not isinstance(fill, bool):
             host = [np.full((b[i], d, d, b[i + 1]), fill) for i in range(nsites)]
         elif fill in ("random", "random real"):
-            from .util import crandn
+            from .scalars import crandn
             rng = np.random.default_rng() if rng is None else rng
             draw = (lambda s: crandn(s, rng)) if fill == "random" else (lambda s: rng.normal(size=s))
             host = [draw((b[i], d, d, b[i + 1])) / np.sqrt(b[i] * d * b[i + 1]) for i in range(nsites)]

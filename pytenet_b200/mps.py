@@ -14,7 +14,7 @@ import torch
 from . import _device as dev
 from .block_sparse_util import qnumber_outer_sum, qnumber_flatten, is_qsparse, block_sparse_qr
 from .bond_ops import split_block_sparse_matrix_svd
-from .util import crandn
+from .scalars import crandn
 
 __all__ = ["MPS", "mps_merge_tensor_pair", "mps_split_tensor_svd",
            "mps_local_orthonormalize_left_qr", "mps_local_orthonormalize_right_qr"]
