@@ -106,6 +106,18 @@ def lanczos_scratch(device):
     return buf
 
 
+_side_streams = {}
+
+
+def side_stream(device):
+    """A second stream per device for copies that overlap compute (host-buffer entry points)."""
+    st = _side_streams.get(device.index)
+    if st is None:
+        st = torch.cuda.Stream(device)
+        _side_streams[device.index] = st
+    return st
+
+
 def release_workspaces():
     _workspaces.clear()
     _scratch.clear()

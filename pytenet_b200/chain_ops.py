@@ -45,6 +45,61 @@ def _finish(out, host_mode):
     return dev.to_host(out) if host_mode else out
 
 
+def _apply_local_hamiltonian_host(a, w, l, r):
+    """Host-buffer entry for large tensors: same three steps as the C entry point, issued one by one so
+    that the host->device copy of `l` (needed only by step 3) overlaps steps 1 and 2 on a second stream."""
+    lib = _lib.load()
+    device = dev.default_device()
+    for t, rk, nm in zip((a, w, l, r), (3, 4, 3, 3), "awlr"):
+        assert np.ndim(t) == rk, f"`{nm}` must be a rank-{rk} tensor"
+    main = torch.cuda.current_stream(device)
+    side = dev.side_stream(device)
+    ad, wd, rd = (dev.to_device(t, device) for t in (a, w, r))          # copy engine order: a, w, r, then l
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        ld = dev.to_device(l, device)
+        l_ready = torch.cuda.Event()
+        l_ready.record(side)
+    cplx = dev.any_complex(ad, wd, ld, rd)
+    ad = dev.as_dtype(ad, cplx); rd = dev.as_dtype(rd, cplx); wd = dev.dense(wd)
+    Dl, d, Dr = ad.shape
+    cl, dout, din, cr = wd.shape
+    assert din == d and ld.shape[0] == Dl and ld.shape[1] == cl, "shape mismatch between a, w and l"
+    assert rd.shape[0] == Dr and rd.shape[1] == cr, "shape mismatch between a, w and r"
+    Dlp, Drp = ld.shape[2], rd.shape[2]
+    dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
+    es = 16 if cplx else 8
+    t1 = torch.empty((Dl * d, cr * Drp), dtype=ad.dtype, device=device)
+    t2 = torch.empty((Dl, cl * dout, Drp), dtype=ad.dtype, device=device)
+    dev.gemm(ad.reshape(Dl * d, Dr), rd.reshape(Dr, cr * Drp), out=t1)                       # step 1
+    csr = dev.w_csr(wd) if (cplx or not wd.dtype.is_complex) else None
+    t1b = t1.reshape(Dl, d * cr, Drp)
+    if csr is not None:                                                                      # step 2
+        rowptr, col, val, _ = csr
+        _lib.check(lib.ptb_wapply_csr(dt, int(wd.dtype.is_complex), cl * dout, d * cr, Drp, rowptr.data_ptr(),
+                                      col.data_ptr(), val.data_ptr(), t1b.data_ptr(), t2.data_ptr(), Dl,
+                                      dev.stream_ptr(device)), "ptb_wapply_csr")
+    elif cplx and not wd.dtype.is_complex:
+        dev.gemm_strided(False, 0, 0, 0, cl * dout, 2 * Drp, d * cr, wd, d * cr, torch.view_as_real(t1b), 2 * Drp,
+                         torch.view_as_real(t2), 2 * Drp, Dl, 0, 2 * d * cr * Drp, 2 * cl * dout * Drp)
+    else:
+        dev.gemm_strided(cplx, 0, 0, 0, cl * dout, Drp, d * cr, dev.as_dtype(wd, cplx), d * cr, t1b, Drp, t2, Drp,
+                         Dl, 0, d * cr * Drp, cl * dout * Drp)
+    main.wait_event(l_ready)
+    ld = dev.as_dtype(ld, cplx)
+    ld.record_stream(main)
+    out = torch.empty((Dlp, dout, Drp), dtype=ad.dtype, device=device)
+    ws = dev.workspace(8 * Dlp * dout * Drp * es, device, tag="splitk")
+    st = lib.ptb_gemm_splitk(dt, 1, 0, 0, Dlp, dout * Drp, Dl * cl, ld.data_ptr(), Dlp, t2.data_ptr(), dout * Drp,
+                             out.data_ptr(), dout * Drp, 1, 0, 0, 0, 0, 0, ws.data_ptr(), ws.numel(),
+                             dev.stream_ptr(device))                                         # step 3
+    _lib.check(st, "ptb_gemm_splitk")
+    return dev.to_host(out)
+
+
+_HOST_OVERLAP_MIN_BYTES = 32 << 20
+
+
 def apply_local_hamiltonian(a, w, l, r, out=None):
     r"""
     Apply a local Hamiltonian operator (pytenet/chain_ops.py:237-279)::
@@ -54,6 +109,9 @@ def apply_local_hamiltonian(a, w, l, r, out=None):
     `a` (Dl,d,Dr), `w` (chi_l,d_out,d_in,chi_r), `l` (Dl,chi_l,Dl'), `r` (Dr,chi_r,Dr').
     """
     lib = _lib.load()
+    if (out is None and all(isinstance(t, np.ndarray) for t in (a, w, l, r)) and np.ndim(l) == 3
+            and l.nbytes >= _HOST_OVERLAP_MIN_BYTES):
+        return _apply_local_hamiltonian_host(a, w, l, r)
     host_mode, device, cplx, (a, w, l, r) = _prep((a, w, l, r), (3, 4, 3, 3), "awlr")
     Dl, d, Dr = a.shape
     cl, dout, din, cr = w.shape

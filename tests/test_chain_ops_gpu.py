@@ -175,3 +175,20 @@ def test_sparse_and_dense_w_step_agree(cuda_lib):
     w = rnd(rng, (cl, d, d, cr), False); w[rng.random(w.shape) < 0.85] = 0
     got = ptb.apply_local_hamiltonian(cu(ar), cu(w), cu(lr), cu(rr)).cpu().numpy()
     assert got.dtype == np.float64 and rel(got, oracle.apply_local_hamiltonian(ar, w, lr, rr)) < TOL
+
+
+def test_host_entry_with_copy_overlap(cuda_lib):
+    """Large NumPy inputs take the host-buffer path that overlaps the copy of `l` with steps 1-2."""
+    import pytenet_b200 as ptb
+    from pytenet_b200 import chain_ops
+    rng = np.random.default_rng(17)
+    Dl, d, Dr, cl, cr = 160, 2, 150, 5, 4
+    a = rnd(rng, (Dl, d, Dr), True); l = rnd(rng, (Dl, cl, Dl), True); r = rnd(rng, (Dr, cr, Dr), True)
+    w = rnd(rng, (cl, d, d, cr), False); w[rng.random(w.shape) < 0.6] = 0
+    old = chain_ops._HOST_OVERLAP_MIN_BYTES
+    try:
+        chain_ops._HOST_OVERLAP_MIN_BYTES = 0
+        got = ptb.apply_local_hamiltonian(a, w, l, r)
+    finally:
+        chain_ops._HOST_OVERLAP_MIN_BYTES = old
+    assert isinstance(got, np.ndarray) and rel(got, oracle.apply_local_hamiltonian(a, w, l, r)) < TOL
