@@ -41,7 +41,10 @@ def to_device(x, device=None):
     if arr.dtype not in (np.float64, np.complex128):
         # the reference's dummy edge blocks are int64 [[[1]]] (chain_ops.py:110)
         arr = arr.astype(np.complex128 if np.iscomplexobj(arr) else np.float64)
-    return torch.from_numpy(np.ascontiguousarray(arr)).to(device or default_device())
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    # page-locked source (e.g. a NumPy view of a pinned buffer): stream-ordered DMA that overlaps with
+    # kernels of other streams; pageable memory is staged synchronously by the driver either way
+    return t.to(device or default_device(), non_blocking=t.is_pinned())
 
 
 def to_host(x):

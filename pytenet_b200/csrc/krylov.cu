@@ -83,14 +83,30 @@ __global__ void __launch_bounds__(RED_THREADS) sumsq_kernel(const double* __rest
     grid_sum_finish(acc, s, red, [=](double tot) { *out_sqrt = sqrt(tot); });
 }
 
-// ---- out = x * (1 / *scale) --------------------------------------------------------------
+// ---- out = x / *scale ------------------------------------------------------------------------
 __global__ void __launch_bounds__(RED_THREADS) scale_inv_kernel(const double* __restrict__ x, int64_t nd,
                                                                 const double* __restrict__ scale,
                                                                 double* __restrict__ out) {
     const double sc = *scale;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    // division (not multiplication by the reciprocal) to match v = w / beta (krylov.py:29,51)
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += stride) out[i] = x[i] / sc;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // division (not multiplication by the reciprocal) to match v = w / beta (krylov.py:29,51);
+    // 16-byte accesses, two independent pairs in flight per thread
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+    const int64_t npair = vec_ok ? nd / 2 : 0;
+    const double2* __restrict__ x2 = reinterpret_cast<const double2*>(x);
+    double2* __restrict__ o2 = reinterpret_cast<double2*>(out);
+    int64_t i = tid;
+    for (; i + stride < npair; i += 2 * stride) {
+        const double2 a = x2[i], b = x2[i + stride];
+        o2[i] = make_double2(a.x / sc, a.y / sc);
+        o2[i + stride] = make_double2(b.x / sc, b.y / sc);
+    }
+    if (i < npair) {
+        const double2 a = x2[i];
+        o2[i] = make_double2(a.x / sc, a.y / sc);
+    }
+    for (int64_t j = 2 * npair + tid; j < nd; j += stride) out[j] = x[j] / sc;
 }
 
 // ---- alpha = Re <w, v>  = sum over doubles of w_i v_i ------------------------------------
