@@ -438,6 +438,19 @@ def run_ours(args):
         mso = time_ms(lambda: ptb.apply_local_hamiltonian(ad, wd, ld, rd), reps=5)
         other.append({"shape": tag, "ms_per_matvec": mso, "gflops": f_alg(Do, do, chi) / mso / 1e6})
         del ad, wd, ld, rd
+    # the other three chain contractions at the one-site headline shape (2048, 2, 2048), chi = 5
+    ao, wo, lo, ro = host_inputs_onesite(D_HEAD, chi, seed=9)
+    ad, wd, ld, rd = (torch.from_numpy(x).to(device) for x in (ao, wo, lo, ro))
+    cd = ad[:, 0, :].contiguous()
+    f_env = f_alg(D_HEAD, 2, chi)
+    f_bond = 8.0 * 2 * chi * D_HEAD ** 3
+    other_ops = []
+    for name, fn, fl in [("contraction_operator_step_left", lambda: ptb.contraction_operator_step_left(ad, ad, wd, ld), f_env),
+                         ("contraction_operator_step_right", lambda: ptb.contraction_operator_step_right(ad, ad, wd, rd), f_env),
+                         ("apply_local_bond_contraction", lambda: ptb.apply_local_bond_contraction(cd, ld, rd), f_bond)]:
+        mso = time_ms(fn, reps=5)
+        other_ops.append({"op": name, "shape": "a (2048,2,2048), chi 5", "ms": mso, "gflops": fl / mso / 1e6})
+    del ad, wd, ld, rd, cd
     block_sparse = None
     if os.environ.get("PTB_BENCH_SKIP_SECTORS") != "1":
         block_sparse = block_sparse_block(torch, ptb, device, time_ms)
@@ -458,6 +471,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "sharded": sharded,
         "other_shapes": other,
+        "other_ops": other_ops,
         "block_sparse": block_sparse,
     }
     print(json.dumps(line))

@@ -82,9 +82,17 @@ int apply_w(bool w_cplx, int trans_w, int64_t rows_out, int64_t rows_in, int64_t
 // MAX_SPLIT copies of the output; used when the output has too few tiles to fill 148 SMs).
 constexpr int MAX_SPLIT = 8;
 
-size_t two_buffers(int dtype, int64_t n1, int64_t n2, int64_t nout = 0) {
+constexpr int FIRST_SPLIT = 4;                       // split factor budgeted for the first GEMM
+constexpr int64_t FIRST_SPLIT_MAX_ELEMS = 6 * 148 * 128 * 64;   // only when it has fewer than ~6 waves of tiles
+
+size_t two_buffers(int dtype, int64_t n1, int64_t n2, int64_t nout = 0, int64_t nfirst = 0) {
     const size_t es = dtype == PTB_COMPLEX128 ? 16 : 8;
-    return align16((size_t)n1 * es) + align16((size_t)n2 * es) + align16((size_t)nout * es * MAX_SPLIT);
+    size_t part = (size_t)nout * es * MAX_SPLIT;
+    if (nfirst > 0 && nfirst < FIRST_SPLIT_MAX_ELEMS) {
+        const size_t p1 = (size_t)nfirst * es * FIRST_SPLIT;
+        if (p1 > part) part = p1;
+    }
+    return align16((size_t)n1 * es) + align16((size_t)n2 * es) + align16(part);
 }
 
 template <bool CPLX>
@@ -104,7 +112,8 @@ int apply_local_hamiltonian_impl(const void* a, const void* w, bool w_cplx, cons
     const size_t part_bytes = ws_bytes - (size_t)(part - t1);
     int rc;
     // (1) t1[(i,s),(kappa,j')] = a[(i,s),j] r[j,(kappa,j')]                 chain_ops.py:273
-    rc = gemm<CPLX>(0, 0, 0, Dl * d, cr * Drp, Dr, a, Dr, r, cr * Drp, t1, cr * Drp, 1, 0, 0, 0, 0, st);
+    rc = gemm<CPLX>(0, 0, 0, Dl * d, cr * Drp, Dr, a, Dr, r, cr * Drp, t1, cr * Drp, 1, 0, 0, 0, 0, st, 0, part,
+                    part_bytes);
     if (rc) return rc;
     // (2) t2[i][(k,s'),j'] = w[(k,s'),(s,kappa)] t1[i][(s,kappa),j']        chain_ops.py:276
     rc = apply_w<CPLX>(w_cplx, 0, cl * dout, d * cr, d * cr, Drp, w, t1, t2, Dl, st);
@@ -132,7 +141,8 @@ int apply_local_hamiltonian_csr_impl(const void* a, const int32_t* w_rowptr, con
     char* t2 = t1 + align16(n1 * es);
     char* part = t2 + align16(n2 * es);
     const size_t part_bytes = ws_bytes - (size_t)(part - t1);
-    int rc = gemm<CPLX>(0, 0, 0, Dl * d, cr * Drp, Dr, a, Dr, r, cr * Drp, t1, cr * Drp, 1, 0, 0, 0, 0, st);
+    int rc = gemm<CPLX>(0, 0, 0, Dl * d, cr * Drp, Dr, a, Dr, r, cr * Drp, t1, cr * Drp, 1, 0, 0, 0, 0, st, 0, part,
+                        part_bytes);
     if (rc) return rc;
     rc = ptb_wapply_csr(CPLX ? PTB_COMPLEX128 : PTB_REAL64, w_cplx ? 1 : 0, cl * dout, d * cr, Drp, w_rowptr, w_col,
                         w_val, t1, t2, Dl, st);
@@ -335,7 +345,8 @@ int ptb_gemm_multicast(int dtype, int trans_a, int trans_b, int conj_b, int64_t 
 size_t ptb_apply_local_hamiltonian_workspace_bytes(int dtype, int64_t Dl, int64_t d_in, int64_t Dr, int64_t chi_l,
                                                    int64_t chi_r, int64_t d_out, int64_t Dlp, int64_t Drp) {
     (void)Dr;
-    return two_buffers(dtype, Dl * d_in * chi_r * Drp, Dl * chi_l * d_out * Drp, Dlp * d_out * Drp);
+    return two_buffers(dtype, Dl * d_in * chi_r * Drp, Dl * chi_l * d_out * Drp, Dlp * d_out * Drp,
+                       Dl * d_in * chi_r * Drp);
 }
 
 int ptb_apply_local_hamiltonian_z(const void* a, const void* w, int w_is_complex, const void* l, const void* r,

@@ -469,13 +469,13 @@ static int launch_ws_inst(const WsParams& p, const CUtensorMap& ta, const CUtens
 }
 
 // Split factor that fills the 148-SM persistent grid best: maximise units / (waves * SMs) over
-// S in {1..8}, keeping at least 8 k-tiles per unit.  Returns 1 when splitting does not help.
+// S in {1..8}, keeping at least 4 k-tiles (one pipeline depth) per unit.  Returns 1 when splitting does not help.
 static int choose_split_k(long long tiles, int KT, int num_sms = 148) {
     if (tiles >= 6LL * num_sms) return 1;
     double best_eff = 0.0;
     int best = 1;
     for (int sk = 1; sk <= 8; sk++) {
-        if (sk > 1 && KT / sk < 8) break;
+        if (sk > 1 && KT / sk < 4) break;
         const long long units = tiles * sk;
         const long long waves = (units + num_sms - 1) / num_sms;
         const double eff = (double)units / (double)(waves * num_sms);
