@@ -468,24 +468,32 @@ static int launch_ws_inst(const WsParams& p, const CUtensorMap& ta, const CUtens
     return PTB_OK;
 }
 
-// Split factor that fills the 148-SM persistent grid best: maximise units / (waves * SMs) over
-// S in {1..8}, keeping at least 4 k-tiles (one pipeline depth) per unit.  Returns 1 when splitting does not help.
-static int choose_split_k(long long tiles, int KT, int num_sms = 148) {
+// Split factor for the persistent grid.  Splitting K by S raises the wave efficiency
+// eff(S) = units / (waves * SMs) but costs S partial tiles written and read back (about 32 S bytes
+// per output element of a complex GEMM at HBM speed).  Per output element the time saved is
+// (8 K / peak) (1/eff(1) - 1/eff(S)); S is chosen to maximise the net gain and only accepted when
+// the saving is at least twice the extra traffic.  At least 4 k-tiles (one pipeline depth) per unit.
+static int choose_split_k(long long tiles, int KT, int K, int num_sms = 148) {
     if (tiles >= 6LL * num_sms) return 1;
-    double best_eff = 0.0;
-    int best = 1;
-    for (int sk = 1; sk <= 8; sk++) {
-        if (sk > 1 && KT / sk < 4) break;
+    const double flop_time = 8.0 * (double)K / 37.0e12;   // seconds per output element at the FP64 peak
+    const double byte_time = 32.0 / 6.0e12;               // write + read of one complex partial element
+    auto eff = [&](int sk) {
         const long long units = tiles * sk;
         const long long waves = (units + num_sms - 1) / num_sms;
-        const double eff = (double)units / (double)(waves * num_sms);
-        if (eff > best_eff + 0.02) { best_eff = eff; best = sk; }
+        return (double)units / (double)(waves * num_sms);
+    };
+    const double e1 = eff(1);
+    double best_net = 0.0;
+    int best = 1;
+    for (int sk = 2; sk <= 8; sk++) {
+        if (KT / sk < 4) break;
+        const double saved = flop_time * (1.0 / e1 - 1.0 / eff(sk));
+        const double cost = byte_time * sk;
+        if (saved > 2.0 * cost && saved - cost > best_net) { best_net = saved - cost; best = sk; }
     }
     return best;
 }
 
-// Returns PTB_OK when launched, 1 when the fast path does not apply (caller falls back to the
-// first-generation kernel), or an error status.
 template <bool CPLX>
 static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp, cudaStream_t stream,
                          int n_extra = 0, double* const* extra = nullptr, int split_k = 1, void* part_ws = nullptr,
@@ -522,7 +530,7 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     if (ktab != nullptr && (reinterpret_cast<uintptr_t>(ktab) % 8) != 0) return PTB_ERR_ALIGNMENT;
     if (split_k != 1 && n_extra == 0 && part_ws != nullptr && ktab == nullptr) {
         const int KT = (gp.K + Cfg::BK - 1) / Cfg::BK;
-        int sk = split_k > 1 ? split_k : choose_split_k((long long)p.tiles_m * p.tiles_n * p.batch, KT);
+        int sk = split_k > 1 ? split_k : choose_split_k((long long)p.tiles_m * p.tiles_n * p.batch, KT, gp.K);
         if (sk > KT) sk = KT;
         const size_t need = (size_t)p.batch * sk * p.M * p.N * E * 8;
         if (sk > 1 && need <= part_ws_bytes && al16(part_ws)) {

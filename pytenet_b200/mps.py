@@ -16,7 +16,7 @@ from .block_sparse_util import qnumber_outer_sum, qnumber_flatten, is_qsparse, b
 from .bond_ops import split_block_sparse_matrix_svd
 from .scalars import crandn
 
-__all__ = ["MPS", "mps_merge_tensor_pair", "mps_split_tensor_svd",
+__all__ = ["MPS", "mps_vdot", "mps_norm", "mps_merge_tensor_pair", "mps_split_tensor_svd",
            "mps_local_orthonormalize_left_qr", "mps_local_orthonormalize_right_qr"]
 
 
@@ -160,6 +160,33 @@ class MPS:
             psi = mps_merge_tensor_pair(psi, nxt)
         assert psi.ndim == 3 and psi.shape[0] == 1 and psi.shape[2] == 1
         return dev.to_host(psi.reshape(-1))
+
+
+def mps_vdot(chi: MPS, psi: MPS):
+    """
+    Scalar product `<chi | psi>` (complex conjugating `chi`), contracted from the right on the device
+    (pytenet/mps.py:430-448): per site `t <- sum a[i,s,j] t[j,j'] conj(b[i',s,j'])`, two GEMMs on the engine.
+    Returns a Python scalar.
+    """
+    assert psi.nsites == chi.nsites
+    if psi.nsites == 0:
+        return 0
+    last = psi.a[-1]
+    n = last.shape[2]
+    assert chi.a[-1].shape[2] == n
+    t = torch.eye(n, dtype=last.dtype, device=last.device)
+    for a, b in zip(reversed(psi.a), reversed(chi.a)):
+        dl, d, dr = a.shape
+        dlp, _, drp = b.shape
+        at = dev.gemm(a.reshape(dl * d, dr), t)                                   # [(i,s), j']
+        t = dev.gemm(at.reshape(dl, d * drp), b.reshape(dlp, d * drp), trans_b=True, conj_b=True)   # [i, i']
+    assert tuple(t.shape) == (1, 1)
+    return t.reshape(-1)[0].item()
+
+
+def mps_norm(psi: MPS):
+    """Standard L2 norm of a matrix product state (pytenet/mps.py:451-457)."""
+    return float(np.sqrt(np.real(mps_vdot(psi, psi))))
 
 
 def _left_multiply(m, t):

@@ -242,3 +242,19 @@ def test_sweeps_with_forced_sector_plans(cuda_lib, golden_dir, monkeypatch):
     psi = load_mps(ptb, z, "psi0", n)
     ptb.tdvp_singlesite(h, psi, complex(z["dt"]), int(z["nsteps"]), numiter_lanczos=5)
     assert rel(psi.to_vector(), z["single/vec"]) < 1e-9
+
+
+def test_mps_norm_and_vdot(cuda_lib, golden_dir):
+    """doc/basics.ipynb:256 (norm of the seed-42 random MPS) and reference test_chain_ops.py:5-29 pattern."""
+    import pytenet_b200 as ptb
+    z = np.load(os.path.join(golden_dir, "basics_notebook.npz"))
+    h, n = load_mpo(ptb, z)
+    psi = load_mps(ptb, z, "psi0", n)
+    assert abs(ptb.mps_norm(psi) - 0.008359386283800499) < 1e-16
+    z = np.load(os.path.join(golden_dir, "mpo_inner.npz"))
+    n = int(z["nsites"])
+    rng = np.random.default_rng(2)
+    qd = np.zeros(3, dtype=int)
+    a = ptb.MPS(qd, [np.zeros(b, int) for b in [1, 4, 9, 7, 3, 1]], fill="random", rng=rng)
+    b = ptb.MPS(qd, [np.zeros(b, int) for b in [1, 3, 8, 5, 2, 1]], fill="random", rng=rng)
+    assert abs(ptb.mps_vdot(b, a) - np.vdot(b.to_vector(), a.to_vector())) < 1e-15
