@@ -72,6 +72,12 @@ struct WsParams {
     // partial tiles to Cpart ([batch][split][M][N], dense); a second kernel sums them in fixed order
     int split_k;
     double* Cpart;
+    // tail splitting: the tiles of the last, partially filled wave (tile index >= tail_begin) are each
+    // computed by `tail_split` work units over disjoint k ranges, so the wave finishes in 1/tail_split
+    // of a tile time; partial tiles go to Cpart as dense [unit][BM][BN] buffers and are summed in fixed
+    // order by a second kernel.  tail_split == 1 disables it.
+    int tail_split;
+    long long tail_begin;
     // sector-banded GEMM: per (batch, tile) range [lo, hi) of k-tiles that can be non-zero given the
     // quantum-number sectors of the operands (nullptr = full range); hi <= lo skips the tile's main loop
     const int2* ktab;
@@ -158,6 +164,53 @@ __device__ __forceinline__ uint32_t producer_operand(bool issue, double* stage, 
     }
 }
 
+// Work unit -> (tile, k-split index, number of splits, kind of destination)
+struct WsUnit {
+    long long tile;   // global tile index (batch-major)
+    int sk, nsplit;   // this unit covers k-tiles [KT*sk/nsplit, KT*(sk+1)/nsplit)
+    int dest;         // 0 = C, 1 = full-matrix split-K partial, 2 = tail tile buffer
+    long long slot;   // tile-buffer index for dest == 2
+};
+
+__device__ __forceinline__ WsUnit ws_decode_unit(const WsParams& p, long long u) {
+    WsUnit w;
+    if (p.split_k > 1) {
+        w.tile = u / p.split_k;
+        w.sk = (int)(u - w.tile * p.split_k);
+        w.nsplit = p.split_k;
+        w.dest = 1;
+        w.slot = 0;
+    } else if (p.tail_split > 1 && u >= p.tail_begin) {
+        const long long v = u - p.tail_begin;
+        w.tile = p.tail_begin + v / p.tail_split;
+        w.sk = (int)(v % p.tail_split);
+        w.nsplit = p.tail_split;
+        w.dest = 2;
+        w.slot = v;
+    } else {
+        w.tile = u;
+        w.sk = 0;
+        w.nsplit = 1;
+        w.dest = 0;
+        w.slot = 0;
+    }
+    return w;
+}
+
+// tile index -> (batch, tile row, tile column) in the grouped order (GROUP tile rows share B panels in L2)
+__device__ __forceinline__ void ws_tile_coords(const WsParams& p, long long t, int& bz, int& tm, int& tn) {
+    constexpr int GROUP = 8;
+    const int tiles_per_batch = p.tiles_m * p.tiles_n;
+    bz = (int)(t / tiles_per_batch);
+    const int tile = (int)(t - (long long)bz * tiles_per_batch);
+    const int per_group = GROUP * p.tiles_n;
+    const int grp = tile / per_group;
+    const int first_m = grp * GROUP;
+    const int gsize = min(p.tiles_m - first_m, GROUP);
+    tm = first_m + (tile % per_group) % gsize;
+    tn = (tile % per_group) / gsize;
+}
+
 template <bool CPLX, bool A_KC, bool B_KC, bool CONJB>
 __global__ void __launch_bounds__(WsCfg<CPLX>::THREADS, 1)
 gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
@@ -188,10 +241,10 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
 
     const int KT_all = (p.K + BK - 1) / BK;
     const int tiles_per_batch = p.tiles_m * p.tiles_n;
-    const int SK = p.split_k;
-    const long long total = (long long)tiles_per_batch * p.batch * SK;
-    constexpr int GROUP = 8;
-    const int per_group = GROUP * p.tiles_n;
+    const long long total_tiles = (long long)tiles_per_batch * p.batch;
+    const long long total = p.split_k > 1 ? total_tiles * p.split_k
+                          : (p.tail_split > 1 ? p.tail_begin + (total_tiles - p.tail_begin) * p.tail_split
+                                              : total_tiles);
 
     int stage = 0;
     uint32_t phase = 0;
@@ -201,17 +254,11 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(Cfg::PRODUCER_REGS));
         if (warp != Cfg::CONSUMER_WARPS) return;
         for (long long u = blockIdx.x; u < total; u += gridDim.x) {
-            const long long t = u / SK;
-            const int sk = (int)(u - t * SK);
-            int kt_begin = (int)(((long long)KT_all * sk) / SK);
-            int kt_end = (int)(((long long)KT_all * (sk + 1)) / SK);
-            const int bz = (int)(t / tiles_per_batch);
-            const int tile = (int)(t - (long long)bz * tiles_per_batch);
-            const int grp = tile / per_group;
-            const int first_m = grp * GROUP;
-            const int gsize = min(p.tiles_m - first_m, GROUP);
-            const int tm = first_m + (tile % per_group) % gsize;
-            const int tn = (tile % per_group) / gsize;
+            const WsUnit un = ws_decode_unit(p, u);
+            int kt_begin = (int)(((long long)KT_all * un.sk) / un.nsplit);
+            int kt_end = (int)(((long long)KT_all * (un.sk + 1)) / un.nsplit);
+            int bz, tm, tn;
+            ws_tile_coords(p, un.tile, bz, tm, tn);
             const int m0 = tm * BM, n0 = tn * BN;
             if (p.ktab != nullptr) {
                 const int2 kr = p.ktab[(long long)bz * tiles_per_batch + (long long)tm * p.tiles_n + tn];
@@ -259,17 +306,11 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
     constexpr int B_NT = B_KC ? 8 * 4 * E : 8 * E;
 
     for (long long u = blockIdx.x; u < total; u += gridDim.x) {
-        const long long t = u / SK;
-        const int sk = (int)(u - t * SK);
-        int kt_begin = (int)(((long long)KT_all * sk) / SK);
-        int kt_end = (int)(((long long)KT_all * (sk + 1)) / SK);
-        const int bz = (int)(t / tiles_per_batch);
-        const int tile = (int)(t - (long long)bz * tiles_per_batch);
-        const int grp = tile / per_group;
-        const int first_m = grp * GROUP;
-        const int gsize = min(p.tiles_m - first_m, GROUP);
-        const int tm = first_m + (tile % per_group) % gsize;
-        const int tn = (tile % per_group) / gsize;
+        const WsUnit un = ws_decode_unit(p, u);
+        int kt_begin = (int)(((long long)KT_all * un.sk) / un.nsplit);
+        int kt_end = (int)(((long long)KT_all * (un.sk + 1)) / un.nsplit);
+        int bz, tm, tn;
+        ws_tile_coords(p, un.tile, bz, tm, tn);
         const int m0 = tm * BM, n0 = tn * BN;
         if (p.ktab != nullptr) {
             const int2 kr = p.ktab[(long long)bz * tiles_per_batch + (long long)tm * p.tiles_n + tn];
@@ -330,12 +371,33 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
 
         // epilogue (overlaps the producer's prefetch of the next tile); with n_extra > 0 the tile is
         // also written to the peer GPUs' buffers (compute + all-gather in one kernel)
-        const bool partial = SK > 1;
+        if (un.dest == 2) {
+            // tail unit: the whole BM x BN partial tile goes to its dense buffer (no bounds: the reduction
+            // kernel only reads the in-range part)
+            double* __restrict__ Tb = p.Cpart + un.slot * (long long)(BM * BN * E);
+#pragma unroll
+            for (int i = 0; i < MT; i++) {
+                const int row = wm * Cfg::WTM + i * 8 + g;
+#pragma unroll
+                for (int j = 0; j < NT; j++) {
+                    const int col = wn * Cfg::WTN + j * 8 + 2 * q;
+                    if constexpr (CPLX) {
+                        double2* dst = reinterpret_cast<double2*>(Tb + ((int64_t)row * BN + col) * 2);
+                        dst[0] = make_double2(acc[i][j][0], acc[i][j][2]);
+                        dst[1] = make_double2(acc[i][j][1], acc[i][j][3]);
+                    } else {
+                        *reinterpret_cast<double2*>(Tb + (int64_t)row * BN + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    }
+                }
+            }
+            continue;
+        }
+        const bool partial = un.dest == 1;
         const int64_t ldc_eff = partial ? (int64_t)p.N : p.ldc;
         const bool accum = !partial && p.accumulate;
         for (int dsti = 0; dsti <= p.n_extra; dsti++) {
             double* __restrict__ Cg =
-                partial ? p.Cpart + ((int64_t)bz * SK + sk) * (int64_t)p.M * p.N * E
+                partial ? p.Cpart + ((int64_t)bz * p.split_k + un.sk) * (int64_t)p.M * p.N * E
                         : (dsti == 0 ? p.C : p.Cx[dsti - 1]) + (int64_t)bz * p.sC * E;
 #pragma unroll
             for (int i = 0; i < MT; i++) {
@@ -372,6 +434,29 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
                 }
             }
         }
+    }
+}
+
+// Sum the tail-unit partial tiles in fixed order and store them at their place in C.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) tail_reduce_kernel(const WsParams p) {
+    using Cfg = WsCfg<CPLX>;
+    constexpr int E = Cfg::E, BM = Cfg::BM, BN = Cfg::BN;
+    const long long t = p.tail_begin + blockIdx.x;
+    int bz, tm, tn;
+    ws_tile_coords(p, t, bz, tm, tn);
+    const int m0 = tm * BM, n0 = tn * BN;
+    const double* __restrict__ src = p.Cpart + (long long)blockIdx.x * p.tail_split * (BM * BN * E);
+    double* __restrict__ Cg = p.C + (int64_t)bz * p.sC * E;
+    for (int idx = threadIdx.x; idx < BM * BN * E; idx += blockDim.x) {
+        const int row = idx / (BN * E);
+        const int cd = idx - row * (BN * E);          // column in doubles
+        if (m0 + row >= p.M || n0 * E + cd >= p.N * E) continue;
+        double acc = 0.0;
+        for (int sidx = 0; sidx < p.tail_split; sidx++) acc += src[(long long)sidx * (BM * BN * E) + idx];
+        double* dst = Cg + ((int64_t)(m0 + row) * p.ldc + n0) * E + cd;
+        if (p.accumulate) acc += *dst;
+        *dst = acc;
     }
 }
 
@@ -451,10 +536,17 @@ static int launch_ws_inst(const WsParams& p, const CUtensorMap& ta, const CUtens
         PTB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid));
         configured = true;
     }
-    const long long total = (long long)p.tiles_m * p.tiles_n * p.batch * p.split_k;
+    const long long total_tiles = (long long)p.tiles_m * p.tiles_n * p.batch;
+    const long long total = p.split_k > 1 ? total_tiles * p.split_k
+                          : (p.tail_split > 1 ? p.tail_begin + (total_tiles - p.tail_begin) * p.tail_split
+                                              : total_tiles);
     const int grid = (int)(total < num_sms ? total : num_sms);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p, ta, tb);
     PTB_CUDA_TRY(cudaGetLastError());
+    if (p.split_k == 1 && p.tail_split > 1) {
+        tail_reduce_kernel<CPLX><<<(unsigned)(total_tiles - p.tail_begin), 256, 0, stream>>>(p);
+        PTB_CUDA_TRY(cudaGetLastError());
+    }
     if (p.split_k > 1) {
         const int ND = p.N * Cfg::E;
         const int64_t per = (int64_t)p.M * ND;
@@ -526,6 +618,8 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     for (int i = 0; i < 7; i++) p.Cx[i] = nullptr;
     p.split_k = 1;
     p.Cpart = nullptr;
+    p.tail_split = 1;
+    p.tail_begin = 0;
     p.ktab = reinterpret_cast<const int2*>(ktab);
     if (ktab != nullptr && (reinterpret_cast<uintptr_t>(ktab) % 8) != 0) return PTB_ERR_ALIGNMENT;
     if (split_k != 1 && n_extra == 0 && part_ws != nullptr && ktab == nullptr) {
@@ -536,6 +630,25 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
         if (sk > 1 && need <= part_ws_bytes && al16(part_ws)) {
             p.split_k = sk;
             p.Cpart = static_cast<double*>(part_ws);
+        }
+        // no global split: split only the tiles of the last, partially filled wave
+        if (p.split_k == 1 && split_k == 0 && al16(part_ws)) {
+            int num_sms = 148;
+            int devid = 0;
+            if (cudaGetDevice(&devid) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid);
+            const long long total_tiles = (long long)p.tiles_m * p.tiles_n * p.batch;
+            const long long tail = total_tiles % num_sms;
+            if (total_tiles > num_sms && tail > 0 && tail <= num_sms / 2) {
+                int ts = (int)(num_sms / tail);
+                if (ts > KT / 4) ts = KT / 4;
+                if (ts > 16) ts = 16;
+                const size_t need_tail = (size_t)tail * ts * Cfg::BM * Cfg::BN * E * 8;
+                if (ts >= 2 && need_tail <= part_ws_bytes) {
+                    p.tail_split = ts;
+                    p.tail_begin = total_tiles - tail;
+                    p.Cpart = static_cast<double*>(part_ws);
+                }
+            }
         }
     }
     if (n_extra > 0) {

@@ -125,7 +125,10 @@ def test_gemm_split_k(cuda_lib, cplx):
     lib = cuda_lib
     for (M, N, K, batch, split, acc, ta) in [(130, 70, 1000, 1, 2, False, 0), (128, 64, 777, 1, 3, True, 1),
                                              (256, 128, 4096, 2, 4, False, 1), (100, 60, 2048, 1, 0, False, 1),
-                                             (64, 64, 50, 1, 8, False, 0)]:
+                                             (64, 64, 50, 1, 8, False, 0),
+                                             # > 148 tiles with a small last wave: tail splitting (auto mode)
+                                             (1664, 768, 512, 1, 0, False, 0), (1600, 700, 300, 1, 0, True, 1),
+                                             (640, 520, 200, 3, 0, False, 1)]:
         A = rnd(rng, (batch, K, M) if ta else (batch, M, K), cplx)
         B = rnd(rng, (batch, K, N), cplx)
         C0 = rnd(rng, (batch, M, N), cplx)
