@@ -126,6 +126,9 @@ def release_workspaces():
     _scratch.clear()
 
 
+_GEMM_SCRATCH_BYTES = 32 << 20
+
+
 def gemm(a, b, trans_a=False, trans_b=False, conj_b=False, out=None):
     """2-D GEMM through the DMMA engine on contiguous device matrices.
 
@@ -146,10 +149,13 @@ def gemm(a, b, trans_a=False, trans_b=False, conj_b=False, out=None):
         return out
     if k == 0:
         return out.zero_()
-    st = lib.ptb_gemm(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, int(trans_a), int(trans_b), int(conj_b),
-                      m, n, k, a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], out.data_ptr(), n,
-                      1, 0, 0, 0, 0, stream_ptr(a.device))
-    _lib.check(st, "ptb_gemm")
+    # a fixed 32 MB scratch lets the engine split K when the output has few tiles, and split the tiles of
+    # the last partial wave of large outputs (both deterministic; see csrc/gemm_ws.cuh)
+    ws = workspace(_GEMM_SCRATCH_BYTES, a.device, tag="gemm")
+    st = lib.ptb_gemm_splitk(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, int(trans_a), int(trans_b),
+                             int(conj_b), m, n, k, a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1],
+                             out.data_ptr(), n, 1, 0, 0, 0, 0, 0, ws.data_ptr(), ws.numel(), stream_ptr(a.device))
+    _lib.check(st, "ptb_gemm_splitk")
     return out
 
 
