@@ -32,7 +32,7 @@ from .mpo import MPO
 from .krylov import eigh_krylov
 from .sharded import _CudaOps, _flat_real
 
-__all__ = ["dmrg_singlesite_sharded", "ShardedSite", "shard_env", "gather_env"]
+__all__ = ["dmrg_singlesite_sharded", "tdvp_singlesite_sharded", "ShardedSite", "shard_env", "gather_env"]
 
 
 def _world(group):
@@ -210,3 +210,108 @@ def _dummy_right(D, chi, group, dtype, device):
     world, _ = _world(group)
     P = -(-chi // world)
     return torch.zeros((D, P, D), dtype=dtype, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# Single-site TDVP on the same sharded environments
+# ---------------------------------------------------------------------------------------------
+
+def _sharded_bond_matvec(c, l_shard, r_shard, ops, group):
+    """Zero-site matvec out[i',j'] = sum_k l[i,k,i'] c[i,j] r[j,k,j'] (pytenet/chain_ops.py:282-317) with both
+    blocks sharded over the SAME MPO bond: every rank contracts its range of k, one all-reduce sums them."""
+    Dl, P, Dlp = l_shard.shape
+    Dr, P2, Drp = r_shard.shape
+    assert P == P2
+    dt = torch.complex128 if (c.dtype.is_complex or l_shard.dtype.is_complex or r_shard.dtype.is_complex) \
+        else torch.float64
+    c = c.to(dt).contiguous()
+    t = torch.empty((Dl, P * Drp), dtype=dt, device=c.device)
+    ops.step1(c, r_shard.to(dt).reshape(Dr, P * Drp), t)                                  # t[i,(k,j')]
+    out = torch.empty((Dlp, Drp), dtype=dt, device=c.device)
+    ops.step3(l_shard.to(dt).reshape(Dl * P, Dlp), t.reshape(Dl * P, Drp), out)             # l^T t
+    world, _ = _world(group)
+    if world > 1:
+        dist.all_reduce(_flat_real(out), op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def tdvp_singlesite_sharded(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lanczos: int = 25, group=None,
+                            ops=None):
+    """
+    Symmetric single-site TDVP (same semantics and return value as `tdvp_singlesite`, pytenet/tdvp.py:26-118)
+    with every environment block sharded over its MPO-bond index across the ranks of `group`.  Site steps use
+    the precontracted left form (`ShardedSite`), bond steps contract the two shards of the shared bond and
+    all-reduce; the right-to-left half of the sweep runs on mirrored tensors.
+    """
+    from .krylov import expm_krylov
+    from .block_sparse_util import qnumber_flatten, block_sparse_qr
+    ops = _ensure_env_ops(ops if ops is not None else _CudaOps())
+    nsites = hamiltonian.nsites
+    assert nsites == psi.nsites
+    ham = hamiltonian.a
+    chi = hamiltonian.bond_dims
+    k = numiter_lanczos
+    nrm = psi.orthonormalize(mode="right")
+    device = psi.a[0].device
+    one = torch.ones((1, 1, 1), dtype=dev.F64, device=device)
+    cplx = True if isinstance(dt, complex) else (any(t.dtype.is_complex for t in psi.a)
+                                                 or any(t.dtype.is_complex for t in ham))
+
+    rshards = [None] * nsites
+    rshards[nsites - 1] = shard_env(one, group)
+    for i in reversed(range(nsites - 1)):
+        rfull = gather_env(rshards[i + 1], chi[i + 2], group)
+        site = ShardedSite(_mirror_w(ham[i + 1]), rfull, _dummy_right(psi.a[i + 1].shape[0], chi[i + 1], group,
+                                                                     rfull.dtype, device), group, ops, cplx)
+        rshards[i] = site.next_env_shard(_mirror_site(psi.a[i + 1]))
+    lshards = [None] * nsites
+    lshards[0] = shard_env(one, group)
+
+    def evolve_site(site, a, tau, mirrored):
+        shape = tuple(a.shape)
+
+        def afunc(x):
+            t = x.reshape(shape)
+            if mirrored:
+                return _mirror_site(site.matvec(_mirror_site(t))).reshape(-1)
+            return site.matvec(t).reshape(-1)
+
+        return expm_krylov(afunc, a.reshape(-1), -tau, k, hermitian=True).reshape(shape)
+
+    def evolve_bond(l_shard, r_shard, c, tau):
+        shape = tuple(c.shape)
+        return expm_krylov(lambda x: _sharded_bond_matvec(x.reshape(shape), l_shard, r_shard, ops, group).reshape(-1),
+                           c.reshape(-1), -tau, k, hermitian=True).reshape(shape)
+
+    for _ in range(numsteps):
+        for i in range(nsites - 1):                                            # tdvp.py:68-84
+            site = ShardedSite(ham[i], gather_env(lshards[i], chi[i], group), rshards[i], group, ops, cplx)
+            psi.a[i] = evolve_site(site, psi.a[i], 0.5 * dt, False)
+            b0, d, b1 = psi.a[i].shape
+            q, c, psi.qbonds[i + 1] = block_sparse_qr(
+                psi.a[i].reshape(b0 * d, b1), qnumber_flatten((psi.qbonds[i], psi.qsite)), psi.qbonds[i + 1])
+            psi.a[i] = dev.dense(q.reshape(b0, d, q.shape[1]))
+            lshards[i + 1] = site.next_env_shard(psi.a[i])
+            c = evolve_bond(lshards[i + 1], rshards[i], dev.dense(c), -0.5 * dt)
+            nxt = psi.a[i + 1]
+            psi.a[i + 1] = dev.gemm(c, nxt.reshape(nxt.shape[0], -1)).reshape((c.shape[0],) + tuple(nxt.shape[1:]))
+        i = nsites - 1                                                         # tdvp.py:87-89
+        site = ShardedSite(ham[i], gather_env(lshards[i], chi[i], group), rshards[i], group, ops, cplx)
+        psi.a[i] = evolve_site(site, psi.a[i], dt, False)
+        for i in reversed(range(1, nsites)):                                   # tdvp.py:92-115
+            at = dev.dense(psi.a[i].permute(2, 1, 0))
+            b1, d, b0 = at.shape
+            q, c, qbond = block_sparse_qr(
+                at.reshape(b1 * d, b0), qnumber_flatten((-psi.qbonds[i + 1], psi.qsite)), -psi.qbonds[i])
+            psi.qbonds[i] = -qbond
+            psi.a[i] = dev.dense(q.reshape(b1, d, q.shape[1]).permute(2, 1, 0))
+            site = ShardedSite(_mirror_w(ham[i]), gather_env(rshards[i], chi[i + 1], group), lshards[i], group, ops,
+                               cplx)
+            rshards[i - 1] = site.next_env_shard(_mirror_site(psi.a[i]))
+            c = evolve_bond(lshards[i], rshards[i - 1], dev.dense(c.T), -0.5 * dt)
+            prv = psi.a[i - 1]
+            psi.a[i - 1] = dev.gemm(prv.reshape(-1, prv.shape[2]), c).reshape(tuple(prv.shape[:2]) + (c.shape[1],))
+            site = ShardedSite(_mirror_w(ham[i - 1]), gather_env(rshards[i - 1], chi[i], group), lshards[i - 1],
+                               group, ops, cplx)
+            psi.a[i - 1] = evolve_site(site, psi.a[i - 1], 0.5 * dt, True)
+    return nrm

@@ -82,3 +82,23 @@ def test_sharded_dmrg_singlesite_molecular_fixture(cuda_lib, golden_dir):
     assert abs(np.linalg.norm(psi.to_vector()) - 1) < 1e-12
     for i in range(n + 1):
         assert len(psi.qbonds[i]) == psi.bond_dims[i]
+
+
+def test_sharded_tdvp_singlesite_matches_reference_fixture(cuda_lib, golden_dir):
+    """tdvp_singlesite_sharded (one rank) on the README config and on the quantum-number XXZ fixture:
+    same state vector as the reference's tdvp_singlesite."""
+    import os
+    import pytenet_b200 as ptb
+    from pytenet_b200.sharded_dmrg import tdvp_singlesite_sharded
+    for name, steps_key in (("tdvp_xxz_L10.npz", "nsteps"), ("tdvp_xxz_qnum_L8.npz", "nsteps")):
+        z = np.load(os.path.join(golden_dir, name))
+        n = int(z["h/nsites"])
+        h = ptb.MPO.from_tensors(z["h/qsite"], [z[f"h/qb{i}"] for i in range(n + 1)], [z[f"h/w{i}"] for i in range(n)])
+        psi = _load(ptb, z, "psi0", n)
+        k = int(z["k"]) if "k" in z else 5
+        nrm = tdvp_singlesite_sharded(h, psi, complex(z["dt"]), int(z[steps_key]), numiter_lanczos=k)
+        v = psi.to_vector()
+        ref = z["single/vec"]
+        assert np.linalg.norm(v - ref) / np.linalg.norm(ref) < 1e-9, name
+        if "single/nrm" in z:
+            assert abs(nrm - float(z["single/nrm"])) < 1e-12

@@ -41,5 +41,21 @@ if rank == 0:
     print(f"sharded dmrg_singlesite on {world} rank(s): energies {en}, max |E - E_reference| = {err:.2e}, "
           f"max psi drift across ranks = {drift:.2e}, MPO bonds {h.bond_dims}", flush=True)
 assert err < 1e-10 and drift < 1e-12
+# ---- sharded single-site TDVP on the README fixture (XXZ, chi = 5 split over the ranks) ----
+from pytenet_b200.sharded_dmrg import tdvp_singlesite_sharded
+z = np.load(os.path.join(ROOT, "tests", "golden", "tdvp_xxz_L10.npz"))
+n = int(z["h/nsites"])
+h = ptb.MPO.from_tensors(z["h/qsite"], [z[f"h/qb{i}"] for i in range(n + 1)], [z[f"h/w{i}"] for i in range(n)])
+psi = ptb.MPS.from_tensors(z["psi0/qsite"], [z[f"psi0/qb{i}"] for i in range(n + 1)], [z[f"psi0/a{i}"] for i in range(n)])
+tdvp_singlesite_sharded(h, psi, complex(z["dt"]), int(z["nsteps"]), numiter_lanczos=int(z["k"]))
+v = psi.to_vector()
+terr = float(np.linalg.norm(v - z["single/vec"]) / np.linalg.norm(z["single/vec"]))
+if world > 1:
+    t = torch.tensor([terr], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    terr = t.item()
+if rank == 0:
+    print(f"sharded tdvp_singlesite on {world} rank(s): rel. state error vs reference = {terr:.2e}", flush=True)
+assert terr < 1e-9
 if world > 1:
     dist.destroy_process_group()
