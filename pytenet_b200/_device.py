@@ -178,6 +178,30 @@ _csr_cache = {}
 _CSR_MAX_NNZ = 4096          # beyond this the dense GEMM W step is the better kernel
 
 
+def w_csr_from_host(w_host, device):
+    """CSR arrays on `device` built from a host (NumPy) MPO tensor; None when too dense for the sparse kernel."""
+    cl, dout, din, cr = w_host.shape
+    mat = np.ascontiguousarray(w_host).reshape(cl * dout, din * cr)
+    if mat.dtype not in (np.float64, np.complex128):
+        mat = mat.astype(np.complex128 if np.iscomplexobj(mat) else np.float64)
+    return _csr_arrays(mat, device)
+
+
+def _csr_arrays(mat, device):
+    rows, cols = np.nonzero(mat)
+    if len(rows) > _CSR_MAX_NNZ:
+        return None
+    rowptr = np.zeros(mat.shape[0] + 1, dtype=np.int32)
+    np.add.at(rowptr, rows + 1, 1)
+    rowptr = np.cumsum(rowptr, dtype=np.int64).astype(np.int32)
+    vals = np.ascontiguousarray(mat[rows, cols])
+    if len(rows) == 0:                           # all-zero MPO tensor: keep the arrays non-empty (non-null pointers)
+        cols = np.zeros(1, dtype=np.int64)
+        vals = np.zeros(1, dtype=mat.dtype)
+    return (torch.from_numpy(rowptr).to(device), torch.from_numpy(cols.astype(np.int32)).to(device),
+            torch.from_numpy(vals).to(device), len(rows))
+
+
 def w_csr(w):
     """(rowptr, col, val, nnz) device arrays of w reshaped to (chi_l*d_out) x (d_in*chi_r), or None when w
     is too dense / large for the sparse W kernel.  Built once per tensor (one small device->host copy of w)."""
@@ -187,18 +211,7 @@ def w_csr(w):
         return hit[0]
     cl, dout, din, cr = w.shape
     mat = w.detach().reshape(cl * dout, din * cr).cpu().numpy()
-    rows, cols = np.nonzero(mat)
-    result = None
-    if len(rows) <= _CSR_MAX_NNZ:
-        rowptr = np.zeros(cl * dout + 1, dtype=np.int32)
-        np.add.at(rowptr, rows + 1, 1)
-        rowptr = np.cumsum(rowptr, dtype=np.int64).astype(np.int32)
-        vals = np.ascontiguousarray(mat[rows, cols])
-        if len(rows) == 0:                       # all-zero MPO tensor: keep the arrays non-empty (non-null pointers)
-            cols = np.zeros(1, dtype=np.int64)
-            vals = np.zeros(1, dtype=mat.dtype)
-        result = (torch.from_numpy(rowptr).to(w.device), torch.from_numpy(cols.astype(np.int32)).to(w.device),
-                  torch.from_numpy(vals).to(w.device), len(rows))
+    result = _csr_arrays(mat, w.device)
     if len(_csr_cache) > 256:
         _csr_cache.clear()
     _csr_cache[key] = (result, w)           # keep `w` alive so the data_ptr key cannot be recycled

@@ -72,7 +72,7 @@ def _apply_local_hamiltonian_host(a, w, l, r):
     t1 = torch.empty((Dl * d, cr * Drp), dtype=ad.dtype, device=device)
     t2 = torch.empty((Dl, cl * dout, Drp), dtype=ad.dtype, device=device)
     dev.gemm(ad.reshape(Dl * d, Dr), rd.reshape(Dr, cr * Drp), out=t1)                       # step 1
-    csr = dev.w_csr(wd) if (cplx or not wd.dtype.is_complex) else None
+    csr = dev.w_csr_from_host(np.asarray(w), device) if (cplx or not wd.dtype.is_complex) else None
     t1b = t1.reshape(Dl, d * cr, Drp)
     if csr is not None:                                                                      # step 2
         rowptr, col, val, _ = csr
@@ -89,12 +89,27 @@ def _apply_local_hamiltonian_host(a, w, l, r):
     ld = dev.as_dtype(ld, cplx)
     ld.record_stream(main)
     out = torch.empty((Dlp, dout, Drp), dtype=ad.dtype, device=device)
+    host = torch.empty((Dlp, dout, Drp), dtype=ad.dtype, pin_memory=True)
     ws = dev.workspace(8 * Dlp * dout * Drp * es, device, tag="splitk")
-    st = lib.ptb_gemm_splitk(dt, 1, 0, 0, Dlp, dout * Drp, Dl * cl, ld.data_ptr(), Dlp, t2.data_ptr(), dout * Drp,
-                             out.data_ptr(), dout * Drp, 1, 0, 0, 0, 0, 0, ws.data_ptr(), ws.numel(),
-                             dev.stream_ptr(device))                                         # step 3
-    _lib.check(st, "ptb_gemm_splitk")
-    return dev.to_host(out)
+    # step 3 in two row blocks of `out`: the device->host copy of the first block overlaps the second GEMM
+    half = (Dlp // 2) if Dlp >= 256 else Dlp
+    for m0, m1 in ((0, half), (half, Dlp)):
+        if m1 <= m0:
+            continue
+        st = lib.ptb_gemm_splitk(dt, 1, 0, 0, m1 - m0, dout * Drp, Dl * cl, ld.data_ptr() + m0 * es, Dlp,
+                                 t2.data_ptr(), dout * Drp, out.data_ptr() + m0 * dout * Drp * es, dout * Drp,
+                                 1, 0, 0, 0, 0, 0, ws.data_ptr(), ws.numel(), dev.stream_ptr(device))
+        _lib.check(st, "ptb_gemm_splitk")
+        if m1 < Dlp:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                host[m0:m1].copy_(out[m0:m1], non_blocking=True)
+            out.record_stream(side)
+        else:
+            host[m0:m1].copy_(out[m0:m1], non_blocking=True)
+    side.synchronize()
+    main.synchronize()
+    return host.numpy()
 
 
 _HOST_OVERLAP_MIN_BYTES = 32 << 20

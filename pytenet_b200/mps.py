@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _device as dev
-from .block_sparse_util import qnumber_outer_sum, qnumber_flatten, is_qsparse, block_sparse_qr
+from .block_sparse_util import qnumber_outer_sum, qnumber_flatten, block_sparse_qr
 from .bond_ops import split_block_sparse_matrix_svd
 from .scalars import crandn
 

@@ -8,9 +8,6 @@ with Lanczos-based local exponentials.  Every tensor (state, environments,
 two-site MPO tensors, Lanczos vectors) stays on the GPU; per local problem one
 small device->host copy returns the Lanczos coefficients.
 """
-import numpy as np
-import torch
-
 from . import _device as dev
 from .mps import MPS, mps_merge_tensor_pair, mps_split_tensor_svd
 from .mpo import MPO, mpo_merge_tensor_pair
