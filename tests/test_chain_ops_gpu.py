@@ -192,3 +192,23 @@ def test_host_entry_with_copy_overlap(cuda_lib):
     finally:
         chain_ops._HOST_OVERLAP_MIN_BYTES = old
     assert isinstance(got, np.ndarray) and rel(got, oracle.apply_local_hamiltonian(a, w, l, r)) < TOL
+
+
+def test_config2_shape_direct_parity_with_oracle(cuda_lib):
+    """Direct parity at BASELINE config-2 size (two-site XXZ, a (1024,4,1024), l/r (1024,5,1024)): the device
+    matvec against the CPU oracle on the same seeded inputs (the oracle needs < 1 s here), 1e-12 relative."""
+    import pytenet_b200 as ptb
+    from bench import host_inputs
+    a, w, l, r = host_inputs(1024, 4, 5, seed=2026)
+    want = oracle.apply_local_hamiltonian(a, w, l, r)
+    got = ptb.apply_local_hamiltonian(cu(a), cu(w), cu(l), cu(r)).cpu().numpy()
+    assert rel(got, want) < TOL
+    # environment updates at the same size (single-site tensors)
+    a1 = a[:, :2, :].copy(); w1 = w[:, :2, :2, :].copy()
+    got = ptb.contraction_operator_step_left(cu(a1), cu(a1), cu(w1), cu(l)).cpu().numpy()
+    assert rel(got, oracle.contraction_operator_step_left(a1, a1, w1, l)) < TOL
+    got = ptb.contraction_operator_step_right(cu(a1), cu(a1), cu(w1), cu(r)).cpu().numpy()
+    assert rel(got, oracle.contraction_operator_step_right(a1, a1, w1, r)) < TOL
+    c = a[:, 0, :].copy()
+    got = ptb.apply_local_bond_contraction(cu(c), cu(l), cu(r)).cpu().numpy()
+    assert rel(got, oracle.apply_local_bond_contraction(c, l, r)) < TOL
