@@ -27,7 +27,7 @@ import torch
 from . import _lib
 from . import _device as dev
 
-__all__ = ["HeffSectorPlan", "tile_k_ranges"]
+__all__ = ["HeffSectorPlan", "EnvSectorPlan", "BondSectorPlan", "tile_k_ranges"]
 
 _EMPTY_LO = np.iinfo(np.int64).max
 _EMPTY_HI = -1
@@ -210,6 +210,207 @@ class HeffSectorPlan:
                                      out.data_ptr(), dout * Drp, dout, 0, Drp, Drp, 0 if first else 1,
                                      self.tab3[k].data_ptr(), stream)
             _lib.check(st, "ptb_gemm_banded(step 3)")
+            first = False
+        if first:
+            out.zero_()
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Environment updates and the zero-site (bond) contraction with the same work-list machinery
+# ---------------------------------------------------------------------------------------------
+
+def _banded(lib, dt, ta, tb, cj, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, batch, sa, sb, sc, acc, tab, stream,
+            what):
+    st = lib.ptb_gemm_banded(dt, ta, tb, cj, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, batch, sa, sb, sc,
+                             int(acc), tab.data_ptr(), stream)
+    _lib.check(st, what)
+
+
+def _active(tabs):
+    return bool(np.any(tabs[..., 1] > tabs[..., 0]))
+
+
+class EnvSectorPlan:
+    """
+    Sector work lists for `contraction_operator_step_left / _right` (pytenet/chain_ops.py:60-99, 16-57) with
+    a == b layouts (ket and bra bonds share quantum numbers, as in the sweeps).  Same conventions as
+    `HeffSectorPlan`; `ql`, `qr` are the bond quantum numbers of the site tensor, `qwl`, `qwr` of the MPO tensor.
+    """
+
+    def __init__(self, ql, qs, qr, qwl, qwr, cplx=True):
+        self.ql = np.asarray(ql, dtype=np.int64); self.qr = np.asarray(qr, dtype=np.int64)
+        self.qs = np.asarray(qs, dtype=np.int64)
+        self.qwl = np.asarray(qwl, dtype=np.int64); self.qwr = np.asarray(qwr, dtype=np.int64)
+        self.cplx = cplx
+        bm, bn, bk = _tile_shape(cplx)
+        Dl, d, Dr, cl, cr = len(self.ql), len(self.qs), len(self.qr), len(self.qwl), len(self.qwr)
+        self.dims = (Dl, d, Dr, cl, cr)
+        self.supported = cplx or (Dl % 2 == 0 and Dr % 2 == 0)
+        ql_, qr_, qs_, qwl_, qwr_ = self.ql, self.qr, self.qs, self.qwl, self.qwr
+        # ---- step_left ----
+        # (L1) per k, batch s':  t[i,k,s',j'] = sum_i' l[i,k,i'] conj(b[i',s',j'])      K index i' (left bond)
+        self.L1 = [np.ascontiguousarray(np.stack(
+            [tile_k_ranges(ql_ + qwl_[k], qr_ - qs_[sp], ql_, bm, bn, bk) for sp in range(d)])) for k in range(cl)]
+        # (L3) per s:  l_next[j,(K,j')] += sum_i a[i,s,j] t2[i,s,K,j']                   K index i
+        cols = (qr_[None, :] - qwr_[:, None]).reshape(-1)
+        self.L3 = [tile_k_ranges(qr_ - qs_[s], cols - qs_[s], ql_, bm, bn, bk)[None] for s in range(d)]
+        # ---- step_right ----
+        # (R1) batch s:  t1[i,s,(K,j')] = sum_j a[i,s,j] r[j,(K,j')]                      K index j
+        self.R1 = np.ascontiguousarray(np.stack(
+            [tile_k_ranges(ql_ + qs_[s], cols, qr_, bm, bn, bk) for s in range(d)]))
+        # (R3) per s', batch k:  r_next[i,k,i'] += sum_j' t2[i,k,s',j'] conj(b[i',s',j'])   K index j'
+        self.R3 = [np.ascontiguousarray(np.stack(
+            [tile_k_ranges(ql_ + qwl_[k] + qs_[sp], ql_ + qs_[sp], qr_, bm, bn, bk) for k in range(cl)]))
+            for sp in range(d)]
+        self._dev = None
+
+    def _upload(self, device):
+        if self._dev is None or self._dev[0] != device:
+            up = lambda t: torch.from_numpy(np.ascontiguousarray(t)).to(device)      # noqa: E731
+            self._dev = (device, [up(t) for t in self.L1], [up(t) for t in self.L3], up(self.R1),
+                         [up(t) for t in self.R3])
+        return self._dev[1:]
+
+    def _prep(self, a, w, env):
+        cplx = dev.any_complex(a, env, w)
+        assert cplx == self.cplx
+        a = dev.as_dtype(a, cplx); env = dev.as_dtype(env, cplx)
+        return cplx, a, dev.dense(w), env
+
+    def _w_step(self, lib, dt, cplx, w, transposed, tin, tout, nb, rows_out, rows_in, drp, stream):
+        """tout[i] = op(W) tin[i]; op = transpose for step_left (chain_ops.py:96)."""
+        wmat = w.reshape(w.shape[0] * w.shape[1], w.shape[2] * w.shape[3])
+        if transposed:
+            wmat = dev.dense(wmat.T)
+        w4 = wmat.reshape(1, rows_out, rows_in, 1)
+        csr = dev.w_csr(w4) if (cplx or not w.dtype.is_complex) else None
+        if csr is not None:
+            rowptr, col, val, _ = csr
+            _lib.check(lib.ptb_wapply_csr(dt, int(w.dtype.is_complex), rows_out, rows_in, drp, rowptr.data_ptr(),
+                                          col.data_ptr(), val.data_ptr(), tin.data_ptr(), tout.data_ptr(), nb,
+                                          stream), "ptb_wapply_csr")
+        elif cplx and not w.dtype.is_complex:
+            dev.gemm_strided(False, 0, 0, 0, rows_out, 2 * drp, rows_in, wmat, rows_in, torch.view_as_real(tin),
+                             2 * drp, torch.view_as_real(tout), 2 * drp, nb, 0, 2 * rows_in * drp, 2 * rows_out * drp)
+        else:
+            dev.gemm_strided(cplx, 0, 0, 0, rows_out, drp, rows_in, dev.as_dtype(wmat, cplx), rows_in, tin, drp,
+                             tout, drp, nb, 0, rows_in * drp, rows_out * drp)
+
+    def step_left(self, a, w, l):
+        """l_next[j,K,j'] = sum l[i,k,i'] conj(a[i',s',j']) w[k,s',s,K] a[i,s,j]."""
+        lib = _lib.load()
+        Dl, d, Dr, cl, cr = self.dims
+        cplx, a, w, l = self._prep(a, w, l)
+        if not self.supported:
+            from .chain_ops import contraction_operator_step_left
+            return contraction_operator_step_left(a, a, w, l)
+        L1, L3, _, _ = self._upload(a.device)
+        dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
+        es = 16 if cplx else 8
+        stream = dev.stream_ptr(a.device)
+        t = torch.zeros((Dl, cl * d, Dr), dtype=a.dtype, device=a.device)
+        t2 = torch.empty((Dl, d * cr, Dr), dtype=a.dtype, device=a.device)
+        for k in range(cl):                                                            # (L1)
+            if not _active(self.L1[k]):
+                continue
+            _banded(lib, dt, 0, 0, 1, Dl, Dr, Dl, l.data_ptr() + k * Dl * es, cl * Dl, a.data_ptr(), d * Dr,
+                    t.data_ptr() + k * d * Dr * es, cl * d * Dr, d, 0, Dr, Dr, False, L1[k], stream, "step_left(1)")
+        self._w_step(lib, dt, cplx, w, True, t, t2, Dl, d * cr, cl * d, Dr, stream)     # (L2)
+        out = torch.empty((Dr, cr, Dr), dtype=a.dtype, device=a.device)
+        first = True
+        for s in range(d):                                                             # (L3)
+            if not _active(self.L3[s]):
+                continue
+            _banded(lib, dt, 1, 0, 0, Dr, cr * Dr, Dl, a.data_ptr() + s * Dr * es, d * Dr,
+                    t2.data_ptr() + s * cr * Dr * es, d * cr * Dr, out.data_ptr(), cr * Dr, 1, 0, 0, 0, not first,
+                    L3[s], stream, "step_left(3)")
+            first = False
+        if first:
+            out.zero_()
+        return out
+
+    def step_right(self, a, w, r):
+        """r_next[i,k,i'] = sum a[i,s,j] r[j,K,j'] w[k,s',s,K] conj(a[i',s',j'])."""
+        lib = _lib.load()
+        Dl, d, Dr, cl, cr = self.dims
+        cplx, a, w, r = self._prep(a, w, r)
+        if not self.supported:
+            from .chain_ops import contraction_operator_step_right
+            return contraction_operator_step_right(a, a, w, r)
+        _, _, R1, R3 = self._upload(a.device)
+        dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
+        es = 16 if cplx else 8
+        stream = dev.stream_ptr(a.device)
+        t1 = torch.empty((Dl, d * cr, Dr), dtype=a.dtype, device=a.device)
+        t2 = torch.empty((Dl, cl * d, Dr), dtype=a.dtype, device=a.device)
+        _banded(lib, dt, 0, 0, 0, Dl, cr * Dr, Dr, a.data_ptr(), d * Dr, r.data_ptr(), cr * Dr, t1.data_ptr(),
+                d * cr * Dr, d, Dr, 0, cr * Dr, False, R1, stream, "step_right(1)")                       # (R1)
+        self._w_step(lib, dt, cplx, w, False, t1, t2, Dl, cl * d, d * cr, Dr, stream)                    # (R2)
+        out = torch.empty((Dl, cl, Dl), dtype=a.dtype, device=a.device)
+        first = True
+        for sp in range(d):                                                                              # (R3)
+            if not _active(self.R3[sp]):
+                continue
+            _banded(lib, dt, 0, 1, 1, Dl, Dl, Dr, t2.data_ptr() + sp * Dr * es, cl * d * Dr,
+                    a.data_ptr() + sp * Dr * es, d * Dr, out.data_ptr(), cl * Dl, cl, d * Dr, 0, Dl, not first,
+                    R3[sp], stream, "step_right(3)")
+            first = False
+        if first:
+            out.zero_()
+        return out
+
+
+class BondSectorPlan:
+    """Sector work lists for the zero-site contraction out[i',j'] = sum l[i,k,i'] c[i,j] r[j,k,j']
+    (pytenet/chain_ops.py:282-317).  `qbl` are the quantum numbers of the rows of `c` (and both bond legs of
+    `l`), `qbr` those of its columns (and of `r`); `c[i,j] != 0` only if `qbl[i] == qbr[j]`."""
+
+    def __init__(self, qbl, qbr, qw, cplx=True):
+        self.qbl = np.asarray(qbl, dtype=np.int64)
+        self.qbr = np.asarray(qbr, dtype=np.int64)
+        self.qw = np.asarray(qw, dtype=np.int64)
+        self.cplx = cplx
+        bm, bn, bk = _tile_shape(cplx)
+        Dl, Dr, chi = len(self.qbl), len(self.qbr), len(self.qw)
+        self.dims = (Dl, Dr, chi)
+        self.supported = cplx or (Dl % 2 == 0 and Dr % 2 == 0)
+        cols = (self.qbr[None, :] - self.qw[:, None]).reshape(-1)
+        # (1) t[i,(k,j')] = sum_j c[i,j] r[j,(k,j')]: row i needs qbr[j] = qbl[i]; column (k,j') needs qbr[j] = qbr[j'] - qw[k]
+        self.B1 = tile_k_ranges(self.qbl, cols, self.qbr, bm, bn, bk)[None]
+        # (2) per k: out[i',j'] += sum_i l[i,k,i'] t[i,k,j']: row i' needs qbl[i] = qbl[i'] - qw[k];
+        #     column j' needs qbl[i] = qbr[j'] - qw[k]
+        self.B2 = [tile_k_ranges(self.qbl - self.qw[k], self.qbr - self.qw[k], self.qbl, bm, bn, bk)[None]
+                   for k in range(chi)]
+        self._dev = None
+
+    def apply(self, c, l, r):
+        lib = _lib.load()
+        Dl, Dr, chi = self.dims
+        cplx = dev.any_complex(c, l, r)
+        assert cplx == self.cplx
+        c = dev.as_dtype(c, cplx); l = dev.as_dtype(l, cplx); r = dev.as_dtype(r, cplx)
+        assert tuple(c.shape) == (Dl, Dr) and tuple(l.shape) == (Dl, chi, Dl) and tuple(r.shape) == (Dr, chi, Dr)
+        if not self.supported:
+            from .chain_ops import apply_local_bond_contraction
+            return apply_local_bond_contraction(c, l, r)
+        if self._dev is None or self._dev[0] != c.device:
+            up = lambda t: torch.from_numpy(np.ascontiguousarray(t)).to(c.device)     # noqa: E731
+            self._dev = (c.device, up(self.B1), [up(t) for t in self.B2])
+        _, B1, B2 = self._dev
+        dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
+        es = 16 if cplx else 8
+        stream = dev.stream_ptr(c.device)
+        t = torch.empty((Dl, chi * Dr), dtype=c.dtype, device=c.device)
+        _banded(lib, dt, 0, 0, 0, Dl, chi * Dr, Dr, c.data_ptr(), Dr, r.data_ptr(), chi * Dr, t.data_ptr(), chi * Dr,
+                1, 0, 0, 0, False, B1, stream, "bond(1)")
+        out = torch.empty((Dl, Dr), dtype=c.dtype, device=c.device)
+        first = True
+        for k in range(chi):
+            if not _active(self.B2[k]):
+                continue
+            _banded(lib, dt, 1, 0, 0, Dl, Dr, Dl, l.data_ptr() + k * Dl * es, chi * Dl, t.data_ptr() + k * Dr * es,
+                    chi * Dr, out.data_ptr(), Dr, 1, 0, 0, 0, not first, B2[k], stream, "bond(2)")
             first = False
         if first:
             out.zero_()

@@ -258,3 +258,37 @@ def test_mps_norm_and_vdot(cuda_lib, golden_dir):
     a = ptb.MPS(qd, [np.zeros(b, int) for b in [1, 4, 9, 7, 3, 1]], fill="random", rng=rng)
     b = ptb.MPS(qd, [np.zeros(b, int) for b in [1, 3, 8, 5, 2, 1]], fill="random", rng=rng)
     assert abs(ptb.mps_vdot(b, a) - np.vdot(b.to_vector(), a.to_vector())) < 1e-15
+
+
+def test_sector_plans_for_environment_updates_and_bond_contraction(cuda_lib):
+    """EnvSectorPlan / BondSectorPlan against the oracle on block-sparse inputs (sorted and unsorted bonds)."""
+    import oracle
+    import oracle.blocksparse as ob
+    from pytenet_b200.sectors import EnvSectorPlan, BondSectorPlan
+    rng = np.random.default_rng(91)
+    cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()      # noqa: E731
+    for (Dl, d, Dr, cl, cr, sort) in [(260, 2, 300, 5, 5, True), (140, 4, 200, 6, 4, True), (150, 3, 131, 4, 5, False)]:
+        qs = rng.integers(-1, 2, size=d)
+        ql = rng.integers(-2, 3, size=Dl); qr = rng.integers(-2, 3, size=Dr)
+        if sort:
+            ql = np.sort(ql); qr = np.sort(qr)
+        qwl = rng.integers(-1, 2, size=cl); qwr = rng.integers(-1, 2, size=cr)
+        crand = lambda *s: rng.normal(size=s) + 1j * rng.normal(size=s)      # noqa: E731
+        a = crand(Dl, d, Dr); ob.enforce_qsparsity(a, [ql, qs, -qr])
+        l = crand(Dl, cl, Dl); ob.enforce_qsparsity(l, [ql, qwl, -ql])
+        r = crand(Dr, cr, Dr); ob.enforce_qsparsity(r, [qr, qwr, -qr])
+        w = rng.normal(size=(cl, d, d, cr)); ob.enforce_qsparsity(w, [qwl, qs, -qs, -qwr])
+        plan = EnvSectorPlan(ql, qs, qr, qwl, qwr, cplx=True)
+        got = plan.step_left(cu(a), cu(w), cu(l)).cpu().numpy()
+        assert rel(got, oracle.contraction_operator_step_left(a, a, w, l)) < 1e-12, ("left", Dl, d, Dr)
+        got = plan.step_right(cu(a), cu(w), cu(r)).cpu().numpy()
+        assert rel(got, oracle.contraction_operator_step_right(a, a, w, r)) < 1e-12, ("right", Dl, d, Dr)
+        # zero-site contraction between a bond of dimension Dl and its copy of dimension Dr
+        qbl = np.sort(rng.integers(-2, 3, size=Dl)) if sort else rng.integers(-2, 3, size=Dl)
+        qbr = np.sort(rng.integers(-2, 3, size=Dr)) if sort else rng.integers(-2, 3, size=Dr)
+        c = crand(Dl, Dr); ob.enforce_qsparsity(c, [qbl, -qbr])
+        lb = crand(Dl, cl, Dl); ob.enforce_qsparsity(lb, [qbl, qwl, -qbl])
+        rb = crand(Dr, cl, Dr); ob.enforce_qsparsity(rb, [qbr, qwl, -qbr])
+        bplan = BondSectorPlan(qbl, qbr, qwl, cplx=True)
+        got = bplan.apply(cu(c), cu(lb), cu(rb)).cpu().numpy()
+        assert rel(got, oracle.apply_local_bond_contraction(c, lb, rb)) < 1e-12, ("bond", Dl, Dr)
