@@ -349,7 +349,12 @@ def run_ours(args):
 
     # ---- end to end through the public API with HOST buffers: `e2e` ----
     e2e_steps = max(2, min(steps, 5))
-    ptb.apply_local_hamiltonian(a_h, w_h, l_h, r_h)            # warm pinned result pool
+    # warm-up: two results alive at once, as in the timed loop (`res` is rebound while the previous result still
+    # exists), so the page-locked result pool holds both buffers before the clock starts -- a cold cudaHostAlloc of
+    # 268 MB costs ~90 ms and is not part of the steady-state call
+    res = ptb.apply_local_hamiltonian(a_h, w_h, l_h, r_h)
+    for _ in range(2):
+        res = ptb.apply_local_hamiltonian(a_h, w_h, l_h, r_h)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

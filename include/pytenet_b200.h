@@ -132,6 +132,22 @@ int ptb_apply_local_hamiltonian_csr_d(const void* a, const int32_t* w_rowptr, co
                                       int64_t chi_l, int64_t chi_r, int64_t d_out, int64_t Dlp, int64_t Drp,
                                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Host-buffer form (the call a NumPy user of the reference makes): a, w, l, r and out are HOST pointers with
+ * the layouts above (page-locked memory gives full-speed DMA; pageable memory works, staged by the driver);
+ * `workspace` is DEVICE memory of at least ptb_apply_local_hamiltonian_host_workspace_bytes(...).  All state
+ * tensors have `dtype`; w is float64 unless w_is_complex.  Operands are copied in slices on internal copy
+ * streams so that the transfers overlap the three contraction steps: step 1 is sliced along its contraction
+ * index (strided 2-D copies of a, contiguous row blocks of r, accumulated), step 3 along the rows of out, which
+ * are copied back block by block.  Ordered after prior work on `stream`; SYNCHRONOUS: `out` is complete on
+ * return.  Sparse w (<= 4096 non-zeros) takes the CSR W step, otherwise the dense one. */
+size_t ptb_apply_local_hamiltonian_host_workspace_bytes(int dtype, int w_is_complex, int64_t Dl, int64_t d_in,
+                                                        int64_t Dr, int64_t chi_l, int64_t chi_r, int64_t d_out,
+                                                        int64_t Dlp, int64_t Drp);
+int ptb_apply_local_hamiltonian_host(int dtype, int w_is_complex, const void* a, const void* w, const void* l,
+                                     const void* r, void* out, int64_t Dl, int64_t d_in, int64_t Dr, int64_t chi_l,
+                                     int64_t chi_r, int64_t d_out, int64_t Dlp, int64_t Drp, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
 /* W step alone (pytenet/chain_ops.py:276, :52, :96):  t_out[b, m, n] = sum_c W[m, c] t_in[b, c, n],
  * W in CSR form (r_out rows), t_in (batch, r_in, n_cols), t_out (batch, r_out, n_cols) dense, dtype
  * t_dtype.  One pass over t_in and t_out: algorithmic bytes = elem_size (r_in + r_out) n_cols batch. */

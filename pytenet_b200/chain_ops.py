@@ -46,69 +46,33 @@ def _finish(out, host_mode):
 
 
 def _apply_local_hamiltonian_host(a, w, l, r):
-    """Host-buffer entry for large tensors: same three steps as the C entry point, issued one by one so
-    that the host->device copy of `l` (needed only by step 3) overlaps steps 1 and 2 on a second stream."""
+    """Host-buffer entry for large tensors: one call of the C ABI's host form (csrc/host_entry.cu), which moves
+    the operands in slices so that the PCIe copies overlap the three contraction steps.  The result lands in a
+    page-locked buffer from torch's caching host allocator and is returned as a fresh ndarray."""
     lib = _lib.load()
     device = dev.default_device()
     for t, rk, nm in zip((a, w, l, r), (3, 4, 3, 3), "awlr"):
         assert np.ndim(t) == rk, f"`{nm}` must be a rank-{rk} tensor"
-    main = torch.cuda.current_stream(device)
-    side = dev.side_stream(device)
-    ad, wd, rd = (dev.to_device(t, device) for t in (a, w, r))          # copy engine order: a, w, r, then l
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        ld = dev.to_device(l, device)
-        l_ready = torch.cuda.Event()
-        l_ready.record(side)
-    cplx = dev.any_complex(ad, wd, ld, rd)
-    ad = dev.as_dtype(ad, cplx); rd = dev.as_dtype(rd, cplx); wd = dev.dense(wd)
-    Dl, d, Dr = ad.shape
-    cl, dout, din, cr = wd.shape
-    assert din == d and ld.shape[0] == Dl and ld.shape[1] == cl, "shape mismatch between a, w and l"
-    assert rd.shape[0] == Dr and rd.shape[1] == cr, "shape mismatch between a, w and r"
-    Dlp, Drp = ld.shape[2], rd.shape[2]
+    cplx = any(np.iscomplexobj(t) for t in (a, l, r, w))
+    w_cplx = bool(np.iscomplexobj(w))
+    sdt = np.complex128 if cplx else np.float64
+    # no-ops for C-ordered arrays of the common dtype (the int64 dummy blocks of chain_ops.py:110 are promoted)
+    a, l, r = (np.ascontiguousarray(t, dtype=sdt) for t in (a, l, r))
+    w = np.ascontiguousarray(w, dtype=np.complex128 if w_cplx else np.float64)
+    Dl, d, Dr = a.shape
+    cl, dout, din, cr = w.shape
+    assert din == d and l.shape[0] == Dl and l.shape[1] == cl, "shape mismatch between a, w and l"
+    assert r.shape[0] == Dr and r.shape[1] == cr, "shape mismatch between a, w and r"
+    Dlp, Drp = l.shape[2], r.shape[2]
     dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
-    es = 16 if cplx else 8
-    t1 = torch.empty((Dl * d, cr * Drp), dtype=ad.dtype, device=device)
-    t2 = torch.empty((Dl, cl * dout, Drp), dtype=ad.dtype, device=device)
-    dev.gemm(ad.reshape(Dl * d, Dr), rd.reshape(Dr, cr * Drp), out=t1)                       # step 1
-    csr = dev.w_csr_from_host(np.asarray(w), device) if (cplx or not wd.dtype.is_complex) else None
-    t1b = t1.reshape(Dl, d * cr, Drp)
-    if csr is not None:                                                                      # step 2
-        rowptr, col, val, _ = csr
-        _lib.check(lib.ptb_wapply_csr(dt, int(wd.dtype.is_complex), cl * dout, d * cr, Drp, rowptr.data_ptr(),
-                                      col.data_ptr(), val.data_ptr(), t1b.data_ptr(), t2.data_ptr(), Dl,
-                                      dev.stream_ptr(device)), "ptb_wapply_csr")
-    elif cplx and not wd.dtype.is_complex:
-        dev.gemm_strided(False, 0, 0, 0, cl * dout, 2 * Drp, d * cr, wd, d * cr, torch.view_as_real(t1b), 2 * Drp,
-                         torch.view_as_real(t2), 2 * Drp, Dl, 0, 2 * d * cr * Drp, 2 * cl * dout * Drp)
-    else:
-        dev.gemm_strided(cplx, 0, 0, 0, cl * dout, Drp, d * cr, dev.as_dtype(wd, cplx), d * cr, t1b, Drp, t2, Drp,
-                         Dl, 0, d * cr * Drp, cl * dout * Drp)
-    main.wait_event(l_ready)
-    ld = dev.as_dtype(ld, cplx)
-    ld.record_stream(main)
-    out = torch.empty((Dlp, dout, Drp), dtype=ad.dtype, device=device)
-    host = torch.empty((Dlp, dout, Drp), dtype=ad.dtype, pin_memory=True)
-    ws = dev.workspace(8 * Dlp * dout * Drp * es, device, tag="splitk")
-    # step 3 in two row blocks of `out`: the device->host copy of the first block overlaps the second GEMM
-    half = (Dlp // 2) if Dlp >= 256 else Dlp
-    for m0, m1 in ((0, half), (half, Dlp)):
-        if m1 <= m0:
-            continue
-        st = lib.ptb_gemm_splitk(dt, 1, 0, 0, m1 - m0, dout * Drp, Dl * cl, ld.data_ptr() + m0 * es, Dlp,
-                                 t2.data_ptr(), dout * Drp, out.data_ptr() + m0 * dout * Drp * es, dout * Drp,
-                                 1, 0, 0, 0, 0, 0, ws.data_ptr(), ws.numel(), dev.stream_ptr(device))
-        _lib.check(st, "ptb_gemm_splitk")
-        if m1 < Dlp:
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                host[m0:m1].copy_(out[m0:m1], non_blocking=True)
-            out.record_stream(side)
-        else:
-            host[m0:m1].copy_(out[m0:m1], non_blocking=True)
-    side.synchronize()
-    main.synchronize()
+    dims = (Dl, d, Dr, cl, cr, dout, Dlp, Drp)
+    nbytes = lib.ptb_apply_local_hamiltonian_host_workspace_bytes(dt, int(w_cplx), *dims)
+    ws = dev.workspace(nbytes, device, tag="host")
+    host = torch.empty((Dlp, dout, Drp), dtype=dev.C128 if cplx else dev.F64, pin_memory=True)
+    st = lib.ptb_apply_local_hamiltonian_host(dt, int(w_cplx), a.ctypes.data, w.ctypes.data, l.ctypes.data,
+                                              r.ctypes.data, host.data_ptr(), *dims, ws.data_ptr(), nbytes,
+                                              dev.stream_ptr(device))
+    _lib.check(st, "apply_local_hamiltonian (host buffers)")
     return host.numpy()
 
 
