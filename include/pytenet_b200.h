@@ -227,6 +227,43 @@ int ptb_lanczos_alpha_z(int64_t n, const void* w, const void* v_j, double* alpha
 int ptb_krylov_combine(int v_dtype, int coeff_dtype, int64_t n, int64_t k, const void* v, int64_t ldv,
                        const void* coeff, void* out, void* stream);
 
+/* expm_krylov's k x k problem and the final combination, on the device (pytenet/krylov.py:122-136, :142-150):
+ *   out = V^T U (|vec| exp(dt w) * U[0, :]),  (w, U) = eigen-decomposition of tridiag(alpha, beta)
+ * `scal` is the [ |vec|, alpha[0..numiter), beta[0..numiter-1) ] array written by the Lanczos entry points;
+ * the breakdown rule of krylov.py:44-50 (beta[j] < 100 n eps) truncates the problem on the device.  No
+ * device->host transfer: a TDVP local step stays asynchronous.  numiter <= 64; `out` (n elements) is complex128,
+ * or float64 when out_is_complex == 0 (allowed for float64 vectors with dt_im == 0, NumPy's result dtype);
+ * coeff_ws: ptb_krylov_expm_workspace_bytes() of device memory, receives the 2*numiter coefficient doubles
+ * followed (at double offset 128) by the int32 k_eff. */
+size_t ptb_krylov_expm_workspace_bytes(void);
+int ptb_krylov_expm_apply(int v_dtype, int64_t n, int numiter, const void* v, int64_t ldv, const double* scal,
+                          double dt_re, double dt_im, int out_is_complex, void* coeff_ws, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * A whole Lanczos run on the local effective Hamiltonian in ONE call
+ *   pytenet/krylov.py:12-57 driven by the closures tdvp.py:223-229 (site), tdvp.py:232-238 (bond),
+ *   dmrg.py:181-189.
+ * Enqueues  v0 = x/|x|;  for j < numiter: w = H_eff v_j, three-term step  -- the same kernels as the
+ * per-step entry points above, issued back to back from C (no host code, allocation or synchronisation
+ * between the iterations: small-bond local problems are launch-latency-bound).  H_eff is square
+ * (Dlp = Dl, Drp = Dr, d_out = d_in).
+ *   V    : numiter x n Lanczos vectors (row-major), n = Dl*d*Dr (site) or Dl*Dr (bond)
+ *   scal : 2*numiter device doubles  [ |x|, alpha[0..numiter), beta[0..numiter-1) ]
+ *   w    : dense MPO tensor, or NULL when the CSR form (w_rowptr, w_col, w_val) is given; when both
+ *          are given the CSR form is used.
+ * The breakdown test of krylov.py:44-50 is the caller's, applied to the betas afterwards (entries
+ * before the breakdown index do not depend on later steps).
+ * ------------------------------------------------------------------------- */
+size_t ptb_heff_lanczos_workspace_bytes(int dtype, int64_t Dl, int64_t d, int64_t Dr, int64_t chi_l, int64_t chi_r);
+int ptb_heff_lanczos(int dtype, const void* x, const void* w, int w_is_complex, const int32_t* w_rowptr,
+                     const int32_t* w_col, const void* w_val, const void* l, const void* r, int64_t Dl, int64_t d,
+                     int64_t Dr, int64_t chi_l, int64_t chi_r, int numiter, void* V, double* scal, void* scratch,
+                     void* workspace, size_t workspace_bytes, void* stream);
+size_t ptb_bond_lanczos_workspace_bytes(int dtype, int64_t Dl, int64_t Dr, int64_t chi);
+int ptb_bond_lanczos(int dtype, const void* c, const void* l, const void* r, int64_t Dl, int64_t Dr, int64_t chi,
+                     int numiter, void* V, double* scal, void* scratch, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 /* ---------------------------------------------------------------------------
  * Diagnostics: register-resident DMMA.8x8x4 (use_dmma != 0) or DFMA loop on
  * `blocks` CTAs x 256 threads, to measure the FP64 pipe peak that the roofline

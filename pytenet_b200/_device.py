@@ -83,12 +83,14 @@ def any_complex(*tensors):
 
 
 def stream_ptr(device):
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw cudaStream_t of torch's current stream on `device` (the fast path of torch.cuda.current_stream)."""
+    idx = device.index
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device() if idx is None else idx)
 
 
 def workspace(nbytes, device, tag="main"):
     """Grow-only per-device workspace; safe because every user is stream-ordered."""
-    key = (device.index, tag, torch.cuda.current_stream(device).cuda_stream)
+    key = (device.index, tag, stream_ptr(device))
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         if buf is not None:
@@ -100,7 +102,7 @@ def workspace(nbytes, device, tag="main"):
 
 
 def lanczos_scratch(device):
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = (device.index, stream_ptr(device))
     buf = _scratch.get(key)
     if buf is None:
         nbytes = _lib.load().ptb_lanczos_scratch_bytes()

@@ -57,6 +57,14 @@ SIGNATURES = {
     "ptb_lanczos_alpha_d": (_int, [_i64] + [_ptr] * 5),
     "ptb_lanczos_alpha_z": (_int, [_i64] + [_ptr] * 5),
     "ptb_krylov_combine": (_int, [_int, _int, _i64, _i64, _ptr, _i64, _ptr, _ptr, _ptr]),
+    "ptb_heff_lanczos_workspace_bytes": (_sz, [_int] + [_i64] * 5),
+    "ptb_heff_lanczos": (_int, [_int, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _ptr, _ptr] + [_i64] * 5
+                         + [_int, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "ptb_bond_lanczos_workspace_bytes": (_sz, [_int] + [_i64] * 3),
+    "ptb_bond_lanczos": (_int, [_int, _ptr, _ptr, _ptr] + [_i64] * 3 + [_int, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "ptb_krylov_expm_workspace_bytes": (_sz, []),
+    "ptb_krylov_expm_apply": (_int, [_int, _i64, _int, _ptr, _i64, _ptr, ctypes.c_double, ctypes.c_double, _int, _ptr,
+                                     _ptr, _ptr]),
     "ptb_probe_fp64_pipe": (_int, [_int, _int, _int, _ptr, ctypes.POINTER(ctypes.c_double), _ptr]),
 }
 

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import _device as dev
+from . import _lib
 from .sectors import HeffSectorPlan
 from .block_sparse_util import is_qsparse
 from .chain_ops import (apply_local_hamiltonian, apply_local_bond_contraction,
@@ -52,6 +53,82 @@ def sector_plan(ql, qs, qr, qwl, qwr, like):
     return HeffSectorPlan(ql, qs, qr, qwl, qwr, cplx=True if like is None else like.dtype.is_complex)
 
 
+class HeffOperator:
+    """The closure of tdvp.py:223-229 / dmrg.py:181-189 as an object: calling it applies the local effective
+    Hamiltonian to a flat vector; `ptb_lanczos_run` hands a whole Lanczos run to the fused C entry
+    (ptb_heff_lanczos: every iteration enqueued by one call), which krylov._lanczos_core prefers."""
+
+    def __init__(self, w, l, r, shape):
+        self.w, self.l, self.r, self.shape = w, l, r, tuple(shape)
+
+    def __call__(self, x):
+        return apply_local_hamiltonian(x.reshape(self.shape), self.w, self.l, self.r).reshape(-1)
+
+    def ptb_lanczos_run(self, x, numiter, V, scal):
+        w, l, r = self.w, self.l, self.r
+        Dl, d, Dr = self.shape
+        if not all(isinstance(t, torch.Tensor) and t.is_cuda for t in (w, l, r)) or w.ndim != 4:
+            return False
+        cplx = x.dtype.is_complex
+        if (l.dtype.is_complex or r.dtype.is_complex or w.dtype.is_complex) and not cplx:
+            return False                 # mixed dtypes: the step-by-step path applies NumPy's promotion rules
+        cl, dout, din, cr = w.shape
+        if (dout != d or din != d or tuple(l.shape) != (Dl, cl, Dl) or tuple(r.shape) != (Dr, cr, Dr)
+                or x.numel() != Dl * d * Dr):
+            return False
+        lib = _lib.load()
+        device = x.device
+        l = dev.as_dtype(l, cplx); r = dev.as_dtype(r, cplx)
+        w_cplx = w.dtype.is_complex
+        if w.dtype not in (dev.F64, dev.C128):
+            return False
+        w = dev.dense(w)
+        csr = dev.w_csr(w)
+        rowptr, col, val = (csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr()) if csr is not None else (None,) * 3
+        dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
+        nbytes = lib.ptb_heff_lanczos_workspace_bytes(dt, Dl, d, Dr, cl, cr)
+        ws = dev.workspace(nbytes, device, tag="lanczos")
+        st = lib.ptb_heff_lanczos(dt, x.data_ptr(), w.data_ptr(), int(w_cplx), rowptr, col, val, l.data_ptr(),
+                                  r.data_ptr(), Dl, d, Dr, cl, cr, numiter, V.data_ptr(), scal.data_ptr(),
+                                  dev.lanczos_scratch(device).data_ptr(), ws.data_ptr(), nbytes,
+                                  dev.stream_ptr(device))
+        _lib.check(st, "heff_lanczos")
+        return True
+
+
+class BondOperator:
+    """The zero-site closure of tdvp.py:232-238; fused form: ptb_bond_lanczos."""
+
+    def __init__(self, l, r, shape):
+        self.l, self.r, self.shape = l, r, tuple(shape)
+
+    def __call__(self, x):
+        return apply_local_bond_contraction(x.reshape(self.shape), self.l, self.r).reshape(-1)
+
+    def ptb_lanczos_run(self, x, numiter, V, scal):
+        l, r = self.l, self.r
+        Dl, Dr = self.shape
+        if not all(isinstance(t, torch.Tensor) and t.is_cuda for t in (l, r)):
+            return False
+        cplx = x.dtype.is_complex
+        if (l.dtype.is_complex or r.dtype.is_complex) and not cplx:
+            return False
+        chi = l.shape[1]
+        if tuple(l.shape) != (Dl, chi, Dl) or tuple(r.shape) != (Dr, chi, Dr) or x.numel() != Dl * Dr:
+            return False
+        lib = _lib.load()
+        device = x.device
+        l = dev.as_dtype(l, cplx); r = dev.as_dtype(r, cplx)
+        dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
+        nbytes = lib.ptb_bond_lanczos_workspace_bytes(dt, Dl, Dr, chi)
+        ws = dev.workspace(nbytes, device, tag="lanczos")
+        st = lib.ptb_bond_lanczos(dt, x.data_ptr(), l.data_ptr(), r.data_ptr(), Dl, Dr, chi, numiter, V.data_ptr(),
+                                  scal.data_ptr(), dev.lanczos_scratch(device).data_ptr(), ws.data_ptr(), nbytes,
+                                  dev.stream_ptr(device))
+        _lib.check(st, "bond_lanczos")
+        return True
+
+
 def _heff(w, l, r, shape, plan):
     if plan is not None:
         def matvec(x):
@@ -59,7 +136,7 @@ def _heff(w, l, r, shape, plan):
                 return apply_local_hamiltonian(x.reshape(shape), w, l, r).reshape(-1)
             return plan.apply(x.reshape(shape), w, l, r).reshape(-1)
         return matvec
-    return lambda x: apply_local_hamiltonian(x.reshape(shape), w, l, r).reshape(-1)
+    return HeffOperator(w, l, r, shape)
 
 
 def local_hamiltonian_step(l, r, w, a, dt, numiter: int, plan=None):
@@ -71,9 +148,7 @@ def local_hamiltonian_step(l, r, w, a, dt, numiter: int, plan=None):
 def local_bond_step(l, r, c, dt, numiter: int):
     """exp(-dt K_eff) c for the zero-site (bond) effective Hamiltonian (tdvp.py:232-238)."""
     shape = tuple(c.shape)
-    return expm_krylov(
-        lambda x: apply_local_bond_contraction(x.reshape(shape), l, r).reshape(-1),
-        c.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
+    return expm_krylov(BondOperator(l, r, shape), c.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
 
 
 def minimize_local_energy(w, l, r, a_start, numiter: int, plan=None):

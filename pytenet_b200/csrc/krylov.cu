@@ -178,9 +178,182 @@ __global__ void __launch_bounds__(256) combine_kernel(const double* __restrict__
     }
 }
 
+// ---- single-CTA forms for short vectors (launch-latency-bound local problems, D <~ 64) --------------
+// One launch instead of two / three; same arithmetic per element, reductions in one block (deterministic).
+constexpr int SMALL_THREADS = 512;
+constexpr int64_t SMALL_ND = 16384;      // doubles; 128 KiB stays in L1/L2 between the passes
+
+__global__ void __launch_bounds__(SMALL_THREADS) start_small_kernel(const double* __restrict__ x, int nd,
+                                                                    double* __restrict__ nrm_out,
+                                                                    double* __restrict__ v0) {
+    __shared__ double red[32];
+    __shared__ double bc;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nd; i += SMALL_THREADS) acc += x[i] * x[i];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) { bc = sqrt(acc); *nrm_out = bc; }
+    __syncthreads();
+    const double sc = bc;
+    for (int i = threadIdx.x; i < nd; i += SMALL_THREADS) v0[i] = x[i] / sc;
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS) ortho_small_kernel(double* w, const double* __restrict__ vj,
+                                                                    const double* __restrict__ vjm1, int nd,
+                                                                    const double* __restrict__ beta_prev,
+                                                                    double* __restrict__ alpha_out,
+                                                                    double* __restrict__ beta_out, double* v_next) {
+    __shared__ double red[32];
+    __shared__ double bc;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nd; i += SMALL_THREADS) acc += w[i] * vj[i];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) { bc = acc; *alpha_out = acc; }
+    __syncthreads();
+    const double al = bc;
+    const double bp = (vjm1 != nullptr && beta_prev != nullptr) ? *beta_prev : 0.0;
+    acc = 0.0;
+    for (int i = threadIdx.x; i < nd; i += SMALL_THREADS) {
+        double sub = al * vj[i];                       // same association as krylov.py:42
+        if (vjm1 != nullptr) sub = sub + bp * vjm1[i];
+        const double r = w[i] - sub;
+        w[i] = r;
+        acc += r * r;
+    }
+    acc = block_sum(acc, red);                         // (starts with a barrier: `bc` has been read by all)
+    if (threadIdx.x == 0) { bc = sqrt(acc); *beta_out = bc; }
+    __syncthreads();
+    const double be = bc;
+    for (int i = threadIdx.x; i < nd; i += SMALL_THREADS) v_next[i] = w[i] / be;   // own elements only
+}
+
+// ---- k x k tridiagonal problem of expm_krylov on the device ------------------------------------------
+// krylov.py:122-136: coeff = U (|vec| exp(dt w) * U[0, :]) with (w, U) the eigen-decomposition of the Lanczos
+// tridiagonal matrix (krylov.py:142-150).  Solved here so that a TDVP local step needs no device->host round
+// trip: implicit symmetric QL iteration (the classic tql2 recurrence).  Every thread runs the scalar
+// recurrence redundantly (identical values, no communication) and applies the plane rotations to ITS row of the
+// eigenvector matrix; thread r ends up holding U[r, :].  The breakdown rule of krylov.py:44-50 is applied to
+// the betas first: k_eff = first j with beta[j] < thresh, plus one.
+constexpr int TRIDIAG_MAX = 64;
+
+__global__ void __launch_bounds__(TRIDIAG_MAX) expm_coeff_kernel(const double* __restrict__ scal, int numiter,
+                                                                 double thresh, double dt_re, double dt_im,
+                                                                 double* __restrict__ coeff, int* __restrict__ keff_out) {
+    __shared__ double u0[TRIDIAG_MAX];          // first row of U
+    __shared__ double ev[TRIDIAG_MAX];
+    const int r = threadIdx.x;
+    const double nrm = scal[0];
+    const double* alpha = scal + 1;
+    const double* beta = alpha + numiter;
+    int n = numiter;
+    for (int j = 0; j < numiter - 1; j++)
+        if (!(beta[j] >= thresh)) { n = j + 1; break; }      // also catches NaN of a speculative step
+    double d[TRIDIAG_MAX], e[TRIDIAG_MAX], z[TRIDIAG_MAX];
+    for (int i = 0; i < n; i++) { d[i] = alpha[i]; e[i] = (i + 1 < n) ? beta[i] : 0.0; z[i] = (i == r) ? 1.0 : 0.0; }
+    // e[i] couples i and i+1 (already in tql2's shifted convention), e[n-1] = 0
+    double f = 0.0, tst1 = 0.0;
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n; l++) {
+        tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
+        int m = l;
+        while (m < n - 1 && fabs(e[m]) > eps * tst1) m++;
+        if (m > l) {
+            int iter = 0;
+            do {
+                iter++;
+                double g = d[l];
+                double p = (d[l + 1] - g) / (2.0 * e[l]);
+                double rr = hypot(p, 1.0);
+                if (p < 0) rr = -rr;
+                d[l] = e[l] / (p + rr);
+                d[l + 1] = e[l] * (p + rr);
+                const double dl1 = d[l + 1];
+                double h = g - d[l];
+                for (int i = l + 2; i < n; i++) d[i] -= h;
+                f += h;
+                p = d[m];
+                double c = 1.0, c2 = 1.0, c3 = 1.0, s = 0.0, s2 = 0.0;
+                const double el1 = e[l + 1];
+                for (int i = m - 1; i >= l; i--) {
+                    c3 = c2; c2 = c; s2 = s;
+                    g = c * e[i];
+                    h = c * p;
+                    rr = hypot(p, e[i]);
+                    e[i + 1] = s * rr;
+                    s = e[i] / rr;
+                    c = p / rr;
+                    p = c * d[i] - s * g;
+                    d[i + 1] = h + s * (c * g + s * d[i]);
+                    const double zh = z[i + 1];             // rotate columns i, i+1 of this thread's row
+                    z[i + 1] = s * z[i] + c * zh;
+                    z[i] = c * z[i] - s * zh;
+                }
+                p = -s * s2 * c3 * el1 * e[l] / dl1;
+                e[l] = s * p;
+                d[l] = c * p;
+            } while (fabs(e[l]) > eps * tst1 && iter < 60);
+        }
+        d[l] = d[l] + f;
+        e[l] = 0.0;
+    }
+    if (r == 0) {
+        for (int i = 0; i < n; i++) { u0[i] = z[i]; ev[i] = d[i]; }
+        *keff_out = n;
+    }
+    __syncthreads();
+    if (r >= numiter) return;
+    double cre = 0.0, cim = 0.0;
+    if (r < n) {
+        for (int j = 0; j < n; j++) {
+            // |vec| exp(dt w_j) U[0, j]
+            const double mag = nrm * exp(dt_re * ev[j]) * u0[j];
+            double sn, cs;
+            sincos(dt_im * ev[j], &sn, &cs);
+            cre += z[j] * mag * cs;
+            cim += z[j] * mag * sn;
+        }
+    }
+    coeff[2 * r] = cre;
+    coeff[2 * r + 1] = cim;
+}
+
+// out[n] = sum_{j < *k_eff} coeff[j] V[j, :]  (complex coefficients; OC: out complex, else the real part is
+// stored -- real vectors with a real time step, where the imaginary parts are exactly zero)
+template <bool VC, bool OC>
+__global__ void __launch_bounds__(256) combine_devk_kernel(const double* __restrict__ v, int64_t ldv, int64_t n,
+                                                           const int* __restrict__ k_eff,
+                                                           const double* __restrict__ coeff, double* __restrict__ out) {
+    __shared__ double cs[2 * TRIDIAG_MAX];
+    const int k = *k_eff;
+    for (int j = threadIdx.x; j < 2 * k; j += blockDim.x) cs[j] = coeff[j];
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double re = 0.0, im = 0.0;
+        for (int j = 0; j < k; j++) {
+            const double cr = cs[2 * j], ci = cs[2 * j + 1];
+            if (VC) {
+                const double2 x = *reinterpret_cast<const double2*>(v + 2 * ((int64_t)j * ldv + i));
+                re += cr * x.x - ci * x.y;
+                im += cr * x.y + ci * x.x;
+            } else {
+                const double x = v[(int64_t)j * ldv + i];
+                re += cr * x;
+                if (OC) im += ci * x;
+            }
+        }
+        if (OC) *reinterpret_cast<double2*>(out + 2 * i) = make_double2(re, im);
+        else out[i] = re;
+    }
+}
+
 int start_impl(int64_t n, int e, const void* x, void* v0, double* nrm, void* scratch, cudaStream_t st) {
     if (n <= 0 || !x || !v0 || !nrm || !scratch) return PTB_ERR_BAD_ARG;
     const int64_t nd = n * e;
+    if (nd <= SMALL_ND) {
+        start_small_kernel<<<1, SMALL_THREADS, 0, st>>>(static_cast<const double*>(x), (int)nd, nrm,
+                                                        static_cast<double*>(v0));
+        return cuda_status(cudaGetLastError());
+    }
     Scratch s = scratch_of(scratch);
     const int gb = red_blocks(nd);
     sumsq_kernel<<<gb, RED_THREADS, 0, st>>>(static_cast<const double*>(x), nd, nrm, s);
@@ -193,9 +366,15 @@ int ortho_impl(int64_t n, int e, void* w, const void* vj, const void* vjm1, cons
     if (n <= 0 || !w || !vj || !alpha_out || !beta_out || !v_next || !scratch) return PTB_ERR_BAD_ARG;
     if ((vjm1 == nullptr) != (beta_prev == nullptr)) return PTB_ERR_BAD_ARG;
     const int64_t nd = n * e;
+    double* wd = static_cast<double*>(w);
+    if (nd <= SMALL_ND) {
+        ortho_small_kernel<<<1, SMALL_THREADS, 0, st>>>(wd, static_cast<const double*>(vj),
+                                                        static_cast<const double*>(vjm1), (int)nd, beta_prev,
+                                                        alpha_out, beta_out, static_cast<double*>(v_next));
+        return cuda_status(cudaGetLastError());
+    }
     Scratch s = scratch_of(scratch);
     const int gb = red_blocks(nd);
-    double* wd = static_cast<double*>(w);
     dot_real_kernel<<<gb, RED_THREADS, 0, st>>>(wd, static_cast<const double*>(vj), nd, alpha_out, s);
     axpy_norm_kernel<<<gb, RED_THREADS, 0, st>>>(wd, static_cast<const double*>(vj),
                                                  static_cast<const double*>(vjm1), nd, alpha_out, beta_prev,
@@ -260,5 +439,31 @@ int ptb_krylov_combine(int v_dtype, int coeff_dtype, int64_t n, int64_t k, const
     else combine_kernel<false, false><<<gb, 256, sh, st>>>(vd, ldv, n, (int)k, cd, od);
     return cuda_status(cudaGetLastError());
 }
+
+int ptb_krylov_expm_apply(int v_dtype, int64_t n, int numiter, const void* v, int64_t ldv, const double* scal,
+                          double dt_re, double dt_im, int out_is_complex, void* coeff_ws, void* out,
+                          void* stream) {
+    if (n <= 0 || numiter < 1 || numiter > TRIDIAG_MAX || !v || !scal || !coeff_ws || !out || ldv < n)
+        return PTB_ERR_BAD_ARG;
+    const bool vc = v_dtype == PTB_COMPLEX128;
+    if (v_dtype != PTB_REAL64 && !vc) return PTB_ERR_BAD_DTYPE;
+    if (!out_is_complex && (vc || dt_im != 0.0)) return PTB_ERR_BAD_DTYPE;
+    if (reinterpret_cast<uintptr_t>(coeff_ws) % 16 || reinterpret_cast<uintptr_t>(out) % 16) return PTB_ERR_ALIGNMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* coeff = static_cast<double*>(coeff_ws);
+    int* keff = reinterpret_cast<int*>(coeff + 2 * TRIDIAG_MAX);
+    const double thresh = 100.0 * (double)n * 2.220446049250313e-16;      // krylov.py:44
+    expm_coeff_kernel<<<1, TRIDIAG_MAX, 0, st>>>(scal, numiter, thresh, dt_re, dt_im, coeff, keff);
+    int64_t gb64 = (n + 255) / 256;
+    const int gb = (int)(gb64 > 148 * 16 ? 148 * 16 : gb64);
+    const double* vd = static_cast<const double*>(v);
+    double* od = static_cast<double*>(out);
+    if (vc) combine_devk_kernel<true, true><<<gb, 256, 0, st>>>(vd, ldv, n, keff, coeff, od);
+    else if (out_is_complex) combine_devk_kernel<false, true><<<gb, 256, 0, st>>>(vd, ldv, n, keff, coeff, od);
+    else combine_devk_kernel<false, false><<<gb, 256, 0, st>>>(vd, ldv, n, keff, coeff, od);
+    return cuda_status(cudaGetLastError());
+}
+
+size_t ptb_krylov_expm_workspace_bytes(void) { return (2 * TRIDIAG_MAX + 2) * sizeof(double); }
 
 }  // extern "C"

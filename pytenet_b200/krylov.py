@@ -18,34 +18,15 @@ import torch
 from . import _lib
 from . import _device as dev
 
-__all__ = ["lanczos_iteration", "eigh_krylov", "expm_krylov", "eigh_tridiag"]
+__all__ = ["lanczos_iteration", "eigh_krylov", "expm_krylov", "eigh_tridiag", "deferred_checks"]
 
 
-def _lanczos_core(afunc, vstart, numiter):
-    """Run the Lanczos recursion on the device.
-
-    Returns (nrm, alpha, beta, Vk): |vstart|, NumPy alpha (k_eff,), beta (k_eff-1,)
-    and the first k_eff rows of the resident (numiter, n) Lanczos-vector buffer.
-    All `numiter` steps are enqueued without host synchronisation; the breakdown
-    test of krylov.py:44-50 is applied afterwards to the betas (entries up to the
-    breakdown index do not depend on later steps, so the truncated results are
-    identical to the reference's early exit)."""
-    lib = _lib.load()
-    assert numiter >= 1
-    x = vstart.reshape(-1)
-    cplx = x.dtype.is_complex
-    x = dev.as_dtype(x, cplx)
-    n = x.shape[0]
-    device = x.device
-    sfx = "z" if cplx else "d"
+def _lanczos_steps(lib, afunc, x, numiter, V, scal, sfx, stream, scratch):
+    """The recursion driven from Python, one matvec callback per iteration (any `afunc`)."""
     start = getattr(lib, "ptb_lanczos_start_" + sfx)
     ortho = getattr(lib, "ptb_lanczos_ortho_step_" + sfx)
     closing = getattr(lib, "ptb_lanczos_alpha_" + sfx)
-    stream = dev.stream_ptr(device)
-    scratch = dev.lanczos_scratch(device).data_ptr()
-    V = torch.empty((numiter, n), dtype=x.dtype, device=device)
-    # device scalars: [nrm, alpha[0:k], beta[0:k-1]]
-    scal = torch.zeros(2 * numiter, dtype=dev.F64, device=device)
+    n = x.shape[0]
     p_nrm = scal.data_ptr()
     p_alpha = p_nrm + 8
     p_beta = p_alpha + 8 * numiter
@@ -70,7 +51,39 @@ def _lanczos_core(afunc, vstart, numiter):
         # alpha_j, w -= alpha v_j + beta_{j-1} v_{j-1}, beta_j, v_{j+1} = w / beta_j  (krylov.py:41-43,51)
         _lib.check(ortho(n, w.data_ptr(), vj, vjm1, bprev, p_alpha + 8 * j, p_beta + 8 * j,
                          vj + row, scratch, stream), "lanczos_ortho_step")
-    host = scal.cpu().numpy()          # the only device->host transfer of the run
+
+
+def _lanczos_device(afunc, vstart, numiter):
+    """Enqueue the Lanczos recursion on the device; returns (n, V, scal) with V the resident (numiter, n)
+    Lanczos-vector buffer and scal = [|vstart|, alpha[0:k], beta[0:k-1]] device doubles.
+    All `numiter` steps are enqueued without host synchronisation; the breakdown
+    test of krylov.py:44-50 is applied afterwards to the betas (entries up to the
+    breakdown index do not depend on later steps, so the truncated results are
+    identical to the reference's early exit)."""
+    lib = _lib.load()
+    assert numiter >= 1
+    x = vstart.reshape(-1)
+    cplx = x.dtype.is_complex
+    x = dev.as_dtype(x, cplx)
+    n = x.shape[0]
+    device = x.device
+    sfx = "z" if cplx else "d"
+    stream = dev.stream_ptr(device)
+    scratch = dev.lanczos_scratch(device).data_ptr()
+    V = torch.empty((numiter, n), dtype=x.dtype, device=device)
+    # device scalars: [nrm, alpha[0:k], beta[0:k-1]]
+    scal = torch.zeros(2 * numiter, dtype=dev.F64, device=device)
+    # operators that know the fused C entry (one call enqueues the whole run: _sweep.HeffOperator /
+    # BondOperator -> ptb_heff_lanczos / ptb_bond_lanczos) take it; any other callable is driven step by step
+    fused = getattr(afunc, "ptb_lanczos_run", None)
+    if fused is None or not fused(x, numiter, V, scal):
+        _lanczos_steps(lib, afunc, x, numiter, V, scal, sfx, stream, scratch)
+    return n, V, scal
+
+
+def _check_scalars(host, n, numiter):
+    """Host-side reading of a run's scalars: norm assertion and the breakdown rule of krylov.py:44-50.
+    Returns (nrm, alpha, beta) truncated at the breakdown index."""
     nrm = host[0]
     assert nrm > 0
     alpha = host[1:1 + numiter].copy()
@@ -82,7 +95,76 @@ def _lanczos_core(afunc, vstart, numiter):
             warnings.warn(f"beta[{j}] ~= 0 encountered during Lanczos iteration.", RuntimeWarning)
             keep = j + 1
             break
-    return nrm, alpha[:keep], beta[:keep - 1], V[:keep]
+    return nrm, alpha[:keep], beta[:keep - 1]
+
+
+def _lanczos_core(afunc, vstart, numiter):
+    """Lanczos run + the one device->host transfer of its scalars.
+    Returns (nrm, alpha, beta, Vk) with Vk the first k_eff rows of the resident Lanczos-vector buffer."""
+    n, V, scal = _lanczos_device(afunc, vstart, numiter)
+    nrm, alpha, beta = _check_scalars(scal.cpu().numpy(), n, numiter)
+    return nrm, alpha, beta, V[:len(alpha)]
+
+
+# ---- deferred scalar checks: keeps a TDVP sweep free of device->host round trips -----------------------------
+# expm_krylov solves its tridiagonal problem on the device (ptb_krylov_expm_apply), so nothing forces a
+# synchronisation per local step -- except the reference's breakdown warning and norm assertion.  Inside
+# `deferred_checks()` (used by the sweep drivers) the scalars of every run are copied asynchronously into a
+# page-locked ring and examined when the block ends (or the ring is full): same warnings, issued later.
+_DEFER_SLOTS = 2048
+_DEFER_WIDTH = 128
+
+
+class _Deferred:
+    depth = 0
+    ring = None
+    meta = []
+
+
+def _flush_deferred():
+    if not _Deferred.meta:
+        return
+    torch.cuda.synchronize()
+    host = _Deferred.ring.numpy()
+    meta, _Deferred.meta = _Deferred.meta, []
+    for slot, (n, numiter) in enumerate(meta):
+        _check_scalars(host[slot], n, numiter)
+
+
+class deferred_checks:
+    """Context manager: Lanczos breakdown warnings / norm assertions of expm_krylov calls on device tensors are
+    collected and issued when the outermost block exits instead of synchronising after every call."""
+
+    def __enter__(self):
+        _Deferred.depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        _Deferred.depth -= 1
+        if _Deferred.depth == 0:
+            _flush_deferred()
+        return False
+
+
+def defer_checks(fn):
+    """Decorator form of `deferred_checks()` for the sweep drivers."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        with deferred_checks():
+            return fn(*args, **kwargs)
+    return wrapped
+
+
+def _defer(scal, n, numiter):
+    if _Deferred.ring is None:
+        _Deferred.ring = torch.empty((_DEFER_SLOTS, _DEFER_WIDTH), dtype=dev.F64, pin_memory=True)
+    if len(_Deferred.meta) == _DEFER_SLOTS:
+        _flush_deferred()
+    slot = len(_Deferred.meta)
+    _Deferred.ring[slot, :2 * numiter].copy_(scal, non_blocking=True)
+    _Deferred.meta.append((n, numiter))
 
 
 def _host_afunc(afunc):
@@ -169,9 +251,35 @@ def expm_krylov(afunc, vec, dt, numiter, hermitian=False):
             "the Arnoldi branch (krylov.py:137-139) is outside the effective-Hamiltonian path")
     host_mode = dev.is_host(vec)
     x = dev.to_device(vec)
+    if not host_mode and numiter <= _EXPM_DEVICE_MAX_ITER:
+        return _expm_device(afunc, x, dt, numiter)
     nrm, alpha, beta, Vk = _lanczos_core(_host_afunc(afunc) if host_mode else afunc, x, numiter)
     w_hess, u_hess = eigh_tridiag(alpha, beta)
     # np.linalg.norm(vec) of the reference (:136) is the norm computed by the start kernel
     coeff = u_hess @ (nrm * np.exp(dt * w_hess) * u_hess[0])
     out = _combine(Vk, coeff)
     return dev.to_host(out) if host_mode else out
+
+
+_EXPM_DEVICE_MAX_ITER = 64
+
+
+def _expm_device(afunc, x, dt, numiter):
+    """expm_krylov with the k x k problem solved on the device (ptb_krylov_expm_apply): no device->host
+    transfer on the way; the scalar checks follow immediately, or at the end of a `deferred_checks()` block."""
+    lib = _lib.load()
+    n, V, scal = _lanczos_device(afunc, x, numiter)
+    vc = V.dtype.is_complex
+    dtc = complex(dt)
+    out_cplx = vc or isinstance(dt, (complex, np.complexfloating))
+    out = torch.empty(n, dtype=dev.C128 if out_cplx else dev.F64, device=V.device)
+    cws = dev.workspace(lib.ptb_krylov_expm_workspace_bytes(), V.device, tag="expm")
+    st = lib.ptb_krylov_expm_apply(_lib.PTB_COMPLEX128 if vc else _lib.PTB_REAL64, n, numiter, V.data_ptr(),
+                                   V.stride(0), scal.data_ptr(), dtc.real, dtc.imag, int(out_cplx), cws.data_ptr(),
+                                   out.data_ptr(), dev.stream_ptr(V.device))
+    _lib.check(st, "krylov_expm_apply")
+    if _Deferred.depth > 0:
+        _defer(scal, n, numiter)
+    else:
+        _check_scalars(scal.cpu().numpy(), n, numiter)
+    return out

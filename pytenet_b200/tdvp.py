@@ -14,10 +14,12 @@ from .mpo import MPO, mpo_merge_tensor_pair
 from .chain_ops import contraction_operator_step_right, contraction_operator_step_left
 from .block_sparse_util import qnumber_flatten, block_sparse_qr
 from ._sweep import prepare_environments, local_hamiltonian_step, local_bond_step, sector_plan
+from .krylov import defer_checks
 
 __all__ = ["tdvp_singlesite", "tdvp_twosite"]
 
 
+@defer_checks
 def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lanczos: int = 25):
     """
     Symmetric single-site TDVP integration; `psi` is overwritten in place.
@@ -75,6 +77,7 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
     return nrm
 
 
+@defer_checks
 def tdvp_twosite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lanczos: int = 25, tol_split=0):
     """
     Symmetric two-site TDVP integration; `psi` is overwritten in place.

@@ -122,3 +122,143 @@ def test_vector_kernels_at_scale(cuda_lib):
     assert abs(beta - torch.linalg.norm(resid).item()) / beta < 1e-13
     assert abs(torch.linalg.norm(vnext).item() - 1) < 1e-13
     assert abs(torch.vdot(vj, vnext).real.item()) < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 7, 896, 8192, 8193, 40000])
+def test_ortho_step_small_and_large_kernels(cuda_lib, n):
+    """The single-CTA form (n*2 <= 16384 doubles) and the grid form of the three-term step against NumPy,
+    including the previous-vector term and aliasing v_next == w."""
+    from pytenet_b200 import _device as dev
+    lib = cuda_lib
+    rng = np.random.default_rng(n)
+    w = rng.normal(size=n) + 1j * rng.normal(size=n)
+    vj = rng.normal(size=n) + 1j * rng.normal(size=n); vj /= np.linalg.norm(vj)
+    vm = rng.normal(size=n) + 1j * rng.normal(size=n); vm /= np.linalg.norm(vm)
+    bprev = 0.37
+    wd, vjd, vmd = cu(w), cu(vj), cu(vm)
+    scal = torch.tensor([0.0, 0.0, bprev], dtype=torch.float64, device="cuda")
+    scratch = dev.lanczos_scratch(wd.device)
+    st = lib.ptb_lanczos_ortho_step_z(n, wd.data_ptr(), vjd.data_ptr(), vmd.data_ptr(), scal.data_ptr() + 16,
+                                      scal.data_ptr(), scal.data_ptr() + 8, wd.data_ptr(), scratch.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream)
+    assert st == 0
+    alpha, beta, _ = scal.cpu().numpy()
+    a_ref = np.vdot(vj, w).real
+    res = w - (a_ref * vj + bprev * vm)
+    assert abs(alpha - a_ref) < 1e-13 * max(1.0, abs(a_ref))
+    assert abs(beta - np.linalg.norm(res)) < 1e-13 * np.linalg.norm(res)
+    assert rel(wd.cpu().numpy(), res / np.linalg.norm(res)) < 1e-13
+    # start kernel: v0 = x / |x|
+    x = cu(w); v0 = torch.empty_like(x); nrm = torch.zeros(1, dtype=torch.float64, device="cuda")
+    assert lib.ptb_lanczos_start_z(n, x.data_ptr(), v0.data_ptr(), nrm.data_ptr(), scratch.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream) == 0
+    assert abs(nrm.item() - np.linalg.norm(w)) < 1e-13 * np.linalg.norm(w)
+    assert rel(v0.cpu().numpy(), w / np.linalg.norm(w)) < 1e-14
+
+
+@pytest.mark.parametrize("cplx,dims", [(True, (16, 2, 28, 5, 5)), (False, (12, 2, 9, 4, 5)), (True, (130, 4, 121, 5, 5)),
+                                       (True, (2, 2, 3, 2, 4))])
+def test_fused_lanczos_run_equals_stepwise(cuda_lib, cplx, dims):
+    """ptb_heff_lanczos / ptb_bond_lanczos (one call enqueues the whole run) give exactly the alphas, betas and
+    Lanczos vectors of the step-by-step path (same kernels), and match the oracle's Lanczos on the same operator."""
+    import pytenet_b200 as ptb
+    from pytenet_b200 import krylov, _sweep
+    Dl, d, Dr, cl, cr = dims
+    rng = np.random.default_rng(Dl * 100 + Dr)
+
+    def rnd(shape, c):
+        x = rng.normal(size=shape)
+        return x + 1j * rng.normal(size=shape) if c else x
+
+    def herm_env(D, chi):
+        # environments of a Hermitian operator: e[:, k, :] Hermitian for every k (then H_eff is Hermitian for
+        # w[k, s', s, kappa] symmetric under s <-> s')
+        e = rnd((D, chi, D), cplx)
+        return np.ascontiguousarray(e + e.conj().transpose(2, 1, 0))
+
+    l, r = herm_env(Dl, cl), herm_env(Dr, cr)
+    w = rnd((cl, d, d, cr), False); w = w + w.transpose(0, 2, 1, 3); w[rng.random(w.shape) < 0.5] = 0
+    w = np.ascontiguousarray(np.minimum(w, w.transpose(0, 2, 1, 3)))      # keep it symmetric after masking
+    a = rnd((Dl, d, Dr), cplx)
+    k = 6
+    op = _sweep.HeffOperator(cu(w), cu(l), cu(r), (Dl, d, Dr))
+    n1, al1, be1, V1 = krylov._lanczos_core(op, cu(a).reshape(-1), k)
+    n2, al2, be2, V2 = krylov._lanczos_core(lambda x: op(x), cu(a).reshape(-1), k)
+    assert n1 == n2 and np.array_equal(al1, al2) and np.array_equal(be1, be2) and torch.equal(V1, V2)
+    oal, obe, oV = oracle.lanczos_iteration(
+        lambda x: oracle.apply_local_hamiltonian(x.reshape(Dl, d, Dr), w, l, r).reshape(-1), a.reshape(-1), k)
+    assert np.allclose(al1, oal, rtol=1e-9, atol=1e-9 * np.abs(oal).max()) and np.allclose(be1, obe, rtol=1e-8)
+    # zero-site (bond) operator: needs a common MPO bond
+    r2 = herm_env(Dr, cl)
+    c = rnd((Dl, Dr), cplx)
+    bop = _sweep.BondOperator(cu(l), cu(r2), (Dl, Dr))
+    n1, al1, be1, V1 = krylov._lanczos_core(bop, cu(c).reshape(-1), k)
+    n2, al2, be2, V2 = krylov._lanczos_core(lambda x: bop(x), cu(c).reshape(-1), k)
+    assert n1 == n2 and np.array_equal(al1, al2) and np.array_equal(be1, be2) and torch.equal(V1, V2)
+    oal, obe, oV = oracle.lanczos_iteration(
+        lambda x: oracle.apply_local_bond_contraction(x.reshape(Dl, Dr), l, r2).reshape(-1), c.reshape(-1), k)
+    assert np.allclose(al1, oal, rtol=1e-9, atol=1e-9 * np.abs(oal).max()) and np.allclose(be1, obe, rtol=1e-8)
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 25, 64])
+@pytest.mark.parametrize("vc,dt", [(True, 0.3 - 0.7j), (False, -0.45), (False, 0.2j)])
+def test_expm_tridiagonal_on_device(cuda_lib, k, vc, dt):
+    """ptb_krylov_expm_apply (implicit QL on the device + combination) against the reference formula
+    v @ (U (|vec| exp(dt w) U[0])) evaluated with numpy.linalg.eigh (krylov.py:122-136, :142-150)."""
+    from pytenet_b200 import _lib, _device as dev
+    lib = cuda_lib
+    rng = np.random.default_rng(1000 * k + int(vc))
+    n = 777
+    alpha = rng.normal(size=k) * 3
+    beta = np.abs(rng.normal(size=max(k - 1, 0))) + 0.1
+    nrm = 1.7
+    V = rng.normal(size=(k, n)) + (1j * rng.normal(size=(k, n)) if vc else 0)
+    scal = np.concatenate([[nrm], alpha, beta, np.zeros(2 * k - 1 - len(alpha) - len(beta))])
+    w_h, u_h = oracle.eigh_tridiag(alpha, beta)
+    want = V.T @ (u_h @ (nrm * np.exp(dt * w_h) * u_h[0]))
+    out_cplx = vc or isinstance(dt, complex)
+    Vd, sd = cu(V), cu(scal)
+    out = torch.empty(n, dtype=torch.complex128 if out_cplx else torch.float64, device="cuda")
+    cws = torch.zeros(lib.ptb_krylov_expm_workspace_bytes() // 8, dtype=torch.float64, device="cuda")
+    dtc = complex(dt)
+    st = lib.ptb_krylov_expm_apply(1 if vc else 0, n, k, Vd.data_ptr(), n, sd.data_ptr(), dtc.real, dtc.imag,
+                                   int(out_cplx), cws.data_ptr(), out.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream)
+    assert st == 0
+    assert rel(out.cpu().numpy(), want) < 1e-12
+    assert int(cws[128:129].view(torch.int32)[0].item()) == k
+
+
+def test_expm_on_device_truncates_at_breakdown(cuda_lib):
+    """A beta below 100 n eps ends the Krylov space on the device exactly as krylov.py:44-50 does on the host
+    (later rows of V may hold NaN from the division by ~0 and must not be touched)."""
+    lib = cuda_lib
+    n, k = 300, 6
+    rng = np.random.default_rng(5)
+    alpha = rng.normal(size=k); beta = np.array([0.8, 0.5, 1e-14, 0.3, 0.2])
+    V = rng.normal(size=(k, n)) + 1j * rng.normal(size=(k, n)); V[3:] = np.nan
+    nrm, dt = 0.9, -0.1 + 0.4j
+    w_h, u_h = oracle.eigh_tridiag(alpha[:3], beta[:2])
+    want = V[:3].T @ (u_h @ (nrm * np.exp(dt * w_h) * u_h[0]))
+    scal = np.concatenate([[nrm], alpha, beta])
+    Vd, sd = cu(V), cu(scal)
+    out = torch.empty(n, dtype=torch.complex128, device="cuda")
+    cws = torch.zeros(lib.ptb_krylov_expm_workspace_bytes() // 8, dtype=torch.float64, device="cuda")
+    assert lib.ptb_krylov_expm_apply(1, n, k, Vd.data_ptr(), n, sd.data_ptr(), dt.real, dt.imag, 1, cws.data_ptr(),
+                                     out.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+    assert rel(out.cpu().numpy(), want) < 1e-12
+
+
+def test_deferred_breakdown_warning(cuda_lib):
+    """Inside deferred_checks() the RuntimeWarning of a Lanczos breakdown is issued when the block exits."""
+    import pytenet_b200 as ptb
+    from pytenet_b200 import _device as dev
+    m = np.diag([1.0, 2.0, 3.0]); v = np.array([1.0, 1.0, 1.0])
+    md = cu(m)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        with ptb.deferred_checks():
+            got = ptb.expm_krylov(lambda x: dev.gemm(md, x.reshape(-1, 1)).reshape(-1), cu(v), -0.5, 6, hermitian=True)
+            assert not any(issubclass(r.category, RuntimeWarning) for r in rec)
+        assert any(issubclass(r.category, RuntimeWarning) and "Lanczos" in str(r.message) for r in rec)
+    assert got.dtype == torch.float64 and rel(got.cpu().numpy(), np.exp(-0.5 * np.array([1.0, 2.0, 3.0]))) < 1e-12
