@@ -204,6 +204,21 @@ def _csr_arrays(mat, device):
             torch.from_numpy(vals).to(device), len(rows))
 
 
+def csr_arrays_any(mat):
+    """CSR device arrays of a 2-D device matrix of any density (no non-zero limit; one small device->host copy)."""
+    host = mat.detach().cpu().numpy()
+    rows, cols = np.nonzero(host)
+    rowptr = np.zeros(host.shape[0] + 1, dtype=np.int64)
+    np.add.at(rowptr, rows + 1, 1)
+    rowptr = np.cumsum(rowptr).astype(np.int32)
+    vals = np.ascontiguousarray(host[rows, cols])
+    if len(rows) == 0:
+        cols = np.zeros(1, dtype=np.int64)
+        vals = np.zeros(1, dtype=host.dtype)
+    return (torch.from_numpy(rowptr).to(mat.device), torch.from_numpy(cols.astype(np.int32)).to(mat.device),
+            torch.from_numpy(vals).to(mat.device), len(rows))
+
+
 def w_csr(w):
     """(rowptr, col, val, nnz) device arrays of w reshaped to (chi_l*d_out) x (d_in*chi_r), or None when w
     is too dense / large for the sparse W kernel.  Built once per tensor (one small device->host copy of w)."""

@@ -15,7 +15,7 @@ import torch
 from . import _device as dev
 
 __all__ = ["qnumber_outer_sum", "common_qnumbers", "qnumber_flatten", "is_qsparse", "enforce_qsparsity",
-           "block_sparse_qr", "block_sparse_svd"]
+           "block_sparse_qr", "block_sparse_eigh", "block_sparse_svd"]
 
 # SVD driver for cuSOLVER: "gesvd" (QR iteration, closest to LAPACK) unless overridden
 _SVD_DRIVER = os.environ.get("PYTENET_B200_SVD_DRIVER", "gesvd")
@@ -133,6 +133,34 @@ def block_sparse_qr(a, q0, q1):
         qinterm[pos:pos + sz] = qn
         pos += sz
     return q, r, qinterm
+
+
+def block_sparse_eigh(a, q0):
+    """
+    Sector-wise diagonalisation of a Hermitian block-sparse matrix (`a[i, j] != 0` only if
+    `q0[i] == q0[j]`) -> `(u, evals, q)` with `a = u diag(evals) u^H`; `evals` a host float64 array
+    (:183-241).  The sectors follow the iteration order of `set(q0)`, as in the reference (:197,212).
+    """
+    assert a.ndim == 2 and a.shape[0] == a.shape[1]
+    q0 = np.asarray(q0)
+    assert len(q0) == a.shape[0]
+    assert is_qsparse(a, [q0, -q0])
+    n = a.shape[0]
+    order = np.argsort(q0, kind="stable")
+    u = torch.zeros((n, n), dtype=a.dtype, device=a.device)
+    ev_dev = torch.zeros(n, dtype=dev.F64, device=a.device)
+    q = np.zeros(n, dtype=q0.dtype)
+    pos = 0
+    for qn in set(q0):
+        idx = order[q0[order] == qn]
+        ev, us = torch.linalg.eigh(_block(a, idx, idx))
+        it = torch.as_tensor(idx, device=a.device)
+        u[it, pos:pos + len(idx)] = us
+        ev_dev[pos:pos + len(idx)] = ev
+        q[pos:pos + len(idx)] = qn
+        pos += len(idx)
+    assert pos == n
+    return u, ev_dev.cpu().numpy(), q
 
 
 def block_sparse_svd(a, q0, q1):

@@ -16,7 +16,7 @@ from . import _device as dev
 
 __all__ = ["contraction_operator_step_right", "contraction_operator_step_left",
            "compute_right_operator_blocks", "mpo_average", "mpo_inner_product",
-           "apply_local_hamiltonian", "apply_local_bond_contraction"]
+           "apply_local_hamiltonian", "apply_local_bond_contraction", "apply_mpo"]
 
 
 def _prep(tensors, ranks, names):
@@ -246,3 +246,41 @@ def mpo_inner_product(chi, op, psi):
 def mpo_average(psi, op):
     """Expectation value `<psi | op | psi>` (pytenet/chain_ops.py:151-163)."""
     return mpo_inner_product(psi, op, psi)
+
+
+def apply_mpo(op, psi):
+    """
+    Apply an operator in MPO form to a state in MPS form (pytenet/chain_ops.py:215-234): per site
+    `t[(k,i), s', (kappa,j)] = sum_s w[k,s',s,kappa] a[i,s,j]`, virtual bonds grouped MPO-major.
+
+    The contraction index has length d, so the step is pure data movement: it runs on the HBM-bound sparse
+    W kernel (`ptb_wapply_csr`, batched over the left bond index i, one pass over the output) followed by
+    the regrouping of the bond indices.
+    """
+    from .mps import MPS
+    from .block_sparse_util import qnumber_flatten, is_qsparse
+    lib = _lib.load()
+    assert np.array_equal(psi.qsite, op.qsite)
+    assert psi.nsites == op.nsites
+    qbonds = [qnumber_flatten((op.qbonds[i], psi.qbonds[i])) for i in range(psi.nsites + 1)]
+    out = MPS(psi.qsite, qbonds, fill="postpone", device=psi.device)
+    for i in range(psi.nsites):
+        a = dev.to_device(psi.a[i], psi.device)
+        w = dev.dense(dev.to_device(op.a[i], psi.device))
+        cplx = dev.any_complex(a, w)
+        a = dev.as_dtype(a, cplx)
+        Dl, d, Dr = a.shape
+        cl, dout, din, cr = w.shape
+        assert din == d
+        # W' = w viewed as ((k, s', kappa), s); t[i, (k, s', kappa), j] = sum_s W'[(k,s',kappa), s] a[i, s, j]
+        wp = dev.dense(w.permute(0, 1, 3, 2)).reshape(cl * dout * cr, d)
+        rowptr, col, val, _ = dev.csr_arrays_any(wp)
+        t = torch.empty((Dl, cl, dout, cr, Dr), dtype=a.dtype, device=a.device)
+        st = lib.ptb_wapply_csr(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, int(w.dtype.is_complex),
+                                cl * dout * cr, d, Dr, rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                a.data_ptr(), t.data_ptr(), Dl, dev.stream_ptr(a.device))
+        _lib.check(st, "ptb_wapply_csr(apply_mpo)")
+        out.a[i] = dev.dense(t.permute(1, 0, 2, 3, 4)).reshape(cl * Dl, dout, cr * Dr)
+        assert is_qsparse(out.a[i], (out.qbonds[i], out.qsite, -out.qbonds[i + 1])), \
+            "sparsity pattern of MPS tensor does not match quantum numbers"
+    return out

@@ -18,7 +18,8 @@ import torch
 from . import _lib
 from . import _device as dev
 
-__all__ = ["lanczos_iteration", "eigh_krylov", "expm_krylov", "eigh_tridiag", "deferred_checks"]
+__all__ = ["lanczos_iteration", "arnoldi_iteration", "eigh_krylov", "expm_krylov", "eigh_tridiag",
+           "deferred_checks"]
 
 
 def _lanczos_steps(lib, afunc, x, numiter, V, scal, sfx, stream, scratch):
@@ -190,6 +191,65 @@ def lanczos_iteration(afunc, vstart, numiter):
     return (alpha, beta, dev.to_host(Vk).T if host_mode else Vk.T)
 
 
+def _arnoldi_core(afunc, vstart, numiter):
+    """Arnoldi recursion on the device: returns (|vstart|, hess (k_eff x k_eff, NumPy), Vk (k_eff x n)).
+    Projections and updates are GEMV-shaped calls of the engine (h = conj(V_j) w, w -= V_j^T h), applied
+    twice per step (classical Gram-Schmidt with re-orthogonalisation, numerically equivalent to the
+    reference's modified Gram-Schmidt loop krylov.py:86-88); norms by the Lanczos start kernel.  All steps
+    are enqueued without host synchronisation, the breakdown test (krylov.py:90-96) is applied afterwards."""
+    lib = _lib.load()
+    assert numiter >= 1
+    x = vstart.reshape(-1)
+    cplx = x.dtype.is_complex
+    x = dev.as_dtype(x, cplx)
+    n = x.shape[0]
+    device = x.device
+    start = lib.ptb_lanczos_start_z if cplx else lib.ptb_lanczos_start_d
+    scratch = dev.lanczos_scratch(device).data_ptr()
+    V = torch.empty((numiter, n), dtype=x.dtype, device=device)
+    hess = torch.zeros((numiter, numiter), dtype=x.dtype, device=device)
+    sub = torch.zeros(numiter + 1, dtype=dev.F64, device=device)          # [|vstart|, h[1,0], h[2,1], ...]
+    _lib.check(start(n, x.data_ptr(), V.data_ptr(), sub.data_ptr(), scratch, dev.stream_ptr(device)), "lanczos_start")
+    for j in range(numiter):
+        w = afunc(V[j]).reshape(-1)
+        if w.dtype != V.dtype:
+            w = w.to(V.dtype)
+        w = dev.dense(w)
+        if w.data_ptr() == V[j].data_ptr():
+            w = w.clone()
+        Vj = V[:j + 1]
+        for _ in range(2):
+            h = dev.gemm(w.reshape(1, n), Vj, trans_b=True, conj_b=True)     # h[0, k] = sum_i w_i conj(V[k, i])
+            hess[:j + 1, j] += h.reshape(-1)
+            dev.gemm_strided(cplx, 0, 0, 0, 1, n, j + 1, -h, j + 1, Vj, n, w, n, accumulate=True)
+        if j < numiter - 1:
+            _lib.check(start(n, w.data_ptr(), V[j + 1].data_ptr(), sub.data_ptr() + 8 * (j + 1), scratch,
+                             dev.stream_ptr(device)), "lanczos_start")
+    hs = hess.cpu().numpy()
+    subh = sub.cpu().numpy()
+    nrm = subh[0]
+    assert nrm > 0
+    keep = numiter
+    for j in range(numiter - 1):
+        if not subh[j + 1] >= 100 * n * np.finfo(float).eps:
+            warnings.warn(f"H[{j+1}, {j}] ~= 0 encountered during Arnoldi iteration.", RuntimeWarning)
+            keep = j + 1
+            break
+        hs[j + 1, j] = subh[j + 1]
+    return nrm, np.ascontiguousarray(hs[:keep, :keep]), V[:keep]
+
+
+def arnoldi_iteration(afunc, vstart, numiter):
+    """
+    "Matrix free" Arnoldi iteration (pytenet/krylov.py:60-107): returns `(hess, v)` with `hess` the
+    `k x k` upper Hessenberg matrix (NumPy) and `v` the `n x k` matrix of orthonormal Arnoldi vectors.
+    """
+    host_mode = dev.is_host(vstart)
+    x = dev.to_device(vstart)
+    _, hess, Vk = _arnoldi_core(_host_afunc(afunc) if host_mode else afunc, x, numiter)
+    return hess, (dev.to_host(Vk).T if host_mode else Vk.T)
+
+
 def eigh_tridiag(d, e):
     """
     Eigen-decomposition of a real symmetric tridiagonal matrix on the host
@@ -244,13 +304,16 @@ def eigh_krylov(afunc, vstart, numiter, numeig):
 def expm_krylov(afunc, vec, dt, numiter, hermitian=False):
     """
     Krylov subspace approximation of `expm(dt*A) @ vec` (pytenet/krylov.py:122-139).
-    Only the Hermitian branch is on the hot path (tdvp.py:229,238 pass hermitian=True).
+    The Hermitian branch is the hot path (tdvp.py:229,238 pass hermitian=True).
     """
-    if not hermitian:
-        raise NotImplementedError(
-            "the Arnoldi branch (krylov.py:137-139) is outside the effective-Hamiltonian path")
     host_mode = dev.is_host(vec)
     x = dev.to_device(vec)
+    if not hermitian:
+        # general branch (krylov.py:137-139): Arnoldi on the device, expm of the k x k Hessenberg matrix on the host
+        from scipy.linalg import expm
+        nrm, hess, Vk = _arnoldi_core(_host_afunc(afunc) if host_mode else afunc, x, numiter)
+        out = _combine(Vk, nrm * expm(dt * hess)[:, 0])
+        return dev.to_host(out) if host_mode else out
     if not host_mode and numiter <= _EXPM_DEVICE_MAX_ITER:
         return _expm_device(afunc, x, dt, numiter)
     nrm, alpha, beta, Vk = _lanczos_core(_host_afunc(afunc) if host_mode else afunc, x, numiter)

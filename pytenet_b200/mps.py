@@ -12,12 +12,13 @@ import numpy as np
 import torch
 
 from . import _device as dev
-from .block_sparse_util import qnumber_outer_sum, qnumber_flatten, block_sparse_qr
-from .bond_ops import split_block_sparse_matrix_svd
+from .block_sparse_util import qnumber_outer_sum, qnumber_flatten, block_sparse_qr, block_sparse_eigh, is_qsparse
+from .bond_ops import split_block_sparse_matrix_svd, retained_bond_indices
 from .scalars import crandn
 
-__all__ = ["MPS", "mps_vdot", "mps_norm", "mps_merge_tensor_pair", "mps_split_tensor_svd",
-           "mps_local_orthonormalize_left_qr", "mps_local_orthonormalize_right_qr"]
+__all__ = ["MPS", "mps_vdot", "mps_norm", "mps_add", "mps_merge_tensor_pair", "mps_split_tensor_svd",
+           "mps_local_orthonormalize_left_qr", "mps_local_orthonormalize_right_qr",
+           "mps_local_orthonormalize_left_svd", "mps_local_orthonormalize_right_svd"]
 
 
 def _scalar_block(device):
@@ -153,6 +154,110 @@ class MPS:
             nrm = -nrm
         return nrm
 
+    def compress(self, tol: float, mode="svd", direction="left"):
+        """
+        Compress and orthonormalise (mps.py:180-290): "svd" = site-local SVDs with singular-value
+        truncation, "density" = rounding by the local density matrix (McCulloch, J. Stat. Mech. (2007) P10014).
+        Returns `(original norm, scaling factor due to compression)`.
+        """
+        if mode == "svd":
+            return self._compress_svd(tol, direction)
+        if mode == "density":
+            return self._compress_density(tol)
+        raise ValueError(f'`mode` = {mode} invalid; must be "svd" or "density".')
+
+    def _compress_svd(self, tol, direction):
+        n = len(self.a)
+        if direction == "left":
+            nrm = self.orthonormalize(mode="right")
+            for i in range(n - 1):
+                self.a[i], self.a[i + 1], self.qbonds[i + 1] = mps_local_orthonormalize_left_svd(
+                    self.a[i], self.a[i + 1], self.qsite, self.qbonds[i:i + 2], tol)
+            self.a[-1], t, self.qbonds[-1] = mps_local_orthonormalize_left_svd(
+                self.a[-1], _scalar_block(self.device), self.qsite, self.qbonds[-2:], tol)
+            edge = n - 1
+        elif direction == "right":
+            nrm = self.orthonormalize(mode="left")
+            for i in reversed(range(1, n)):
+                self.a[i], self.a[i - 1], self.qbonds[i] = mps_local_orthonormalize_right_svd(
+                    self.a[i], self.a[i - 1], self.qsite, self.qbonds[i:i + 2], tol)
+            self.a[0], t, self.qbonds[0] = mps_local_orthonormalize_right_svd(
+                self.a[0], _scalar_block(self.device), self.qsite, self.qbonds[:2], tol)
+            edge = 0
+        else:
+            raise ValueError(f'`direction` = {direction} invalid; must be "left" or "right".')
+        for i in range(n):
+            assert is_qsparse(self.a[i], [self.qbonds[i], self.qsite, -self.qbonds[i + 1]]), \
+                "sparsity pattern of MPS tensor does not match quantum numbers"
+        assert tuple(t.shape) == (1, 1, 1)
+        t0 = t.reshape(-1)[0].item()
+        # absorb a potential phase factor into the edge tensor (mps.py:216,235)
+        self.a[edge] = self.a[edge] * (t0 / abs(t0))
+        return (nrm, abs(t0))
+
+    def _compress_density(self, tol):
+        lblocks = _mps_compute_left_blocks(self, self)
+        top = lblocks[-1].reshape(-1)[0].item()
+        assert tuple(lblocks[-1].shape) == (1, 1) and np.real(top) > 0
+        nrm = float(np.sqrt(np.real(top)))
+        dtype = self.a[-1].dtype
+        b = torch.ones((1, 1, 1), dtype=dtype, device=self.device)
+        u = torch.ones((1, 1, 1), dtype=dtype, device=self.device)
+        for i in reversed(range(1, self.nsites)):
+            # b[j, m] = sum_{s,j'} b_prev[j, s, j'] conj(u[m, s, j'])  then  b[i, s, m] = a[i, s, j] b[j, m]
+            bm = dev.gemm(b.reshape(b.shape[0], -1), u.reshape(u.shape[0], -1), trans_b=True, conj_b=True)
+            ai = self.a[i]
+            b = dev.gemm(ai.reshape(-1, ai.shape[2]), bm).reshape(ai.shape[0], ai.shape[1], bm.shape[1])
+            # rho[(s,m),(s',m')] = sum_{i,i'} b[i,s,m] L[i,i'] conj(b[i',s',m'])
+            lb = dev.gemm(lblocks[i], b.reshape(b.shape[0], -1), trans_a=True)             # [i', (s,m)] = L^T b
+            rho = dev.gemm(lb, b.reshape(b.shape[0], -1), trans_a=True, conj_b=True)       # [(s,m), (s',m')]
+            qnums_rho = qnumber_flatten((self.qsite, -self.qbonds[i + 1]))
+            assert is_qsparse(rho, (qnums_rho, -qnums_rho))
+            uu, evals, qnums_eig = block_sparse_eigh(rho, qnums_rho)
+            idx = retained_bond_indices(np.abs(evals), tol)       # eigenvalues are real but can be negative
+            uu = uu.index_select(1, torch.as_tensor(idx, device=uu.device))
+            qnums_eig = -qnums_eig[idx]
+            u = dev.dense(uu.reshape(ai.shape[1], b.shape[2], len(idx)).permute(2, 0, 1))
+            self.a[i] = u
+            self.qbonds[i] = qnums_eig
+        bm = dev.gemm(b.reshape(b.shape[0], -1), u.reshape(u.shape[0], -1), trans_b=True, conj_b=True)
+        a0 = self.a[0]
+        b = dev.gemm(a0.reshape(-1, a0.shape[2]), bm).reshape(a0.shape[0], a0.shape[1], bm.shape[1])
+        s = float(torch.linalg.norm(b.reshape(-1)).item())
+        self.a[0] = b / s
+        return (nrm, s / nrm)
+
+    @classmethod
+    def from_vector(cls, d: int, nsites: int, v, tol: float = 0, device=None):
+        """
+        MPS representation of the vector `v` by the TT-SVD algorithm for local dimension `d`; all quantum
+        numbers are zero (mps.py:304-337).  SVDs on the device (cuSOLVER), truncation rule on the host.
+        """
+        mps = cls(d * [0], [[0] for _ in range(nsites + 1)], fill="postpone", device=device)
+        v = dev.to_device(v, mps.device)
+        assert v.ndim == 1 and len(v) == d ** nsites, f"`v` has length {len(v)}, expecting {d**nsites}."
+        v = v.reshape(1, -1)
+        from .block_sparse_util import _SVD_DRIVER
+        for i in range(nsites):
+            bleft = v.shape[0]
+            u, s, vh = torch.linalg.svd(dev.dense(v).reshape(bleft * d, d ** (nsites - i - 1)), full_matrices=False,
+                                        driver=_SVD_DRIVER)
+            idx = retained_bond_indices(s.cpu().numpy(), tol)
+            it = torch.as_tensor(idx, device=v.device)
+            u = u.index_select(1, it); s = s.index_select(0, it)
+            v = dev.dense(vh).index_select(0, it) * s[:, None]
+            mps.a[i] = dev.dense(u.reshape(bleft, d, len(idx)))
+            mps.qbonds[i + 1] = np.zeros(len(idx), dtype=int)
+        assert tuple(v.shape) == (1, 1)
+        mps.a[-1] = mps.a[-1] * v.reshape(-1)[0]
+        return mps
+
+    def __add__(self, other):
+        return mps_add(self, other)
+
+    def __sub__(self, other):
+        return mps_add(self, other, alpha=-1)
+
     def to_vector(self) -> np.ndarray:
         """Full Hilbert-space vector as a NumPy array (validation at small sizes; mps.py:292-301)."""
         psi = self.a[0]
@@ -160,6 +265,21 @@ class MPS:
             psi = mps_merge_tensor_pair(psi, nxt)
         assert psi.ndim == 3 and psi.shape[0] == 1 and psi.shape[2] == 1
         return dev.to_host(psi.reshape(-1))
+
+
+def _mps_compute_left_blocks(chi: MPS, psi: MPS):
+    """All partial contractions of `<chi | psi>` from the left (mps.py:384-427):
+    `l_next[j, j'] = sum a[i,s,j] l[i,i'] conj(b[i',s,j'])`, two GEMMs per site on the engine."""
+    nsites = chi.nsites
+    assert nsites == psi.nsites
+    first = psi.a[0]
+    blocks = [torch.eye(1, dtype=first.dtype, device=first.device)]
+    for a, b in zip(psi.a, chi.a):
+        dl, d, dr = a.shape
+        dlp, _, drp = b.shape
+        t = dev.gemm(blocks[-1], b.reshape(dlp, d * drp), conj_b=True)                    # [i, (s, j')]
+        blocks.append(dev.gemm(a.reshape(dl * d, dr), t.reshape(dl * d, drp), trans_a=True))   # [j, j']
+    return blocks
 
 
 def mps_vdot(chi: MPS, psi: MPS):
@@ -220,6 +340,27 @@ def mps_local_orthonormalize_right_qr(a, a_prev, qsite, qbonds):
     return a, _right_multiply_t(a_prev, r), -qbond
 
 
+def mps_local_orthonormalize_left_svd(a, a_next, qsite, qbonds, tol: float):
+    """Left-orthonormalise `a` by a truncated SVD and absorb `sigma v` into the next tensor (mps.py:494-508)."""
+    s = a.shape
+    assert len(s) == 3
+    u, sigma, v, qbond = split_block_sparse_matrix_svd(
+        a.reshape(s[0] * s[1], s[2]), qnumber_flatten((qbonds[0], qsite)), qbonds[1], tol)
+    sv = dev.dense(v) * torch.as_tensor(sigma, device=a.device)[:, None]
+    return dev.dense(u.reshape(s[0], s[1], u.shape[1])), _left_multiply(sv, a_next), qbond
+
+
+def mps_local_orthonormalize_right_svd(a, a_prev, qsite, qbonds, tol: float):
+    """Right-orthonormalise `a` by a truncated SVD and absorb `u sigma` into the previous tensor (mps.py:511-525)."""
+    s = a.shape
+    assert len(s) == 3
+    u, sigma, v, qbond = split_block_sparse_matrix_svd(
+        a.reshape(s[0], s[1] * s[2]), qbonds[0], qnumber_flatten([-np.asarray(qsite), qbonds[1]]), tol)
+    us = dev.dense(u) * torch.as_tensor(sigma, device=a.device)
+    prev = dev.gemm(a_prev.reshape(-1, a_prev.shape[-1]), us).reshape(tuple(a_prev.shape[:-1]) + (us.shape[1],))
+    return dev.dense(v.reshape(v.shape[0], s[1], s[2])), prev, qbond
+
+
 def mps_merge_tensor_pair(a0, a1):
     """Contract two neighbouring MPS tensors into `(b0, d0*d1, b2)` (mps.py:528-535)."""
     b0, d0, b1 = a0.shape
@@ -256,3 +397,37 @@ def mps_split_tensor_svd(a, qsite0, qsite1, qbonds_outer, svd_distr: str, tol=0)
     else:
         raise ValueError('`svd_distr` parameter must be "left", "right" or "sqrt".')
     return dev.dense(u.reshape(b0, d0, nb)), dev.dense(v.reshape(nb, d1, b2)), qbond
+
+
+def mps_add(mps0: MPS, mps1: MPS, alpha=1) -> MPS:
+    """
+    Logical sum `mps0 + alpha mps1`: virtual bond dimensions add, tensors become block diagonal
+    (mps.py:571-617).  Pure data movement on the device.
+    """
+    assert mps0.nsites == mps1.nsites
+    nsites = mps0.nsites
+    assert np.array_equal(mps0.qsite, mps1.qsite)
+    assert np.array_equal(mps0.qbonds[0], mps1.qbonds[0]) and np.array_equal(mps0.qbonds[-1], mps1.qbonds[-1])
+    qbonds = [np.asarray(mps0.qbonds[0]).copy()]
+    qbonds += [np.concatenate((mps0.qbonds[i], mps1.qbonds[i])) for i in range(1, nsites)]
+    qbonds.append(np.asarray(mps0.qbonds[-1]).copy())
+    out = MPS(mps0.qsite, qbonds, fill="postpone", device=mps0.device)
+    cplx = (dev.any_complex(*mps0.a, *mps1.a) or isinstance(alpha, complex)) if nsites else False
+    a0 = [dev.as_dtype(t, cplx) for t in mps0.a]
+    a1 = [dev.as_dtype(t, cplx) for t in mps1.a]
+    if nsites == 1:
+        out.a[0] = a0[0] + alpha * a1[0]
+    elif nsites > 1:
+        out.a[0] = torch.cat((a0[0], alpha * a1[0]), dim=2)
+        for i in range(1, nsites - 1):
+            s0, s1 = a0[i].shape, a1[i].shape
+            t = torch.zeros((s0[0] + s1[0], s0[1], s0[2] + s1[2]), dtype=a0[i].dtype, device=a0[i].device)
+            t[:s0[0], :, :s0[2]] = a0[i]
+            t[s0[0]:, :, s0[2]:] = a1[i]
+            out.a[i] = t
+        out.a[-1] = torch.cat((a0[-1], a1[-1]), dim=0)
+    for i in range(nsites):
+        out.a[i] = dev.dense(out.a[i])
+        assert is_qsparse(out.a[i], (out.qbonds[i], out.qsite, -out.qbonds[i + 1])), \
+            "sparsity pattern of MPS tensor does not match quantum numbers"
+    return out

@@ -382,6 +382,66 @@ def molecular_dmrg_case():
     print("dmrg_molecular_N8.npz: MPO bonds", h.bond_dims, "energies", en, "ED (sector)", e_ed)
 
 
+def mps_ops_case():
+    """apply_mpo, MPS.compress (svd both directions, density), mps_add and
+    MPS.from_vector on a Heisenberg chain with quantum numbers (reference test_mps.py / test_chain_ops.py
+    style, seeded); the oracle restatement (oracle/mps_ops.py) is checked against the reference here."""
+    import oracle.mps_ops as om
+    L = 6
+    h = ptn.heisenberg_xxz_1d_mpo(L, 0.7, 1.1, 0.3)
+    rng = np.random.default_rng(77)
+    qbonds = [np.array([0])]
+    for i in range(L - 1):
+        cand = np.array([q + h.qsite for q in qbonds[-1]]).reshape(-1)
+        qbonds.append(np.sort(cand)[rng.permutation(len(cand))[:min(len(cand), 7)]])
+    qbonds.append(np.array([2]))
+    psi = ptn.MPS(h.qsite, qbonds, fill="random", rng=rng)
+    chi = ptn.MPS(h.qsite, qbonds, fill="random", rng=rng)
+    out = {}
+    save_mpo(out, "h", h); save_mps(out, "psi", psi); save_mps(out, "chi", chi)
+    # apply_mpo
+    hp = ptn.apply_mpo(h, psi)
+    ohp = om.apply_mpo(h.a, h.qbonds, to_chain(psi))
+    assert all(np.array_equal(x, y) for x, y in zip(hp.qbonds, ohp.qbonds))
+    assert all(rel(x, y) < 1e-14 for x, y in zip(ohp.a, hp.a))
+    save_mps(out, "hpsi", hp)
+    out["hpsi/vec"] = hp.to_vector()
+    # mps_add
+    alpha = 0.3 - 0.8j
+    sm = ptn.mps.mps_add(psi, chi, alpha)
+    osm = om.mps_add(to_chain(psi), to_chain(chi), alpha)
+    assert all(np.array_equal(x, y) for x, y in zip(sm.qbonds, osm.qbonds))
+    assert all(np.array_equal(x, y) for x, y in zip(osm.a, sm.a))
+    out["add/alpha"] = np.array(alpha); out["add/vec"] = sm.to_vector()
+    save_mps(out, "add", sm)
+    # compress: svd in both directions and density mode, with and without truncation
+    for tag, tol, mode, direction in [("svd_l0", 0.0, "svd", "left"), ("svd_r0", 0.0, "svd", "right"),
+                                      ("svd_l", 1e-3, "svd", "left"), ("svd_r", 1e-3, "svd", "right"),
+                                      ("den", 1e-3, "density", "left"), ("den0", 0.0, "density", "left")]:
+        p = copy.deepcopy(hp)
+        nrm, scale = p.compress(tol, mode=mode, direction=direction)
+        o = to_chain(copy.deepcopy(hp))
+        onrm, oscale = (om.compress_svd(o, tol, direction) if mode == "svd" else om.compress_density(o, tol))
+        assert abs(nrm - onrm) < 1e-12 * nrm and abs(scale - oscale) < 1e-12, (tag, nrm, onrm, scale, oscale)
+        assert all(np.array_equal(x, y) for x, y in zip(p.qbonds, o.qbonds)), tag
+        assert rel(o.to_vector(), p.to_vector()) < 1e-11, (tag, rel(o.to_vector(), p.to_vector()))
+        out[f"cmp/{tag}/tol"] = np.array(tol); out[f"cmp/{tag}/nrm"] = np.array(nrm)
+        out[f"cmp/{tag}/scale"] = np.array(scale); out[f"cmp/{tag}/vec"] = p.to_vector()
+        out[f"cmp/{tag}/bond_dims"] = np.array(p.bond_dims)
+        for i, q in enumerate(p.qbonds):
+            out[f"cmp/{tag}/qb{i}"] = np.asarray(q)
+    # from_vector (TT-SVD)
+    v = ptn.crandn(3 ** 5, rng)
+    for tag, tol in (("fv0", 0.0), ("fv", 1e-2)):
+        m = ptn.MPS.from_vector(3, 5, v, tol=tol)
+        o = om.from_vector(3, 5, v, tol=tol)
+        assert m.bond_dims == o.bond_dims and rel(o.to_vector(), m.to_vector()) < 1e-12
+        out[f"{tag}/tol"] = np.array(tol); out[f"{tag}/vec"] = m.to_vector(); out[f"{tag}/bond_dims"] = np.array(m.bond_dims)
+    out["fv/input"] = v
+    np.savez_compressed(os.path.join(HERE, "mps_ops.npz"), **out)
+    print("mps_ops.npz: oracle == reference; H psi bond dims", hp.bond_dims)
+
+
 if __name__ == "__main__":
     chain_ops_cases()
     mpo_inner_case()
@@ -391,4 +451,5 @@ if __name__ == "__main__":
     dmrg_notebook_case()
     basics_notebook_case()
     molecular_dmrg_case()
+    mps_ops_case()
     print("all golden fixtures written to", HERE)

@@ -262,3 +262,28 @@ def test_deferred_breakdown_warning(cuda_lib):
             assert not any(issubclass(r.category, RuntimeWarning) for r in rec)
         assert any(issubclass(r.category, RuntimeWarning) and "Lanczos" in str(r.message) for r in rec)
     assert got.dtype == torch.float64 and rel(got.cpu().numpy(), np.exp(-0.5 * np.array([1.0, 2.0, 3.0]))) < 1e-12
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+def test_arnoldi_and_general_expm(cuda_lib, cplx):
+    """Arnoldi branch (krylov.py:60-107, :137-139) for a non-Hermitian operator: Hessenberg relation
+    V^H A V = H, orthonormal V, and expm_krylov(hermitian=False) against scipy's dense expm."""
+    import pytenet_b200 as ptb
+    from scipy.linalg import expm
+    rng = np.random.default_rng(9)
+    n, k = 60, 60
+    m = rng.normal(size=(n, n)) / np.sqrt(n)
+    v = rng.normal(size=n)
+    if cplx:
+        m = m + 1j * rng.normal(size=(n, n)) / np.sqrt(n); v = v + 1j * rng.normal(size=n)
+    hess, V = ptb.arnoldi_iteration(dev_matvec(m), cu(v), 12)
+    Vh = V.cpu().numpy()
+    assert rel(Vh.conj().T @ Vh, np.eye(12)) < 1e-13
+    assert rel(Vh.conj().T @ m @ Vh, hess) < 1e-12
+    assert np.allclose(np.tril(hess, -2), 0)
+    dt = 0.4 - 0.3j if cplx else 0.4
+    got = ptb.expm_krylov(dev_matvec(m), cu(v), dt, k)            # default: hermitian=False, as the reference
+    assert rel(got.cpu().numpy(), expm(dt * m) @ v) < 1e-10
+    # host-buffer entry
+    got_h = ptb.expm_krylov(lambda x: m @ x, v, dt, 25)
+    assert isinstance(got_h, np.ndarray) and rel(got_h, expm(dt * m) @ v) < 1e-10

@@ -140,3 +140,30 @@ def test_retained_indices_and_sectors():
     assert np.all(np.diff(qb) >= 0)              # sector-ascending layout
     q, r, qi = ob.block_sparse_qr(a, q0, q1)
     assert rel(q @ r, a) < 1e-13 and rel(q.T @ q, np.identity(q.shape[1])) < 1e-13
+
+
+def test_mps_ops_match_reference(golden_dir):
+    """apply_mpo, mps_add, compress (svd / density) and from_vector of oracle/mps_ops.py against the fixture
+    generated from the reference."""
+    import copy
+    import oracle.mps_ops as om
+    z = np.load(os.path.join(golden_dir, "mps_ops.npz"))
+    hw, hq, n = load_op(z)
+    psi, chi = load_chain(z, "psi", n), load_chain(z, "chi", n)
+    hp = om.apply_mpo(hw, hq, psi)
+    assert all(np.array_equal(hp.qbonds[i], z[f"hpsi/qb{i}"]) for i in range(n + 1))
+    assert all(rel(hp.a[i], z[f"hpsi/a{i}"]) < 1e-14 for i in range(n))
+    sm = om.mps_add(psi, chi, complex(z["add/alpha"]))
+    assert all(np.array_equal(sm.a[i], z[f"add/a{i}"]) for i in range(n))
+    for tag, mode, direction in [("svd_l0", "svd", "left"), ("svd_r0", "svd", "right"), ("svd_l", "svd", "left"),
+                                 ("svd_r", "svd", "right"), ("den", "density", "left"), ("den0", "density", "left")]:
+        p = copy.deepcopy(hp)
+        tol = float(z[f"cmp/{tag}/tol"])
+        nrm, scale = om.compress_svd(p, tol, direction) if mode == "svd" else om.compress_density(p, tol)
+        assert abs(nrm - float(z[f"cmp/{tag}/nrm"])) < 1e-12 * nrm and abs(scale - float(z[f"cmp/{tag}/scale"])) < 1e-12
+        assert p.bond_dims == list(z[f"cmp/{tag}/bond_dims"])
+        assert all(np.array_equal(p.qbonds[i], z[f"cmp/{tag}/qb{i}"]) for i in range(n + 1))
+        assert rel(p.to_vector(), z[f"cmp/{tag}/vec"]) < 1e-11
+    for tag in ("fv0", "fv"):
+        m = om.from_vector(3, 5, z["fv/input"], tol=float(z[f"{tag}/tol"]))
+        assert m.bond_dims == list(z[f"{tag}/bond_dims"]) and rel(m.to_vector(), z[f"{tag}/vec"]) < 1e-12
