@@ -52,7 +52,10 @@ def test_mps_add(case):
     sm = ptb.mps_add(psi, chi, alpha)
     for i in range(n):
         assert np.array_equal(sm.qbonds[i], z[f"add/qb{i}"])
-        assert np.array_equal(sm.a[i].cpu().numpy(), z[f"add/a{i}"])
+        # alpha * a is one complex product per entry: the device fuses multiply-adds, NumPy does not (last-bit)
+        got = sm.a[i].cpu().numpy()
+        assert got.shape == z[f"add/a{i}"].shape and np.allclose(got, z[f"add/a{i}"], rtol=1e-14, atol=0)
+        assert np.array_equal(got == 0, z[f"add/a{i}"] == 0)               # block structure exact
     assert rel((psi - chi).to_vector(), psi.to_vector() - chi.to_vector()) < 1e-13
     assert rel((psi + chi).to_vector(), psi.to_vector() + chi.to_vector()) < 1e-13
 
