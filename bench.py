@@ -115,7 +115,15 @@ def block_sparse_block(torch, ptb, device, time_ms, D=2048):
     ms_d = time_ms(lambda: ptb.apply_local_hamiltonian(a, w, l, r), reps=2)
     ms_b = time_ms(lambda: plan.apply(a, w, l, r), reps=5)
     fa = f_alg(D, d1 * d1, 6)
-    return {"workload": f"two-site Fermi-Hubbard heff matvec a ({D},16,{D}), h2 (6,16,16,6), {int((sizes > 0).sum())} "
+    fc = plan.flop_counts(nnz_w=int(np.count_nonzero(w2)))
+    t1_bytes = 16.0 * D * d1 * d1 * 6 * D
+    extra = {"flops_visited": fc["visited"], "flops_exact_sector_blocks": fc["exact"], "flops_w_step": fc["w_step"],
+             "tflops_exec_banded_path": (fc["visited"] + fc["w_step"]) / ms_b / 1e9,
+             "note": "dense-layout intermediates: t1 and t2 (%.1f GB each) are written and read once per matvec "
+                     "(>= %.1f ms at the HBM peak); the GEMMs visit whole k-tiles of whole output tiles "
+                     "(flops_visited), a sector-packed layout would execute flops_exact_sector_blocks"
+                     % (t1_bytes / 1e9, 4 * t1_bytes / 6.5e12 * 1e3)}
+    return {**extra, "workload": f"two-site Fermi-Hubbard heff matvec a ({D},16,{D}), h2 (6,16,16,6), {int((sizes > 0).sum())} "
                         f"(N,Sz) sectors (Gaussian size profile, max {int(sizes.max())})",
             "tensor_fill": float((a != 0).double().mean().item()), "ms_dense": ms_d, "ms_sector_banded": ms_b,
             "speedup": ms_d / ms_b, "gflops_alg_dense_path": fa / ms_d / 1e6, "gflops_alg_banded_path": fa / ms_b / 1e6,

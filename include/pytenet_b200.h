@@ -83,6 +83,20 @@ int ptb_gemm_banded(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, 
                     int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c, int accumulate,
                     const int32_t* ktab, void* stream);
 int ptb_gemm_tile_shape(int dtype, int* bm, int* bn, int* bk);
+/* Segmented GEMM (sums over an outer index inside ONE launch):  C[b] (+)= sum_seg A_seg^T B_seg  with both
+ * operands stored K-major (A is K x M, B is K x N, row-major: trans_a = 1, trans_b = 0 in ptb_gemm terms).
+ * Output tile t (same numbering as ptb_gemm_banded) accumulates the segments
+ * segs[seg_ptr[t] .. seg_ptr[t+1]); a segment is 4 int32 {first k-tile, end k-tile, selector, 0}, and
+ * sel_off[2*selector], sel_off[2*selector+1] are ELEMENT offsets added to the a / b base pointers for that
+ * segment.  Step 3 of the sector path,  out[i',s',j'] = sum_k sum_i l[i,k,i'] t2[i,k,s',j'],  uses one selector per
+ * left MPO index k (offsets k*Dlp and k*d*Drp, lda = chi_l*Dlp, ldb = chi_l*d*Drp) and per tile only the k-tile
+ * ranges the quantum numbers allow -- one launch instead of chi_l accumulating ones.  A tile without segments is
+ * zero (or untouched when accumulating).  All tables are device arrays (segs 16-byte aligned).  TMA engine only. */
+int ptb_gemm_segmented(int dtype, int conj_b, int64_t m, int64_t n, int64_t k, const void* a, int64_t lda,
+                       const void* b, int64_t ldb, void* c, int64_t ldc, int64_t batch, int64_t stride_a,
+                       int64_t stride_b, int64_t stride_c, int accumulate, const int32_t* seg_ptr, const int32_t* segs,
+                       const int64_t* sel_off, void* stream);
+
 
 /* Fused GEMM + all-gather: C = op(A) op(B) is written to n_dst (1..8) output buffers of identical
  * layout in the kernel's epilogue.  c_list is a HOST array of device pointers; entries beyond the

@@ -28,6 +28,8 @@ SIGNATURES = {
                                _i64, _i64, _i64, _i64, _int, _int, _ptr, _sz, _ptr]),
     "ptb_gemm_banded": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                                _i64, _i64, _i64, _i64, _int, _ptr, _ptr]),
+    "ptb_gemm_segmented": (_int, [_int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64,
+                                  _int, _ptr, _ptr, _ptr, _ptr]),
     "ptb_gemm_tile_shape": (_int, [_int, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
     "ptb_gemm_multicast": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64,
                                   ctypes.POINTER(_ptr), _int, _i64, _ptr]),

@@ -305,6 +305,30 @@ int ptb_gemm_banded(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, 
     return rc == 1 ? PTB_ERR_ALIGNMENT : rc;
 }
 
+int ptb_gemm_segmented(int dtype, int conj_b, int64_t m, int64_t n, int64_t k, const void* a, int64_t lda,
+                       const void* b, int64_t ldb, void* c, int64_t ldc, int64_t batch, int64_t stride_a,
+                       int64_t stride_b, int64_t stride_c, int accumulate, const int32_t* seg_ptr, const int32_t* segs,
+                       const int64_t* sel_off, void* stream) {
+    if (!a || !b || !c || !seg_ptr || !segs || !sel_off) return PTB_ERR_BAD_ARG;
+    if (m <= 0 || n <= 0 || k <= 0 || batch <= 0 || !fits_int({m, n, k, batch})) return PTB_ERR_BAD_ARG;
+    GemmParams p;
+    p.A = static_cast<const double*>(a);
+    p.B = static_cast<const double*>(b);
+    p.C = static_cast<double*>(c);
+    p.M = (int)m; p.N = (int)n; p.K = (int)k;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.sA = stride_a; p.sB = stride_b; p.sC = stride_c;
+    p.batch = (int)batch;
+    p.accumulate = accumulate;
+    p.tiles_m = p.tiles_n = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset table is int64");
+    const long long* off = reinterpret_cast<const long long*>(sel_off);
+    if (dtype == PTB_COMPLEX128) return launch_ws_segmented<true>(conj_b, p, st, seg_ptr, segs, off);
+    if (dtype == PTB_REAL64) return launch_ws_segmented<false>(0, p, st, seg_ptr, segs, off);
+    return PTB_ERR_BAD_DTYPE;
+}
+
 int ptb_gemm_tile_shape(int dtype, int* bm, int* bn, int* bk) {
     if (!bm || !bn || !bk) return PTB_ERR_BAD_ARG;
     if (dtype == PTB_COMPLEX128) { *bm = WsCfg<true>::BM; *bn = WsCfg<true>::BN; *bk = WsCfg<true>::BK; return PTB_OK; }

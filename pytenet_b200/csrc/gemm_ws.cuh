@@ -81,6 +81,13 @@ struct WsParams {
     // sector-banded GEMM: per (batch, tile) range [lo, hi) of k-tiles that can be non-zero given the
     // quantum-number sectors of the operands (nullptr = full range); hi <= lo skips the tile's main loop
     const int2* ktab;
+    // segmented GEMM (SEG kernels): tile t accumulates the segments segs[seg_ptr[t] .. seg_ptr[t+1]); a segment is
+    // {first k-tile, end k-tile, selector, unused}; sel_off[2*selector + {0,1}] are element offsets added to the
+    // A / B base pointers for that segment (mn-contiguous operands only).  Used for sums over an outer index
+    // (e.g. the left MPO bond in step 3 of the sector path) that would otherwise need one accumulating launch each.
+    const int* seg_ptr;
+    const int4* segs;
+    const long long* sel_off;
 };
 
 // ---- mbarrier / TMA primitives ---------------------------------------------------------
@@ -211,7 +218,7 @@ __device__ __forceinline__ void ws_tile_coords(const WsParams& p, long long t, i
     tn = (tile % per_group) / gsize;
 }
 
-template <bool CPLX, bool A_KC, bool B_KC, bool CONJB>
+template <bool CPLX, bool A_KC, bool B_KC, bool CONJB, bool SEG = false>
 __global__ void __launch_bounds__(WsCfg<CPLX>::THREADS, 1)
 gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
     using Cfg = WsCfg<CPLX>;
@@ -268,25 +275,42 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
             const double* Ag = p.A + (int64_t)bz * p.sA * E;
             const double* Bg = p.B + (int64_t)bz * p.sB * E;
             const int ba = p.batched_a ? bz : 0, bb = p.batched_b ? bz : 0;
-            for (int kt = kt_begin; kt < kt_end; kt++) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                double* a_st = sA + stage * SA;
-                double* b_st = sB + stage * SB;
-                const int k0 = kt * BK;
-                uint32_t bytes = producer_operand<CPLX, A_KC, BM>(false, a_st, &tmA, Ag, p.lda, m0, k0, p.M, p.K, ba,
-                                                                  &full[stage], lane);
-                bytes += producer_operand<CPLX, B_KC, BN>(false, b_st, &tmB, Bg, p.ldb, n0, k0, p.N, p.K, bb,
-                                                          &full[stage], lane);
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full[stage], bytes);
-                    producer_operand<CPLX, A_KC, BM>(true, a_st, &tmA, Ag, p.lda, m0, k0, p.M, p.K, ba, &full[stage],
-                                                     lane);
-                    producer_operand<CPLX, B_KC, BN>(true, b_st, &tmB, Bg, p.ldb, n0, k0, p.N, p.K, bb, &full[stage],
-                                                     lane);
+            int seg = 0, seg_end = 1;
+            if constexpr (SEG) {
+                const long long tix = (long long)bz * tiles_per_batch + (long long)tm * p.tiles_n + tn;
+                seg = p.seg_ptr[tix];
+                seg_end = p.seg_ptr[tix + 1];
+            }
+            for (; seg < seg_end; seg++) {
+                const double* Ags = Ag;
+                const double* Bgs = Bg;
+                if constexpr (SEG) {
+                    const int4 sg = p.segs[seg];
+                    kt_begin = max(sg.x, 0);
+                    kt_end = min(sg.y, KT_all);
+                    Ags += p.sel_off[2 * sg.z] * E;
+                    Bgs += p.sel_off[2 * sg.z + 1] * E;
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                for (int kt = kt_begin; kt < kt_end; kt++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    double* a_st = sA + stage * SA;
+                    double* b_st = sB + stage * SB;
+                    const int k0 = kt * BK;
+                    uint32_t bytes = producer_operand<CPLX, A_KC, BM>(false, a_st, &tmA, Ags, p.lda, m0, k0, p.M, p.K,
+                                                                      ba, &full[stage], lane);
+                    bytes += producer_operand<CPLX, B_KC, BN>(false, b_st, &tmB, Bgs, p.ldb, n0, k0, p.N, p.K, bb,
+                                                              &full[stage], lane);
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&full[stage], bytes);
+                        producer_operand<CPLX, A_KC, BM>(true, a_st, &tmA, Ags, p.lda, m0, k0, p.M, p.K, ba,
+                                                         &full[stage], lane);
+                        producer_operand<CPLX, B_KC, BN>(true, b_st, &tmB, Bgs, p.ldb, n0, k0, p.N, p.K, bb,
+                                                         &full[stage], lane);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
         return;
@@ -326,6 +350,18 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
 #pragma unroll
                 for (int e = 0; e < 2 * E; e++) acc[i][j][e] = 0.0;
 
+        int seg = 0, seg_end = 1;
+        if constexpr (SEG) {
+            const long long tix = (long long)bz * tiles_per_batch + (long long)tm * p.tiles_n + tn;
+            seg = p.seg_ptr[tix];
+            seg_end = p.seg_ptr[tix + 1];
+        }
+        for (; seg < seg_end; seg++) {
+        if constexpr (SEG) {
+            const int4 sg = p.segs[seg];
+            kt_begin = max(sg.x, 0);
+            kt_end = min(sg.y, KT_all);
+        }
         for (int kt = kt_begin; kt < kt_end; kt++) {
             mbar_wait(&full[stage], phase);
             const double* As = sA + stage * SA + a_off;
@@ -368,6 +404,7 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        }   // segments
 
         // epilogue (overlaps the producer's prefetch of the next tile); with n_extra > 0 the tile is
         // also written to the peer GPUs' buffers (compute + all-gather in one kernel)
@@ -523,10 +560,10 @@ static bool make_kc_map(CUtensorMap* map, const double* ptr, int MN, int K, int6
     return r == CUDA_SUCCESS;
 }
 
-template <bool CPLX, bool A_KC, bool B_KC, bool CONJB>
+template <bool CPLX, bool A_KC, bool B_KC, bool CONJB, bool SEG = false>
 static int launch_ws_inst(const WsParams& p, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
     using Cfg = WsCfg<CPLX>;
-    auto kern = gemm_ws_kernel<CPLX, A_KC, B_KC, CONJB>;
+    auto kern = gemm_ws_kernel<CPLX, A_KC, B_KC, CONJB, SEG>;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
@@ -621,6 +658,7 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     p.tail_split = 1;
     p.tail_begin = 0;
     p.ktab = reinterpret_cast<const int2*>(ktab);
+    p.seg_ptr = nullptr; p.segs = nullptr; p.sel_off = nullptr;
     if (ktab != nullptr && (reinterpret_cast<uintptr_t>(ktab) % 8) != 0) return PTB_ERR_ALIGNMENT;
     if (split_k != 1 && n_extra == 0 && part_ws != nullptr && ktab == nullptr) {
         const int KT = (gp.K + Cfg::BK - 1) / Cfg::BK;
@@ -678,6 +716,40 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
         case 7: return launch_ws_inst<CPLX, true, true, CPLX>(p, ta, tb, stream);
     }
     return 1;
+}
+
+// Segmented GEMM on mn-contiguous operands (A stored K x M, B stored K x N): see WsParams::seg_ptr.
+template <bool CPLX>
+static int launch_ws_segmented(int conjB, const GemmParams& gp, cudaStream_t stream, const int* seg_ptr,
+                               const int* segs, const long long* sel_off) {
+    using Cfg = WsCfg<CPLX>;
+    auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+    if (!al16(gp.A) || !al16(gp.B) || !al16(gp.C) || !al16(segs)) return PTB_ERR_ALIGNMENT;
+    if (!CPLX && (((gp.lda | gp.ldb | gp.sA | gp.sB) & 1) || (gp.M & 1) || (gp.N & 1))) return PTB_ERR_ALIGNMENT;
+    if (gp.K < 1) return PTB_ERR_BAD_ARG;
+    WsParams p;
+    p.A = gp.A; p.B = gp.B; p.C = gp.C;
+    p.M = gp.M; p.N = gp.N; p.K = gp.K;
+    p.lda = gp.lda; p.ldb = gp.ldb; p.ldc = gp.ldc;
+    p.sA = gp.sA; p.sB = gp.sB; p.sC = gp.sC;
+    p.batch = gp.batch;
+    p.accumulate = gp.accumulate;
+    p.tiles_m = (gp.M + Cfg::BM - 1) / Cfg::BM;
+    p.tiles_n = (gp.N + Cfg::BN - 1) / Cfg::BN;
+    p.batched_a = (gp.sA != 0 && gp.batch > 1) ? 1 : 0;
+    p.batched_b = (gp.sB != 0 && gp.batch > 1) ? 1 : 0;
+    p.n_extra = 0;
+    for (int i = 0; i < 7; i++) p.Cx[i] = nullptr;
+    p.split_k = 1; p.Cpart = nullptr; p.tail_split = 1; p.tail_begin = 0;
+    p.ktab = nullptr;
+    p.seg_ptr = seg_ptr;
+    p.segs = reinterpret_cast<const int4*>(segs);
+    p.sel_off = sel_off;
+    CUtensorMap ta, tb;
+    memset(&ta, 0, sizeof(ta));
+    memset(&tb, 0, sizeof(tb));
+    if (CPLX && conjB) return launch_ws_inst<CPLX, false, false, CPLX, true>(p, ta, tb, stream);
+    return launch_ws_inst<CPLX, false, false, false, true>(p, ta, tb, stream);
 }
 
 }  // namespace ptb

@@ -29,6 +29,9 @@ from . import _device as dev
 
 __all__ = ["HeffSectorPlan", "EnvSectorPlan", "BondSectorPlan", "tile_k_ranges"]
 
+import os
+_SEGMENTED = os.environ.get("PYTENET_B200_SEGMENTED", "1") != "0"
+
 _EMPTY_LO = np.iinfo(np.int64).max
 _EMPTY_HI = -1
 
@@ -130,6 +133,20 @@ class HeffSectorPlan:
             self.tab3_host.append(tabs)
         self.tab1 = None
         self.tab3 = None
+        # step 3 as ONE segmented launch (ptb_gemm_segmented): per output tile the list of (k-tile range, left MPO
+        # index) pairs that can contribute; selector k adds k*Dlp / k*dout*Drp elements to the l / t2 base pointers
+        allk = np.stack(self.tab3_host, axis=-2)                      # (dout, tiles_m, tiles_n, cl, 2)
+        mask = allk[..., 1] > allk[..., 0]
+        flat = mask.reshape(-1, cl)
+        self.seg_ptr_host = np.concatenate([[0], np.cumsum(flat.sum(axis=1))]).astype(np.int32)
+        tile_idx, k_idx = np.nonzero(flat)
+        lohi = allk.reshape(-1, cl, 2)[tile_idx, k_idx]
+        segs = np.zeros((max(len(k_idx), 1), 4), dtype=np.int32)
+        segs[:len(k_idx), 0:2] = lohi
+        segs[:len(k_idx), 2] = k_idx
+        self.segs_host = segs
+        self.sel_off_host = np.stack([np.arange(cl) * Dlp, np.arange(cl) * dout * Drp], axis=1).astype(np.int64)
+        self.seg3 = None
 
         # bookkeeping for benchmarks: fraction of the dense k-tile visits that remain
         kt1 = -(-Dr // bk)
@@ -140,11 +157,48 @@ class HeffSectorPlan:
         den3 = float(cl * dout * (-(-Dlp // bm)) * (-(-Drp // bn)) * kt3)
         self.visit_fraction = (vis1 / max(den1, 1.0), vis3 / max(den3, 1.0))
 
+    def flop_counts(self, nnz_w=None):
+        """Floating-point operations of one apply(): `visited` = what the banded / segmented GEMMs execute
+        (whole k-tiles of whole output tiles), `exact` = the non-zero sector blocks only (what a sector-packed
+        contraction would execute), both for the two large GEMM steps; `w_step` = 2 * nnz(W) * 4 (complex x real)
+        per (i, j') column of the W step when `nnz_w` is given."""
+        Dl, d, Dr, cl, cr, dout, Dlp, Drp = self.dims
+        bm, bn, bk = self.tile
+        per_ktile = 8.0 * bm * bn * bk if self.cplx else 2.0 * bm * bn * bk
+        vis1 = float(np.sum(self.tab1_host[..., 1] - self.tab1_host[..., 0])) * per_ktile
+        vis3 = float(np.sum(self.segs_host[:, 1] - self.segs_host[:, 0])) * per_ktile
+        per_mac = 8.0 if self.cplx else 2.0
+
+        def count(q):
+            vals, cnt = np.unique(q, return_counts=True)
+            return dict(zip(vals.tolist(), cnt.tolist()))
+        nl, nr, nlp, nrp = count(self.ql), count(self.qr), count(self.qlp), count(self.qrp)
+        ex1 = 0.0
+        for qi, ni in nl.items():                       # t1[i,s,K,j'] = sum_j a[i,s,j] r[j,K,j']
+            for s in range(d):
+                nj = nr.get(qi + int(self.qs_in[s]), 0)
+                if nj:
+                    for K in range(cr):
+                        ex1 += ni * nj * nrp.get(qi + int(self.qs_in[s]) + int(self.qwr[K]), 0)
+        ex3 = 0.0
+        for qip, nip in nlp.items():                    # out[i',s',j'] = sum_{i,k} l[i,k,i'] t2[i,k,s',j']
+            for k in range(cl):
+                ni = nl.get(qip - int(self.qwl[k]), 0)
+                if ni:
+                    for sp in range(dout):
+                        ex3 += nip * ni * nrp.get(qip + int(self.qs_out[sp]), 0)
+        out = {"visited": vis1 + vis3, "exact": per_mac * (ex1 + ex3)}
+        if nnz_w is not None:
+            out["w_step"] = (4.0 if self.cplx else 2.0) * nnz_w * Dl * Drp
+        return out
+
     def _upload(self, device):
         if self.tab1 is None or self.tab1.device != device:
             self.tab1 = torch.from_numpy(self.tab1_host).to(device)
             self.tab3 = [torch.from_numpy(t).to(device) if act else None
                          for t, act in zip(self.tab3_host, self.k_active)]
+            self.seg3 = (torch.from_numpy(self.seg_ptr_host).to(device), torch.from_numpy(self.segs_host).to(device),
+                         torch.from_numpy(self.sel_off_host).to(device))
 
     @classmethod
     def for_site(cls, psi_qbond_l, qsite_in, psi_qbond_r, mpo_qbond_l, mpo_qbond_r, device=None, cplx=True):
@@ -199,7 +253,15 @@ class HeffSectorPlan:
         else:
             dev.gemm_strided(cplx, 0, 0, 0, cl * dout, Drp, d * cr, dev.as_dtype(w, cplx), d * cr, t1, Drp, t2, Drp,
                              Dl, 0, d * cr * Drp, cl * dout * Drp)
-        # (3) one banded launch per left MPO index, batched over s', accumulating into out
+        # (3) one segmented launch, batched over s': every tile sums its (k-range, left MPO index) segments
+        if _SEGMENTED:
+            seg_ptr, segs, sel_off = self.seg3
+            st = lib.ptb_gemm_segmented(dt, 0, Dlp, Drp, Dl, l.data_ptr(), cl * Dlp, t2.data_ptr(), cl * dout * Drp,
+                                        out.data_ptr(), dout * Drp, dout, 0, Drp, Drp, 0, seg_ptr.data_ptr(),
+                                        segs.data_ptr(), sel_off.data_ptr(), stream)
+            _lib.check(st, "ptb_gemm_segmented(step 3)")
+            return out
+        # alternative (PYTENET_B200_SEGMENTED=0): one banded launch per left MPO index, accumulating into out
         first = True
         for k in range(cl):
             if not self.k_active[k]:

@@ -141,3 +141,60 @@ def test_gemm_split_k(cuda_lib, cplx):
         assert st == 0, lib.ptb_status_string(st)
         want = (A.transpose(0, 2, 1) if ta else A) @ B + (C0 if acc else 0)
         assert rel(dC.cpu().numpy(), want) < TOL, (M, N, K, batch, split, acc, ta)
+
+
+@pytest.mark.parametrize("cplx,conj", [(True, False), (True, True), (False, False)])
+def test_gemm_segmented(cuda_lib, cplx, conj):
+    """ptb_gemm_segmented: every output tile sums its own list of (k-tile range, selector) segments, the selector
+    adding element offsets to the A / B base pointers; tiles without segments are zero.  Checked tile by tile
+    against NumPy on ragged extents with two batches."""
+    import ctypes
+    lib = cuda_lib
+    rng = np.random.default_rng(42 + int(cplx) + 2 * int(conj))
+    bm, bn, bk = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.ptb_gemm_tile_shape(1 if cplx else 0, ctypes.byref(bm), ctypes.byref(bn), ctypes.byref(bk)) == 0
+    bm, bn, bk = bm.value, bn.value, bk.value
+    M, N, K, batch, nsel = 2 * bm + 38, 3 * bn + 10, 5 * bk + 6, 2, 3
+    KT = -(-K // bk)
+    tm, tn = -(-M // bm), -(-N // bn)
+
+    def rnd(*shape):
+        x = rng.normal(size=shape)
+        return x + 1j * rng.normal(size=shape) if cplx else x
+
+    A = rnd(batch, nsel, K, M)                 # selector s of batch b: element offset s*K*M, batch stride nsel*K*M
+    B = rnd(batch, nsel, K, N)
+    want = np.zeros((batch, M, N), dtype=A.dtype)
+    seg_ptr, segs = [0], []
+    for b in range(batch):
+        for i in range(tm):
+            for j in range(tn):
+                nseg = int(rng.integers(0, 4))
+                for _ in range(nseg):
+                    lo = int(rng.integers(0, KT)); hi = int(rng.integers(lo, KT + 1)); sel = int(rng.integers(0, nsel))
+                    segs.append([lo, hi, sel, 0])
+                    rows = slice(i * bm, min((i + 1) * bm, M)); cols = slice(j * bn, min((j + 1) * bn, N))
+                    ks = slice(lo * bk, min(hi * bk, K))
+                    bb = B[b, sel, ks, cols]
+                    want[b, rows, cols] += A[b, sel, ks, rows].T @ (bb.conj() if conj else bb)
+                seg_ptr.append(len(segs))
+    if not segs:
+        segs.append([0, 0, 0, 0])
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    dC = torch.full((batch, M, N), 7.0, dtype=dA.dtype, device="cuda")
+    dptr = torch.tensor(seg_ptr, dtype=torch.int32, device="cuda")
+    dseg = torch.tensor(segs, dtype=torch.int32, device="cuda")
+    doff = torch.tensor([[s * K * M, s * K * N] for s in range(nsel)], dtype=torch.int64, device="cuda")
+    st = lib.ptb_gemm_segmented(1 if cplx else 0, int(conj), M, N, K, dA.data_ptr(), M, dB.data_ptr(), N, dC.data_ptr(),
+                                N, batch, nsel * K * M, nsel * K * N, M * N, 0, dptr.data_ptr(), dseg.data_ptr(),
+                                doff.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert st == 0
+    got = dC.cpu().numpy()
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < TOL
+    assert np.array_equal(got == 0, want == 0)              # tiles without segments are exactly zero
+    # accumulate on top of an existing C
+    st = lib.ptb_gemm_segmented(1 if cplx else 0, int(conj), M, N, K, dA.data_ptr(), M, dB.data_ptr(), N, dC.data_ptr(),
+                                N, batch, nsel * K * M, nsel * K * N, M * N, 1, dptr.data_ptr(), dseg.data_ptr(),
+                                doff.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert st == 0
+    assert np.linalg.norm(dC.cpu().numpy() - 2 * want) / np.linalg.norm(want) < TOL

@@ -191,13 +191,17 @@ def test_dmrg_against_exact_diagonalisation(cuda_lib):
     assert max(psi.bond_dims) > 6          # bonds must have grown
 
 
-def test_sector_banded_matvec_matches_dense(cuda_lib):
+@pytest.mark.parametrize("segmented", [True, False])
+def test_sector_banded_matvec_matches_dense(cuda_lib, monkeypatch, segmented):
     """Block-sparse path: HeffSectorPlan.apply == dense device matvec == oracle on block-sparse inputs
-    (sorted and unsorted bonds), and it actually skips work for sorted sectors."""
+    (sorted and unsorted bonds), and it actually skips work for sorted sectors.  Step 3 both as one segmented
+    launch (default) and as one accumulating banded launch per left MPO index."""
     import oracle
     import oracle.blocksparse as ob
     import pytenet_b200 as ptb
+    from pytenet_b200 import sectors
     from pytenet_b200.sectors import HeffSectorPlan
+    monkeypatch.setattr(sectors, "_SEGMENTED", segmented)
     rng = np.random.default_rng(77)
     for (Dl, d, Dr, cl, cr, sort) in [(300, 2, 260, 5, 5, True), (150, 4, 330, 6, 6, True), (200, 3, 129, 4, 5, False)]:
         qs = rng.integers(-1, 2, size=d)
