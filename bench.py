@@ -15,6 +15,8 @@ Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of 
 reference (oracle/, NumPy + OpenBLAS on all host cores) on a bounded sample.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -499,10 +501,26 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # exactly ONE line on stdout (the JSON): libraries that write to fd 1 on their own (NCCL prints its version
+    # banner there) are diverted to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    lines = [ln for ln in out.getvalue().splitlines() if ln.startswith("{")]
+    for ln in out.getvalue().splitlines():
+        if not ln.startswith("{"):
+            print(ln, file=sys.stderr)
+    if lines:
+        print(lines[-1], flush=True)
 
 
 if __name__ == "__main__":
