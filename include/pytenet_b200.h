@@ -77,7 +77,9 @@ int ptb_gemm_splitk(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, 
  * (device array of int32 pairs, tile shape from ptb_gemm_tile_shape).  The caller derives the ranges
  * from the quantum numbers of the operand indices: contributions outside them are exact zeros
  * (pytenet/block_sparse_util.py:47-53), so the result equals the dense product.  An empty range
- * leaves the tile zero (or untouched when accumulating).  TMA engine only. */
+ * leaves the tile zero (or untouched when accumulating).  accumulate == 2: overwrite like 0, but leave
+ * tiles with an empty range untouched (the caller keeps the structurally empty part of C zeroed once
+ * instead of having the zeros rewritten by every call).  TMA engine only. */
 int ptb_gemm_banded(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k,
                     const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc,
                     int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c, int accumulate,
@@ -167,6 +169,13 @@ int ptb_apply_local_hamiltonian_host(int dtype, int w_is_complex, const void* a,
  * t_dtype.  One pass over t_in and t_out: algorithmic bytes = elem_size (r_in + r_out) n_cols batch. */
 int ptb_wapply_csr(int t_dtype, int w_is_complex, int64_t r_out, int64_t r_in, int64_t n_cols, const int32_t* rowptr,
                    const int32_t* col, const void* val, const void* t_in, void* t_out, int64_t batch, void* stream);
+
+/* Same with row-activity flags (sector path): for every (batch block b / batch_block, 128-column block n / 128),
+ * in that order, r_in + r_out bytes: flag[c] == 0 marks input row c as structurally zero (not read), flag[r_in + m]
+ * == 0 marks output row m as structurally zero (not written: it keeps the zeros the caller initialised once). */
+int ptb_wapply_csr_masked(int t_dtype, int w_is_complex, int64_t r_out, int64_t r_in, int64_t n_cols,
+                          const int32_t* rowptr, const int32_t* col, const void* val, const void* t_in, void* t_out,
+                          int64_t batch, const uint8_t* active, int64_t batch_block, void* stream);
 
 /* ---------------------------------------------------------------------------
  * apply_local_bond_contraction(c, l, r)          pytenet/chain_ops.py:282-317

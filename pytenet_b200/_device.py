@@ -123,9 +123,13 @@ def side_stream(device):
     return st
 
 
+ws_owner = {}       # (device index, stream) -> token of the sector plan whose structural zeros are in the workspace
+
+
 def release_workspaces():
     _workspaces.clear()
     _scratch.clear()
+    ws_owner.clear()
 
 
 _GEMM_SCRATCH_BYTES = 32 << 20

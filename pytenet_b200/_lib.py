@@ -43,6 +43,7 @@ SIGNATURES = {
     "ptb_apply_local_hamiltonian_host_workspace_bytes": (_sz, [_int, _int] + _DIMS8),
     "ptb_apply_local_hamiltonian_host": (_int, [_int, _int, _ptr, _ptr, _ptr, _ptr, _ptr] + _DIMS8 + [_ptr, _sz, _ptr]),
     "ptb_wapply_csr": (_int, [_int, _int, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ptb_wapply_csr_masked": (_int, [_int, _int, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr]),
     "ptb_apply_local_bond_contraction_workspace_bytes": (_sz, [_int] + [_i64] * 5),
     "ptb_apply_local_bond_contraction_z": (_int, [_ptr] * 4 + [_i64] * 5 + [_ptr, _sz, _ptr]),
     "ptb_apply_local_bond_contraction_d": (_int, [_ptr] * 4 + [_i64] * 5 + [_ptr, _sz, _ptr]),

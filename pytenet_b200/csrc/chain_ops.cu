@@ -51,7 +51,7 @@ int gemm(int ta, int tb, int cj, int64_t M, int64_t N, int64_t K, const void* A,
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.sA = sA; p.sB = sB; p.sC = sC;
     p.batch = (int)batch;
-    p.accumulate = acc;
+    p.accumulate = acc ? 1 : 0;
     p.tiles_m = p.tiles_n = 0;
     if (M == 0 || N == 0 || batch == 0) return PTB_OK;
     // engine selection: 0 = auto (warp-specialised TMA kernel when it applies), 1 = first-generation
@@ -284,6 +284,7 @@ int ptb_gemm_banded(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, 
                     int64_t stride_b, int64_t stride_c, int accumulate, const int32_t* ktab, void* stream) {
     if (!a || !b || !c || !ktab) return PTB_ERR_BAD_ARG;
     if (m <= 0 || n <= 0 || k <= 0 || batch <= 0 || !fits_int({m, n, k, batch})) return PTB_ERR_BAD_ARG;
+    if (accumulate < 0 || accumulate > 2) return PTB_ERR_BAD_ARG;
     GemmParams p;
     p.A = static_cast<const double*>(a);
     p.B = static_cast<const double*>(b);
@@ -319,7 +320,7 @@ int ptb_gemm_segmented(int dtype, int conj_b, int64_t m, int64_t n, int64_t k, c
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.sA = stride_a; p.sB = stride_b; p.sC = stride_c;
     p.batch = (int)batch;
-    p.accumulate = accumulate;
+    p.accumulate = accumulate ? 1 : 0;
     p.tiles_m = p.tiles_n = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static_assert(sizeof(long long) == sizeof(int64_t), "offset table is int64");

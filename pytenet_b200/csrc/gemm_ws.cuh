@@ -342,6 +342,10 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
             kt_end = min(kr.y, KT_all);
         }
 
+        // banded GEMM with accumulate == 2: tiles with an empty k range are left untouched (the caller keeps the
+        // structurally empty part of C zeroed once, instead of rewriting the zeros on every call)
+        if (!SEG && p.ktab != nullptr && p.accumulate == 2 && kt_end <= kt_begin) continue;
+
         double acc[MT][NT][2 * E];
 #pragma unroll
         for (int i = 0; i < MT; i++)
@@ -431,7 +435,7 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
         }
         const bool partial = un.dest == 1;
         const int64_t ldc_eff = partial ? (int64_t)p.N : p.ldc;
-        const bool accum = !partial && p.accumulate;
+        const bool accum = !partial && p.accumulate == 1;
         for (int dsti = 0; dsti <= p.n_extra; dsti++) {
             double* __restrict__ Cg =
                 partial ? p.Cpart + ((int64_t)bz * p.split_k + un.sk) * (int64_t)p.M * p.N * E

@@ -30,7 +30,10 @@ from . import _device as dev
 __all__ = ["HeffSectorPlan", "EnvSectorPlan", "BondSectorPlan", "tile_k_ranges"]
 
 import os
+import itertools
 _SEGMENTED = os.environ.get("PYTENET_B200_SEGMENTED", "1") != "0"
+_SKIP_EMPTY = os.environ.get("PYTENET_B200_SKIP_EMPTY", "1") != "0"
+_PLAN_IDS = itertools.count(1)
 
 _EMPTY_LO = np.iinfo(np.int64).max
 _EMPTY_HI = -1
@@ -147,6 +150,22 @@ class HeffSectorPlan:
         self.segs_host = segs
         self.sel_off_host = np.stack([np.arange(cl) * Dlp, np.arange(cl) * dout * Drp], axis=1).astype(np.int64)
         self.seg3 = None
+        # row-activity flags of the W step: for every (BM-row block of i) x (128-column block of j') which input rows
+        # (s, K) of t1 can hold entries, i.e. overlap a t1 tile that step 1 writes.  Inactive parts of t1 / t2 are
+        # never written -- they keep the zeros of the one-time initialisation of the workspace (see apply) and are
+        # neither read nor written by the W kernel, so the dense-layout intermediates cost traffic only where the
+        # quantum numbers allow entries.  (The output-row flags follow from these and W's pattern: _w_flags.)
+        nonempty1 = self.tab1_host[..., 1] > self.tab1_host[..., 0]                        # (d, tiles_m, tiles_n1)
+        ncb = -(-Drp // 128)
+        act = np.zeros((nonempty1.shape[1], ncb, d, cr), dtype=bool)
+        for K in range(cr):
+            for jb in range(ncb):
+                c0 = K * Drp + jb * 128
+                c1 = K * Drp + min((jb + 1) * 128, Drp)
+                act[:, jb, :, K] = np.any(nonempty1[:, :, c0 // bn:(c1 - 1) // bn + 1], axis=2).T
+        self.in_active_host = act.reshape(nonempty1.shape[1], ncb, d * cr)
+        self._flag_cache = {}
+        self._uid = next(_PLAN_IDS)
 
         # bookkeeping for benchmarks: fraction of the dense k-tile visits that remain
         kt1 = -(-Dr // bk)
@@ -192,6 +211,28 @@ class HeffSectorPlan:
             out["w_step"] = (4.0 if self.cplx else 2.0) * nnz_w * Dl * Drp
         return out
 
+    def _w_flags(self, csr, key, device):
+        """Device array of W-step row flags for the MPO tensor whose CSR form is `csr` (cached per tensor):
+        input flags from the plan, output row m active iff some non-zero W[m, c] meets an active input row c."""
+        hit = self._flag_cache.get(key)
+        if hit is not None:
+            return hit
+        rowptr = csr[0].cpu().numpy().astype(np.int64)
+        nnz = int(rowptr[-1])
+        col = csr[1].cpu().numpy().astype(np.int64)[:nnz]
+        r_out = len(rowptr) - 1
+        ina = self.in_active_host                                                 # (nib, ncb, r_in)
+        rows = np.repeat(np.arange(r_out), np.diff(rowptr))
+        outa = np.zeros(ina.shape[:2] + (r_out,), dtype=bool)
+        if nnz:
+            np.logical_or.at(outa, (slice(None), slice(None), rows), ina[:, :, col])
+        flags = np.ascontiguousarray(np.concatenate([ina, outa], axis=2).astype(np.uint8))
+        dev_flags = torch.from_numpy(flags).to(device)
+        if len(self._flag_cache) > 8:
+            self._flag_cache.clear()
+        self._flag_cache[key] = dev_flags
+        return dev_flags
+
     def _upload(self, device):
         if self.tab1 is None or self.tab1.device != device:
             self.tab1 = torch.from_numpy(self.tab1_host).to(device)
@@ -199,6 +240,7 @@ class HeffSectorPlan:
                          for t, act in zip(self.tab3_host, self.k_active)]
             self.seg3 = (torch.from_numpy(self.seg_ptr_host).to(device), torch.from_numpy(self.segs_host).to(device),
                          torch.from_numpy(self.sel_off_host).to(device))
+            self._flag_cache = {}
 
     @classmethod
     def for_site(cls, psi_qbond_l, qsite_in, psi_qbond_r, mpo_qbond_l, mpo_qbond_r, device=None, cplx=True):
@@ -229,20 +271,41 @@ class HeffSectorPlan:
         stream = dev.stream_ptr(device)
         n1 = Dl * d * cr * Drp
         n2 = Dl * cl * dout * Drp
-        ws = dev.workspace((n1 + n2) * es + 32, device, tag="sectors")
+        nbytes = (n1 + n2) * es + 32
+        ws = dev.workspace(nbytes, device, tag="sectors")
         t1 = ws[:n1 * es].view(a.dtype).reshape(Dl, d, cr * Drp)
         off2 = (n1 * es + 15) // 16 * 16
         t2 = ws[off2:off2 + n2 * es].view(a.dtype).reshape(Dl, cl * dout, Drp)
         if out is None:
             out = torch.empty((Dlp, dout, Drp), dtype=a.dtype, device=device)
+        csr = dev.w_csr(w) if (cplx or not w.dtype.is_complex) else None
+        # Structural zeros are written ONCE per plan: the workspace is zeroed when this plan takes it over; after that
+        # step 1 stores only tiles with a non-empty k range and the W kernel touches only active blocks, so every
+        # other entry of t1 / t2 keeps its zero across the matvecs of a Lanczos run (k = 25 per plan in a sweep).
+        lean = _SKIP_EMPTY and csr is not None
+        if lean:
+            key = (device.index, stream)
+            owner = (self._uid, ws.data_ptr(), nbytes, w.data_ptr(), w._version)
+            if dev.ws_owner.get(key) != owner:
+                ws[:nbytes].zero_()
+                dev.ws_owner[key] = owner
+        else:
+            dev.ws_owner.pop((device.index, stream), None)
         # (1) batched over s, banded in j
         st = lib.ptb_gemm_banded(dt, 0, 0, 0, Dl, cr * Drp, Dr, a.data_ptr(), d * Dr, r.data_ptr(), cr * Drp,
-                                 t1.data_ptr(), d * cr * Drp, d, Dr, 0, cr * Drp, 0, self.tab1.data_ptr(), stream)
+                                 t1.data_ptr(), d * cr * Drp, d, Dr, 0, cr * Drp, 2 if lean else 0,
+                                 self.tab1.data_ptr(), stream)
         _lib.check(st, "ptb_gemm_banded(step 1)")
         # (2) W step batched over i (t1[i] is (d*cr) x Drp, t2[i] is (cl*dout) x Drp): sparse CSR kernel for
         #     the usual sparse MPO tensors, dense small GEMM otherwise
-        csr = dev.w_csr(w) if (cplx or not w.dtype.is_complex) else None
-        if csr is not None:
+        if lean:
+            rowptr, col, val, _ = csr
+            flags = self._w_flags(csr, (w.data_ptr(), w._version), device)
+            st = lib.ptb_wapply_csr_masked(dt, int(w.dtype.is_complex), cl * dout, d * cr, Drp, rowptr.data_ptr(),
+                                           col.data_ptr(), val.data_ptr(), t1.data_ptr(), t2.data_ptr(), Dl,
+                                           flags.data_ptr(), self.tile[0], stream)
+            _lib.check(st, "ptb_wapply_csr_masked")
+        elif csr is not None:
             rowptr, col, val, _ = csr
             st = lib.ptb_wapply_csr(dt, int(w.dtype.is_complex), cl * dout, d * cr, Drp, rowptr.data_ptr(),
                                     col.data_ptr(), val.data_ptr(), t1.data_ptr(), t2.data_ptr(), Dl, stream)

@@ -224,6 +224,42 @@ def test_sector_banded_matvec_matches_dense(cuda_lib, monkeypatch, segmented):
         assert np.all(got[mask] == 0)
 
 
+def test_sector_plan_reuse_keeps_structural_zeros(cuda_lib):
+    """The lean sector path writes the structural zeros of t1 / t2 once per plan and afterwards only touches what
+    the quantum numbers allow: repeated applications with new vectors, another plan in between (same workspace)
+    and a different MPO tensor on the same plan must all still equal the dense device matvec."""
+    import oracle.blocksparse as ob
+    import pytenet_b200 as ptb
+    from pytenet_b200.sectors import HeffSectorPlan
+    rng = np.random.default_rng(5)
+    cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+    def make(Dl, d, Dr, cl, cr, nsec):
+        qs = rng.integers(-1, 2, size=d)
+        ql = np.sort(rng.integers(-nsec, nsec + 1, size=Dl)); qr = np.sort(rng.integers(-nsec, nsec + 1, size=Dr))
+        qwl = rng.integers(-1, 2, size=cl); qwr = rng.integers(-1, 2, size=cr)
+        def tensor(shape, qn):
+            t = rng.normal(size=shape) + 1j * rng.normal(size=shape); ob.enforce_qsparsity(t, qn); return t
+        vecs = [tensor((Dl, d, Dr), [ql, qs, -qr]) for _ in range(3)]
+        l = tensor((Dl, cl, Dl), [ql, qwl, -ql]); r = tensor((Dr, cr, Dr), [qr, qwr, -qr])
+        ws = []
+        for dens in (0.5, 0.15):
+            w = rng.normal(size=(cl, d, d, cr)); w[rng.random(w.shape) > dens] = 0
+            ob.enforce_qsparsity(w, [qwl, qs, -qs, -qwr]); ws.append(w)
+        return HeffSectorPlan(ql, qs, qr, qwl, qwr, cplx=True), vecs, ws, l, r
+
+    p1, v1, w1, l1, r1 = make(700, 3, 650, 5, 4, 6)
+    p2, v2, w2, l2, r2 = make(520, 2, 900, 4, 6, 5)
+    seq = [(p1, v1[0], w1[0], l1, r1), (p1, v1[1], w1[0], l1, r1), (p2, v2[0], w2[0], l2, r2),
+           (p1, v1[2], w1[0], l1, r1), (p1, v1[0], w1[1], l1, r1), (p2, v2[1], w2[1], l2, r2),
+           (p2, v2[2], w2[1], l2, r2)]
+    for plan, a, w, l, r in seq:
+        wd = cu(w)
+        got = plan.apply(cu(a), wd, cu(l), cu(r))
+        want = ptb.apply_local_hamiltonian(cu(a), wd, cu(l), cu(r))
+        assert (torch.linalg.norm(got - want) / torch.linalg.norm(want)).item() < 1e-13
+
+
 def test_sweeps_with_forced_sector_plans(cuda_lib, golden_dir, monkeypatch):
     """The sweeps give the same energies / sector layouts when every local problem goes through the
     sector-banded matvec (forced; by default it is only used for bonds >= 256)."""
