@@ -85,6 +85,23 @@ int ptb_gemm_banded(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, 
                     int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c, int accumulate,
                     const int32_t* ktab, void* stream);
 int ptb_gemm_tile_shape(int dtype, int* bm, int* bn, int* bk);
+/* General form of the two sector GEMMs with an optional tile schedule.  Exactly one of `ktab` (banded mode, as
+ * ptb_gemm_banded; accumulate 0 / 1 / 2) and `seg_ptr` + `segs` + `sel_off` (segmented mode, as ptb_gemm_segmented;
+ * needs trans_a = 1, trans_b = 0) is given.  `order` (optional) is a permutation of the tile indices: work unit u of
+ * the persistent grid processes tile order[u].  The k ranges of the tiles differ widely, so the caller sorts the
+ * tiles by decreasing work, which balances the round-robin assignment of units to the 148 CTAs.  All tables are
+ * device arrays. */
+typedef struct {
+    const int32_t* ktab;
+    const int32_t* seg_ptr;
+    const int32_t* segs;
+    const int64_t* sel_off;
+    const int32_t* order;
+} ptb_sector_tables;
+int ptb_gemm_sector(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k, const void* a,
+                    int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t batch, int64_t stride_a,
+                    int64_t stride_b, int64_t stride_c, int accumulate, const ptb_sector_tables* tables, void* stream);
+
 /* Segmented GEMM (sums over an outer index inside ONE launch):  C[b] (+)= sum_seg A_seg^T B_seg  with both
  * operands stored K-major (A is K x M, B is K x N, row-major: trans_a = 1, trans_b = 0 in ptb_gemm terms).
  * Output tile t (same numbering as ptb_gemm_banded) accumulates the segments

@@ -71,6 +71,16 @@ SIGNATURES = {
     "ptb_probe_fp64_pipe": (_int, [_int, _int, _int, _ptr, ctypes.POINTER(ctypes.c_double), _ptr]),
 }
 
+
+
+class SectorTables(ctypes.Structure):
+    """ptb_sector_tables of include/pytenet_b200.h (device pointers; None = NULL)."""
+    _fields_ = [("ktab", _ptr), ("seg_ptr", _ptr), ("segs", _ptr), ("sel_off", _ptr), ("order", _ptr)]
+
+
+SIGNATURES["ptb_gemm_sector"] = (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
+                                        _i64, _i64, _i64, _i64, _int, ctypes.POINTER(SectorTables), _ptr])
+
 _lib = None
 
 

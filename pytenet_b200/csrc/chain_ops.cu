@@ -330,6 +330,37 @@ int ptb_gemm_segmented(int dtype, int conj_b, int64_t m, int64_t n, int64_t k, c
     return PTB_ERR_BAD_DTYPE;
 }
 
+int ptb_gemm_sector(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k, const void* a,
+                    int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t batch, int64_t stride_a,
+                    int64_t stride_b, int64_t stride_c, int accumulate, const ptb_sector_tables* t, void* stream) {
+    if (!a || !b || !c || !t) return PTB_ERR_BAD_ARG;
+    if (m <= 0 || n <= 0 || k <= 0 || batch <= 0 || !fits_int({m, n, k, batch})) return PTB_ERR_BAD_ARG;
+    const bool seg = t->seg_ptr != nullptr;
+    if (seg ? (!t->segs || !t->sel_off || t->ktab || trans_a != 1 || trans_b != 0) : !t->ktab) return PTB_ERR_BAD_ARG;
+    if (accumulate < 0 || accumulate > 2 || (seg && accumulate == 2)) return PTB_ERR_BAD_ARG;
+    GemmParams p;
+    p.A = static_cast<const double*>(a);
+    p.B = static_cast<const double*>(b);
+    p.C = static_cast<double*>(c);
+    p.M = (int)m; p.N = (int)n; p.K = (int)k;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.sA = stride_a; p.sB = stride_b; p.sC = stride_c;
+    p.batch = (int)batch;
+    p.accumulate = accumulate;
+    p.tiles_m = p.tiles_n = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool cplx = dtype == PTB_COMPLEX128;
+    if (!cplx && dtype != PTB_REAL64) return PTB_ERR_BAD_DTYPE;
+    if (seg) {
+        const long long* off = reinterpret_cast<const long long*>(t->sel_off);
+        return cplx ? launch_ws_segmented<true>(conj_b, p, st, t->seg_ptr, t->segs, off, t->order)
+                    : launch_ws_segmented<false>(0, p, st, t->seg_ptr, t->segs, off, t->order);
+    }
+    const int rc = cplx ? try_launch_ws<true>(trans_a, trans_b, conj_b, p, st, 0, nullptr, 1, nullptr, 0, t->ktab, t->order)
+                        : try_launch_ws<false>(trans_a, trans_b, 0, p, st, 0, nullptr, 1, nullptr, 0, t->ktab, t->order);
+    return rc == 1 ? PTB_ERR_ALIGNMENT : rc;
+}
+
 int ptb_gemm_tile_shape(int dtype, int* bm, int* bn, int* bk) {
     if (!bm || !bn || !bk) return PTB_ERR_BAD_ARG;
     if (dtype == PTB_COMPLEX128) { *bm = WsCfg<true>::BM; *bn = WsCfg<true>::BN; *bk = WsCfg<true>::BK; return PTB_OK; }

@@ -88,6 +88,10 @@ struct WsParams {
     const int* seg_ptr;
     const int4* segs;
     const long long* sel_off;
+    // optional permutation of the tile indices (sector path): work unit u processes tile order[u].  The host sorts
+    // the tiles by decreasing work so that the round-robin assignment of units to the persistent CTAs is balanced
+    // although the per-tile k ranges differ widely.
+    const int* order;
 };
 
 // ---- mbarrier / TMA primitives ---------------------------------------------------------
@@ -195,7 +199,7 @@ __device__ __forceinline__ WsUnit ws_decode_unit(const WsParams& p, long long u)
         w.dest = 2;
         w.slot = v;
     } else {
-        w.tile = u;
+        w.tile = p.order != nullptr ? (long long)p.order[u] : u;
         w.sk = 0;
         w.nsplit = 1;
         w.dest = 0;
@@ -630,7 +634,7 @@ static int choose_split_k(long long tiles, int KT, int K, int num_sms = 148) {
 template <bool CPLX>
 static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp, cudaStream_t stream,
                          int n_extra = 0, double* const* extra = nullptr, int split_k = 1, void* part_ws = nullptr,
-                         size_t part_ws_bytes = 0, const int32_t* ktab = nullptr) {
+                         size_t part_ws_bytes = 0, const int32_t* ktab = nullptr, const int32_t* order = nullptr) {
     using Cfg = WsCfg<CPLX>;
     constexpr int E = Cfg::E;
     const bool a_kc = (transA == 0), b_kc = (transB != 0);
@@ -663,6 +667,7 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     p.tail_begin = 0;
     p.ktab = reinterpret_cast<const int2*>(ktab);
     p.seg_ptr = nullptr; p.segs = nullptr; p.sel_off = nullptr;
+    p.order = order;
     if (ktab != nullptr && (reinterpret_cast<uintptr_t>(ktab) % 8) != 0) return PTB_ERR_ALIGNMENT;
     if (split_k != 1 && n_extra == 0 && part_ws != nullptr && ktab == nullptr) {
         const int KT = (gp.K + Cfg::BK - 1) / Cfg::BK;
@@ -725,7 +730,7 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
 // Segmented GEMM on mn-contiguous operands (A stored K x M, B stored K x N): see WsParams::seg_ptr.
 template <bool CPLX>
 static int launch_ws_segmented(int conjB, const GemmParams& gp, cudaStream_t stream, const int* seg_ptr,
-                               const int* segs, const long long* sel_off) {
+                               const int* segs, const long long* sel_off, const int* order = nullptr) {
     using Cfg = WsCfg<CPLX>;
     auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
     if (!al16(gp.A) || !al16(gp.B) || !al16(gp.C) || !al16(segs)) return PTB_ERR_ALIGNMENT;
@@ -749,6 +754,7 @@ static int launch_ws_segmented(int conjB, const GemmParams& gp, cudaStream_t str
     p.seg_ptr = seg_ptr;
     p.segs = reinterpret_cast<const int4*>(segs);
     p.sel_off = sel_off;
+    p.order = order;
     CUtensorMap ta, tb;
     memset(&ta, 0, sizeof(ta));
     memset(&tb, 0, sizeof(tb));

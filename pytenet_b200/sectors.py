@@ -33,6 +33,10 @@ import os
 import itertools
 _SEGMENTED = os.environ.get("PYTENET_B200_SEGMENTED", "1") != "0"
 _SKIP_EMPTY = os.environ.get("PYTENET_B200_SKIP_EMPTY", "1") != "0"
+# tile schedules sorted by work: measured at the config-3 shape, step 1 gains 13 % (physical sector profile), the
+# segmented step 3 does not (its tiles are more uniform and the sorted order costs L2 locality) -- off by default there
+_ORDERED = os.environ.get("PYTENET_B200_TILE_ORDER", "1") != "0"
+_ORDERED_STEP3 = os.environ.get("PYTENET_B200_TILE_ORDER_STEP3", "0") != "0"
 _PLAN_IDS = itertools.count(1)
 
 _EMPTY_LO = np.iinfo(np.int64).max
@@ -150,6 +154,15 @@ class HeffSectorPlan:
         self.segs_host = segs
         self.sel_off_host = np.stack([np.arange(cl) * Dlp, np.arange(cl) * dout * Drp], axis=1).astype(np.int64)
         self.seg3 = None
+        # tile schedules: tiles sorted by decreasing number of k-tiles (stable), so that the round-robin assignment
+        # of work units to the persistent CTAs is balanced although the per-tile work differs widely
+        work1 = (self.tab1_host[..., 1] - self.tab1_host[..., 0]).reshape(-1)
+        self.order1_host = np.argsort(-np.maximum(work1, 0), kind="stable").astype(np.int32)
+        seg_len = np.zeros(len(self.seg_ptr_host) - 1, dtype=np.int64)
+        if len(k_idx):
+            np.add.at(seg_len, tile_idx, (lohi[:, 1] - lohi[:, 0]).astype(np.int64))
+        self.order3_host = np.argsort(-seg_len, kind="stable").astype(np.int32)
+        self.order = None
         # row-activity flags of the W step: for every (BM-row block of i) x (128-column block of j') which input rows
         # (s, K) of t1 can hold entries, i.e. overlap a t1 tile that step 1 writes.  Inactive parts of t1 / t2 are
         # never written -- they keep the zeros of the one-time initialisation of the workspace (see apply) and are
@@ -241,6 +254,7 @@ class HeffSectorPlan:
             self.seg3 = (torch.from_numpy(self.seg_ptr_host).to(device), torch.from_numpy(self.segs_host).to(device),
                          torch.from_numpy(self.sel_off_host).to(device))
             self._flag_cache = {}
+            self.order = (torch.from_numpy(self.order1_host).to(device), torch.from_numpy(self.order3_host).to(device))
 
     @classmethod
     def for_site(cls, psi_qbond_l, qsite_in, psi_qbond_r, mpo_qbond_l, mpo_qbond_r, device=None, cplx=True):
@@ -292,10 +306,11 @@ class HeffSectorPlan:
         else:
             dev.ws_owner.pop((device.index, stream), None)
         # (1) batched over s, banded in j
-        st = lib.ptb_gemm_banded(dt, 0, 0, 0, Dl, cr * Drp, Dr, a.data_ptr(), d * Dr, r.data_ptr(), cr * Drp,
+        tabs = _lib.SectorTables(self.tab1.data_ptr(), None, None, None, self.order[0].data_ptr() if _ORDERED else None)
+        st = lib.ptb_gemm_sector(dt, 0, 0, 0, Dl, cr * Drp, Dr, a.data_ptr(), d * Dr, r.data_ptr(), cr * Drp,
                                  t1.data_ptr(), d * cr * Drp, d, Dr, 0, cr * Drp, 2 if lean else 0,
-                                 self.tab1.data_ptr(), stream)
-        _lib.check(st, "ptb_gemm_banded(step 1)")
+                                 ctypes.byref(tabs), stream)
+        _lib.check(st, "ptb_gemm_sector(step 1)")
         # (2) W step batched over i (t1[i] is (d*cr) x Drp, t2[i] is (cl*dout) x Drp): sparse CSR kernel for
         #     the usual sparse MPO tensors, dense small GEMM otherwise
         if lean:
@@ -319,10 +334,11 @@ class HeffSectorPlan:
         # (3) one segmented launch, batched over s': every tile sums its (k-range, left MPO index) segments
         if _SEGMENTED:
             seg_ptr, segs, sel_off = self.seg3
-            st = lib.ptb_gemm_segmented(dt, 0, Dlp, Drp, Dl, l.data_ptr(), cl * Dlp, t2.data_ptr(), cl * dout * Drp,
-                                        out.data_ptr(), dout * Drp, dout, 0, Drp, Drp, 0, seg_ptr.data_ptr(),
-                                        segs.data_ptr(), sel_off.data_ptr(), stream)
-            _lib.check(st, "ptb_gemm_segmented(step 3)")
+            tabs = _lib.SectorTables(None, seg_ptr.data_ptr(), segs.data_ptr(), sel_off.data_ptr(),
+                                     self.order[1].data_ptr() if _ORDERED_STEP3 else None)
+            st = lib.ptb_gemm_sector(dt, 1, 0, 0, Dlp, Drp, Dl, l.data_ptr(), cl * Dlp, t2.data_ptr(), cl * dout * Drp,
+                                     out.data_ptr(), dout * Drp, dout, 0, Drp, Drp, 0, ctypes.byref(tabs), stream)
+            _lib.check(st, "ptb_gemm_sector(step 3)")
             return out
         # alternative (PYTENET_B200_SEGMENTED=0): one banded launch per left MPO index, accumulating into out
         first = True
