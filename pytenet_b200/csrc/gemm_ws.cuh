@@ -214,6 +214,11 @@ __device__ __forceinline__ void ws_tile_coords(const WsParams& p, long long t, i
     const int tiles_per_batch = p.tiles_m * p.tiles_n;
     bz = (int)(t / tiles_per_batch);
     const int tile = (int)(t - (long long)bz * tiles_per_batch);
+    if (p.order != nullptr) {      // scheduled tiles are given in table order (batch, tile row, tile column)
+        tm = tile / p.tiles_n;
+        tn = tile - tm * p.tiles_n;
+        return;
+    }
     const int per_group = GROUP * p.tiles_n;
     const int grp = tile / per_group;
     const int first_m = grp * GROUP;

@@ -33,10 +33,9 @@ import os
 import itertools
 _SEGMENTED = os.environ.get("PYTENET_B200_SEGMENTED", "1") != "0"
 _SKIP_EMPTY = os.environ.get("PYTENET_B200_SKIP_EMPTY", "1") != "0"
-# tile schedules sorted by work: measured at the config-3 shape, step 1 gains 13 % (physical sector profile), the
-# segmented step 3 does not (its tiles are more uniform and the sorted order costs L2 locality) -- off by default there
+# tile schedules sorted by decreasing work (PYTENET_B200_TILE_ORDER=0 disables them, for A/B measurements)
 _ORDERED = os.environ.get("PYTENET_B200_TILE_ORDER", "1") != "0"
-_ORDERED_STEP3 = os.environ.get("PYTENET_B200_TILE_ORDER_STEP3", "0") != "0"
+_ORDERED_STEP3 = _ORDERED
 _PLAN_IDS = itertools.count(1)
 
 _EMPTY_LO = np.iinfo(np.int64).max
