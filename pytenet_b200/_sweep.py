@@ -14,10 +14,11 @@ import torch
 
 from . import _device as dev
 from . import _lib
-from .sectors import HeffSectorPlan
+from .sectors import HeffSectorPlan, EnvSectorPlan, BondSectorPlan
 from .block_sparse_util import is_qsparse
 from .chain_ops import (apply_local_hamiltonian, apply_local_bond_contraction,
-                        compute_right_operator_blocks)
+                        compute_right_operator_blocks, contraction_operator_step_left,
+                        contraction_operator_step_right)
 from .krylov import eigh_krylov, expm_krylov
 
 
@@ -51,6 +52,42 @@ def sector_plan(ql, qs, qr, qwl, qwr, like):
     if not (np.any(ql) or np.any(qr) or np.any(qs) or np.any(qwl) or np.any(qwr)):
         return None
     return HeffSectorPlan(ql, qs, qr, qwl, qwr, cplx=True if like is None else like.dtype.is_complex)
+
+
+def _use_sectors(nbond, *qnums):
+    if _SECTOR_MODE == "0":
+        return False
+    if _SECTOR_MODE != "1" and nbond < _SECTOR_MIN_BOND:
+        return False
+    return any(np.any(q) for q in qnums)
+
+
+def env_step_left(psi, hamiltonian, i, l):
+    """lblocks[i+1] from lblocks[i] and site i (tdvp.py:79,179; dmrg.py:72,153), through the sector work lists
+    when the quantum numbers are non-trivial and the bonds large, else the dense contraction."""
+    a, w = psi.a[i], hamiltonian.a[i]
+    qn = (psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], hamiltonian.qbonds[i], hamiltonian.qbonds[i + 1])
+    if _use_sectors(max(a.shape[0], a.shape[2]), *qn) and isinstance(l, torch.Tensor) and l.shape[0] == a.shape[0]:
+        plan = EnvSectorPlan(*qn, cplx=dev.any_complex(a, l, w))
+        return plan.step_left(a, w, l)
+    return contraction_operator_step_left(a, a, w, l)
+
+
+def env_step_right(psi, hamiltonian, i, r):
+    """rblocks[i-1] from rblocks[i] and site i (tdvp.py:106,197,216; dmrg.py:83,168); see env_step_left."""
+    a, w = psi.a[i], hamiltonian.a[i]
+    qn = (psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], hamiltonian.qbonds[i], hamiltonian.qbonds[i + 1])
+    if _use_sectors(max(a.shape[0], a.shape[2]), *qn) and isinstance(r, torch.Tensor) and r.shape[0] == a.shape[2]:
+        plan = EnvSectorPlan(*qn, cplx=dev.any_complex(a, r, w))
+        return plan.step_right(a, w, r)
+    return contraction_operator_step_right(a, a, w, r)
+
+
+def bond_plan(qbl, qbr, qw, c, l, r):
+    """BondSectorPlan for the zero-site problem on a bond (rows of `c`: qbl, columns: qbr), or None."""
+    if not _use_sectors(max(c.shape), qbl, qbr, qw):
+        return None
+    return BondSectorPlan(qbl, qbr, qw, cplx=dev.any_complex(c, l, r))
 
 
 class HeffOperator:
@@ -145,9 +182,15 @@ def local_hamiltonian_step(l, r, w, a, dt, numiter: int, plan=None):
     return expm_krylov(_heff(w, l, r, shape, plan), a.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
 
 
-def local_bond_step(l, r, c, dt, numiter: int):
+def local_bond_step(l, r, c, dt, numiter: int, plan=None):
     """exp(-dt K_eff) c for the zero-site (bond) effective Hamiltonian (tdvp.py:232-238)."""
     shape = tuple(c.shape)
+    if plan is not None and plan.cplx == (c.dtype.is_complex or l.dtype.is_complex or r.dtype.is_complex):
+        def matvec(x):
+            if x.dtype.is_complex != plan.cplx:
+                return apply_local_bond_contraction(x.reshape(shape), l, r).reshape(-1)
+            return plan.apply(x.reshape(shape), l, r).reshape(-1)
+        return expm_krylov(matvec, c.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
     return expm_krylov(BondOperator(l, r, shape), c.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
 
 

@@ -12,8 +12,7 @@ from . import _device as dev
 from .mps import (MPS, mps_local_orthonormalize_left_qr, mps_local_orthonormalize_right_qr,
                   mps_merge_tensor_pair, mps_split_tensor_svd)
 from .mpo import MPO, mpo_merge_tensor_pair
-from .chain_ops import contraction_operator_step_right, contraction_operator_step_left
-from ._sweep import prepare_environments, minimize_local_energy, sector_plan
+from ._sweep import prepare_environments, minimize_local_energy, sector_plan, env_step_left, env_step_right
 from .block_sparse_util import qnumber_flatten
 
 __all__ = ["dmrg_singlesite", "dmrg_twosite"]
@@ -49,12 +48,12 @@ def dmrg_singlesite(hamiltonian: MPO, psi: MPS, numsweeps: int, numiter_lanczos:
             en, psi.a[i] = minimize_local_energy(ham[i], lblocks[i], rblocks[i], psi.a[i], k, site_plan(i))
             psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_local_orthonormalize_left_qr(
                 psi.a[i], psi.a[i + 1], psi.qsite, psi.qbonds[i:i + 2])
-            lblocks[i + 1] = contraction_operator_step_left(psi.a[i], psi.a[i], ham[i], lblocks[i])
+            lblocks[i + 1] = env_step_left(psi, hamiltonian, i, lblocks[i])
         for i in reversed(range(1, nsites)):                                 # dmrg.py:76-84
             en, psi.a[i] = minimize_local_energy(ham[i], lblocks[i], rblocks[i], psi.a[i], k, site_plan(i))
             psi.a[i], psi.a[i - 1], psi.qbonds[i] = mps_local_orthonormalize_right_qr(
                 psi.a[i], psi.a[i - 1], psi.qsite, psi.qbonds[i:i + 2])
-            rblocks[i - 1] = contraction_operator_step_right(psi.a[i], psi.a[i], ham[i], rblocks[i])
+            rblocks[i - 1] = env_step_right(psi, hamiltonian, i, rblocks[i])
         _renormalize_first_site(psi)
         en_min[n] = en                     # energy of the last local problem of the sweep (dmrg.py:91)
 
@@ -90,10 +89,10 @@ def dmrg_twosite(hamiltonian: MPO, psi: MPS, numsweeps: int, numiter_lanczos: in
         en = 0
         for i in range(nsites - 2):                                          # dmrg.py:142-154
             en = optimize_pair(i, "right")
-            lblocks[i + 1] = contraction_operator_step_left(psi.a[i], psi.a[i], ham[i], lblocks[i])
+            lblocks[i + 1] = env_step_left(psi, hamiltonian, i, lblocks[i])
         for i in reversed(range(nsites - 1)):                                # dmrg.py:157-169
             en = optimize_pair(i, "left")
-            rblocks[i] = contraction_operator_step_right(psi.a[i + 1], psi.a[i + 1], ham[i + 1], rblocks[i + 1])
+            rblocks[i] = env_step_right(psi, hamiltonian, i + 1, rblocks[i + 1])
         _renormalize_first_site(psi)
         en_min[n] = en
 

@@ -90,6 +90,32 @@ def tile_k_ranges(need_rows, need_cols, qk, bm, bn, bk):
     return np.stack([lo_t, hi_t], axis=-1).astype(np.int32)
 
 
+def segment_tables(tabs):
+    """Tables of a segmented GEMM from per-selector k-range tables: `tabs` is a list (one entry per selector) of
+    (batch, tiles_m, tiles_n, 2) int arrays.  Returns host arrays (seg_ptr, segs, order): per output tile the
+    non-empty (lo, hi, selector, 0) segments in selector order, and the tiles sorted by decreasing work."""
+    nsel = len(tabs)
+    allk = np.stack(tabs, axis=-2)                                # (batch, tiles_m, tiles_n, nsel, 2)
+    flat = (allk[..., 1] > allk[..., 0]).reshape(-1, nsel)
+    seg_ptr = np.concatenate([[0], np.cumsum(flat.sum(axis=1))]).astype(np.int32)
+    tile_idx, sel_idx = np.nonzero(flat)
+    lohi = allk.reshape(-1, nsel, 2)[tile_idx, sel_idx]
+    segs = np.zeros((max(len(sel_idx), 1), 4), dtype=np.int32)
+    segs[:len(sel_idx), 0:2] = lohi
+    segs[:len(sel_idx), 2] = sel_idx
+    work = np.zeros(flat.shape[0], dtype=np.int64)
+    if len(sel_idx):
+        np.add.at(work, tile_idx, (lohi[:, 1] - lohi[:, 0]).astype(np.int64))
+    order = np.argsort(-work, kind="stable").astype(np.int32)
+    return seg_ptr, segs, order
+
+
+def banded_order(tab):
+    """Tiles of a banded GEMM sorted by decreasing k-range length (stable); `tab` is (..., 2)."""
+    work = (tab[..., 1] - tab[..., 0]).reshape(-1)
+    return np.argsort(-np.maximum(work, 0), kind="stable").astype(np.int32)
+
+
 class HeffSectorPlan:
     """
     Work lists for `out = L.W.A.R` on one site (or merged site pair) with quantum numbers.
@@ -141,26 +167,12 @@ class HeffSectorPlan:
         self.tab3 = None
         # step 3 as ONE segmented launch (ptb_gemm_segmented): per output tile the list of (k-tile range, left MPO
         # index) pairs that can contribute; selector k adds k*Dlp / k*dout*Drp elements to the l / t2 base pointers
-        allk = np.stack(self.tab3_host, axis=-2)                      # (dout, tiles_m, tiles_n, cl, 2)
-        mask = allk[..., 1] > allk[..., 0]
-        flat = mask.reshape(-1, cl)
-        self.seg_ptr_host = np.concatenate([[0], np.cumsum(flat.sum(axis=1))]).astype(np.int32)
-        tile_idx, k_idx = np.nonzero(flat)
-        lohi = allk.reshape(-1, cl, 2)[tile_idx, k_idx]
-        segs = np.zeros((max(len(k_idx), 1), 4), dtype=np.int32)
-        segs[:len(k_idx), 0:2] = lohi
-        segs[:len(k_idx), 2] = k_idx
-        self.segs_host = segs
+        self.seg_ptr_host, self.segs_host, self.order3_host = segment_tables(self.tab3_host)
         self.sel_off_host = np.stack([np.arange(cl) * Dlp, np.arange(cl) * dout * Drp], axis=1).astype(np.int64)
         self.seg3 = None
         # tile schedules: tiles sorted by decreasing number of k-tiles (stable), so that the round-robin assignment
         # of work units to the persistent CTAs is balanced although the per-tile work differs widely
-        work1 = (self.tab1_host[..., 1] - self.tab1_host[..., 0]).reshape(-1)
-        self.order1_host = np.argsort(-np.maximum(work1, 0), kind="stable").astype(np.int32)
-        seg_len = np.zeros(len(self.seg_ptr_host) - 1, dtype=np.int64)
-        if len(k_idx):
-            np.add.at(seg_len, tile_idx, (lohi[:, 1] - lohi[:, 0]).astype(np.int64))
-        self.order3_host = np.argsort(-seg_len, kind="stable").astype(np.int32)
+        self.order1_host = banded_order(self.tab1_host)
         self.order = None
         # row-activity flags of the W step: for every (BM-row block of i) x (128-column block of j') which input rows
         # (s, K) of t1 can hold entries, i.e. overlap a t1 tile that step 1 writes.  Inactive parts of t1 / t2 are
@@ -522,6 +534,10 @@ class BondSectorPlan:
         #     column j' needs qbl[i] = qbr[j'] - qw[k]
         self.B2 = [tile_k_ranges(self.qbl - self.qw[k], self.qbr - self.qw[k], self.qbl, bm, bn, bk)[None]
                    for k in range(chi)]
+        # step 2 as one segmented launch (selector k: offsets k*Dl into l, k*Dr into t), work-sorted schedules
+        self.seg_ptr_host, self.segs_host, self.order2_host = segment_tables(self.B2)
+        self.sel_off_host = np.stack([np.arange(chi) * Dl, np.arange(chi) * Dr], axis=1).astype(np.int64)
+        self.order1_host = banded_order(self.B1)
         self._dev = None
 
     def apply(self, c, l, r):
@@ -536,15 +552,25 @@ class BondSectorPlan:
             return apply_local_bond_contraction(c, l, r)
         if self._dev is None or self._dev[0] != c.device:
             up = lambda t: torch.from_numpy(np.ascontiguousarray(t)).to(c.device)     # noqa: E731
-            self._dev = (c.device, up(self.B1), [up(t) for t in self.B2])
-        _, B1, B2 = self._dev
+            self._dev = (c.device, up(self.B1), [up(t) for t in self.B2], up(self.seg_ptr_host), up(self.segs_host),
+                         up(self.sel_off_host), up(self.order1_host), up(self.order2_host))
+        _, B1, B2, seg_ptr, segs, sel_off, order1, order2 = self._dev
         dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
         es = 16 if cplx else 8
         stream = dev.stream_ptr(c.device)
         t = torch.empty((Dl, chi * Dr), dtype=c.dtype, device=c.device)
-        _banded(lib, dt, 0, 0, 0, Dl, chi * Dr, Dr, c.data_ptr(), Dr, r.data_ptr(), chi * Dr, t.data_ptr(), chi * Dr,
-                1, 0, 0, 0, False, B1, stream, "bond(1)")
+        tabs = _lib.SectorTables(B1.data_ptr(), None, None, None, order1.data_ptr() if _ORDERED else None)
+        st = lib.ptb_gemm_sector(dt, 0, 0, 0, Dl, chi * Dr, Dr, c.data_ptr(), Dr, r.data_ptr(), chi * Dr, t.data_ptr(),
+                                 chi * Dr, 1, 0, 0, 0, 0, ctypes.byref(tabs), stream)
+        _lib.check(st, "bond(1)")
         out = torch.empty((Dl, Dr), dtype=c.dtype, device=c.device)
+        if _SEGMENTED:
+            tabs = _lib.SectorTables(None, seg_ptr.data_ptr(), segs.data_ptr(), sel_off.data_ptr(),
+                                     order2.data_ptr() if _ORDERED else None)
+            st = lib.ptb_gemm_sector(dt, 1, 0, 0, Dl, Dr, Dl, l.data_ptr(), chi * Dl, t.data_ptr(), chi * Dr,
+                                     out.data_ptr(), Dr, 1, 0, 0, 0, 0, ctypes.byref(tabs), stream)
+            _lib.check(st, "bond(2)")
+            return out
         first = True
         for k in range(chi):
             if not _active(self.B2[k]):

@@ -11,9 +11,9 @@ small device->host copy returns the Lanczos coefficients.
 from . import _device as dev
 from .mps import MPS, mps_merge_tensor_pair, mps_split_tensor_svd
 from .mpo import MPO, mpo_merge_tensor_pair
-from .chain_ops import contraction_operator_step_right, contraction_operator_step_left
 from .block_sparse_util import qnumber_flatten, block_sparse_qr
-from ._sweep import prepare_environments, local_hamiltonian_step, local_bond_step, sector_plan
+from ._sweep import (prepare_environments, local_hamiltonian_step, local_bond_step, sector_plan, bond_plan,
+                     env_step_left, env_step_right)
 from .krylov import defer_checks
 
 __all__ = ["tdvp_singlesite", "tdvp_twosite"]
@@ -47,11 +47,14 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
         for i in range(nsites - 1):
             psi.a[i] = local_hamiltonian_step(lblocks[i], rblocks[i], ham[i], psi.a[i], 0.5 * dt, k, site_plan(i))
             b0, d, b1 = psi.a[i].shape
+            qold = psi.qbonds[i + 1]
             q, c, psi.qbonds[i + 1] = block_sparse_qr(
                 psi.a[i].reshape(b0 * d, b1), qnumber_flatten((psi.qbonds[i], psi.qsite)), psi.qbonds[i + 1])
             psi.a[i] = dev.dense(q.reshape(b0, d, q.shape[1]))
-            lblocks[i + 1] = contraction_operator_step_left(psi.a[i], psi.a[i], ham[i], lblocks[i])
-            c = local_bond_step(lblocks[i + 1], rblocks[i], dev.dense(c), -0.5 * dt, k)
+            lblocks[i + 1] = env_step_left(psi, hamiltonian, i, lblocks[i])
+            c = dev.dense(c)
+            c = local_bond_step(lblocks[i + 1], rblocks[i], c, -0.5 * dt, k,
+                                bond_plan(psi.qbonds[i + 1], qold, qh[i + 1], c, lblocks[i + 1], rblocks[i]))
             nxt = psi.a[i + 1]
             psi.a[i + 1] = dev.gemm(c, nxt.reshape(nxt.shape[0], -1)).reshape((c.shape[0],) + tuple(nxt.shape[1:]))
 
@@ -65,10 +68,13 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
             b1, d, b0 = at.shape
             q, c, qbond = block_sparse_qr(
                 at.reshape(b1 * d, b0), qnumber_flatten((-psi.qbonds[i + 1], psi.qsite)), -psi.qbonds[i])
+            qold = psi.qbonds[i]
             psi.qbonds[i] = -qbond
             psi.a[i] = dev.dense(q.reshape(b1, d, q.shape[1]).permute(2, 1, 0))
-            rblocks[i - 1] = contraction_operator_step_right(psi.a[i], psi.a[i], ham[i], rblocks[i])
-            c = local_bond_step(lblocks[i], rblocks[i - 1], dev.dense(c.T), -0.5 * dt, k)
+            rblocks[i - 1] = env_step_right(psi, hamiltonian, i, rblocks[i])
+            c = dev.dense(c.T)
+            c = local_bond_step(lblocks[i], rblocks[i - 1], c, -0.5 * dt, k,
+                                bond_plan(qold, psi.qbonds[i], qh[i], c, lblocks[i], rblocks[i - 1]))
             prv = psi.a[i - 1]
             psi.a[i - 1] = dev.gemm(prv.reshape(-1, prv.shape[2]), c).reshape(tuple(prv.shape[:2]) + (c.shape[1],))
             psi.a[i - 1] = local_hamiltonian_step(
@@ -117,16 +123,16 @@ def tdvp_twosite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lanczos:
         # left -> right (tdvp.py:168-184)
         for i in range(nsites - 2):
             evolve_pair(i, 0.5 * dt, "right")
-            lblocks[i + 1] = contraction_operator_step_left(psi.a[i], psi.a[i], ham[i], lblocks[i])
+            lblocks[i + 1] = env_step_left(psi, hamiltonian, i, lblocks[i])
             backward_site(i + 1)
         # rightmost pair, full step (tdvp.py:187-198)
         i = nsites - 2
         evolve_pair(i, dt, "left")
-        rblocks[i] = contraction_operator_step_right(psi.a[i + 1], psi.a[i + 1], ham[i + 1], rblocks[i + 1])
+        rblocks[i] = env_step_right(psi, hamiltonian, i + 1, rblocks[i + 1])
         # right -> left (tdvp.py:201-217)
         for i in reversed(range(nsites - 2)):
             backward_site(i + 1)
             evolve_pair(i, 0.5 * dt, "left")
-            rblocks[i] = contraction_operator_step_right(psi.a[i + 1], psi.a[i + 1], ham[i + 1], rblocks[i + 1])
+            rblocks[i] = env_step_right(psi, hamiltonian, i + 1, rblocks[i + 1])
 
     return nrm

@@ -45,8 +45,8 @@ def timed(name, fn):
 _sweep.apply_local_hamiltonian = timed("matvec", chain_ops.apply_local_hamiltonian)
 _sweep.apply_local_bond_contraction = timed("bond_matvec", chain_ops.apply_local_bond_contraction)
 for mod in (ptdvp, pdmrg):
-    mod.contraction_operator_step_left = timed("env_update", chain_ops.contraction_operator_step_left)
-    mod.contraction_operator_step_right = timed("env_update", chain_ops.contraction_operator_step_right)
+    mod.env_step_left = timed("env_update", _sweep.env_step_left)
+    mod.env_step_right = timed("env_update", _sweep.env_step_right)
 qr_t = timed("qr_cusolver", block_sparse_util.block_sparse_qr)
 svd_t = timed("svd_cusolver", block_sparse_util.block_sparse_svd)
 pmps.block_sparse_qr = qr_t; ptdvp.block_sparse_qr = qr_t
