@@ -43,6 +43,24 @@ _SECTOR_MODE = os.environ.get("PYTENET_B200_SECTORS", "auto")
 _SECTOR_MIN_BOND = 256
 
 
+# Plans depend on the quantum numbers only.  Sweeps revisit the same bonds (every time step of TDVP, every sweep of
+# DMRG once the sector layouts have settled), so finished plans -- host work lists and their device copies -- are
+# kept in a small cache keyed by the quantum-number arrays.
+_PLAN_CACHE = {}
+_PLAN_CACHE_MAX = 512
+
+
+def _cached_plan(cls, cplx, *qnums):
+    key = (cls.__name__, bool(cplx)) + tuple(np.asarray(q, dtype=np.int64).tobytes() for q in qnums)
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.clear()
+        plan = cls(*qnums, cplx=cplx)
+        _PLAN_CACHE[key] = plan
+    return plan
+
+
 def sector_plan(ql, qs, qr, qwl, qwr, like):
     """HeffSectorPlan for a local problem, or None when the dense path is the right choice."""
     if _SECTOR_MODE == "0":
@@ -51,7 +69,7 @@ def sector_plan(ql, qs, qr, qwl, qwr, like):
         return None
     if not (np.any(ql) or np.any(qr) or np.any(qs) or np.any(qwl) or np.any(qwr)):
         return None
-    return HeffSectorPlan(ql, qs, qr, qwl, qwr, cplx=True if like is None else like.dtype.is_complex)
+    return _cached_plan(HeffSectorPlan, True if like is None else like.dtype.is_complex, ql, qs, qr, qwl, qwr)
 
 
 def _use_sectors(nbond, *qnums):
@@ -68,7 +86,7 @@ def env_step_left(psi, hamiltonian, i, l):
     a, w = psi.a[i], hamiltonian.a[i]
     qn = (psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], hamiltonian.qbonds[i], hamiltonian.qbonds[i + 1])
     if _use_sectors(max(a.shape[0], a.shape[2]), *qn) and isinstance(l, torch.Tensor) and l.shape[0] == a.shape[0]:
-        plan = EnvSectorPlan(*qn, cplx=dev.any_complex(a, l, w))
+        plan = _cached_plan(EnvSectorPlan, dev.any_complex(a, l, w), *qn)
         return plan.step_left(a, w, l)
     return contraction_operator_step_left(a, a, w, l)
 
@@ -78,7 +96,7 @@ def env_step_right(psi, hamiltonian, i, r):
     a, w = psi.a[i], hamiltonian.a[i]
     qn = (psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], hamiltonian.qbonds[i], hamiltonian.qbonds[i + 1])
     if _use_sectors(max(a.shape[0], a.shape[2]), *qn) and isinstance(r, torch.Tensor) and r.shape[0] == a.shape[2]:
-        plan = EnvSectorPlan(*qn, cplx=dev.any_complex(a, r, w))
+        plan = _cached_plan(EnvSectorPlan, dev.any_complex(a, r, w), *qn)
         return plan.step_right(a, w, r)
     return contraction_operator_step_right(a, a, w, r)
 
@@ -87,7 +105,7 @@ def bond_plan(qbl, qbr, qw, c, l, r):
     """BondSectorPlan for the zero-site problem on a bond (rows of `c`: qbl, columns: qbr), or None."""
     if not _use_sectors(max(c.shape), qbl, qbr, qw):
         return None
-    return BondSectorPlan(qbl, qbr, qw, cplx=dev.any_complex(c, l, r))
+    return _cached_plan(BondSectorPlan, dev.any_complex(c, l, r), qbl, qbr, qw)
 
 
 class HeffOperator:

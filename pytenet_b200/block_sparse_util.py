@@ -60,7 +60,7 @@ def is_qsparse(a, qnums):
         if all(not np.any(np.asarray(q)) for q in qnums):
             return True                      # all quantum numbers zero: nothing is forbidden
         mask = _forbidden_mask(qnums, a.device)
-        return not bool(torch.any(a[mask] != 0).item())
+        return not bool(torch.any((a != 0) & mask).item())         # one fused pass, no boolean gather
     mask = qnumber_outer_sum(qnums) != 0
     return not np.any(np.asarray(a)[mask])
 
@@ -83,6 +83,15 @@ def _sector_plan(q0, q1):
     rows = [o0[q0[o0] == q] for q in sectors]
     cols = [o1[q1[o1] == q] for q in sectors]
     return sectors, rows, cols
+
+
+def _device_indices(index_lists, device):
+    """One host->device copy for all index arrays of a sector loop; returns per-array device views."""
+    lens = [len(ix) for ix in index_lists]
+    if sum(lens) == 0:
+        return [torch.empty(0, dtype=torch.int64, device=device) for _ in index_lists]
+    flat = torch.from_numpy(np.concatenate([np.asarray(ix, dtype=np.int64) for ix in index_lists])).to(device)
+    return list(torch.split(flat, lens))
 
 
 def _is_identity_range(idx, n):
@@ -124,10 +133,10 @@ def block_sparse_qr(a, q0, q1):
     r = torch.zeros((nb, a.shape[1]), dtype=a.dtype, device=a.device)
     qinterm = np.zeros(nb, dtype=q0.dtype)
     pos = 0
-    for qn, ri, ci, sz in zip(sectors, rows, cols, sizes):
-        qs, rs = torch.linalg.qr(_block(a, ri, ci), mode="reduced")
-        rt = torch.as_tensor(ri, device=a.device)
-        ct = torch.as_tensor(ci, device=a.device)
+    dix = _device_indices(list(rows) + list(cols), a.device)
+    rts, cts = dix[:len(rows)], dix[len(rows):]
+    for qn, rt, ct, sz in zip(sectors, rts, cts, sizes):
+        qs, rs = torch.linalg.qr(a.index_select(0, rt).index_select(1, ct), mode="reduced")
         q[rt, pos:pos + sz] = qs
         r[pos:pos + sz, ct] = rs
         qinterm[pos:pos + sz] = qn
@@ -190,10 +199,11 @@ def block_sparse_svd(a, q0, q1):
     s_dev = torch.zeros(nb, dtype=dev.F64, device=a.device)
     q = np.zeros(nb, dtype=q0.dtype)
     pos = 0
-    for qn, ri, ci, sz in zip(sectors, rows, cols, sizes):
-        us, ss, vs = torch.linalg.svd(_block(a, ri, ci), full_matrices=False, driver=_SVD_DRIVER)
-        rt = torch.as_tensor(ri, device=a.device)
-        ct = torch.as_tensor(ci, device=a.device)
+    dix = _device_indices(list(rows) + list(cols), a.device)
+    rts, cts = dix[:len(rows)], dix[len(rows):]
+    for qn, rt, ct, sz in zip(sectors, rts, cts, sizes):
+        us, ss, vs = torch.linalg.svd(a.index_select(0, rt).index_select(1, ct), full_matrices=False,
+                                      driver=_SVD_DRIVER)
         u[rt, pos:pos + sz] = us
         v[pos:pos + sz, ct] = vs
         s_dev[pos:pos + sz] = ss
