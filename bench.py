@@ -144,8 +144,19 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1, which OpenBLAS honours at load time; the CPU arm is meant to use every
+    host core, so the BLAS pool is reset explicitly."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1, user_api="blas")
+    except Exception:
+        pass
+
+
 def cpu_time_matvec(D, d, chi, reps=1):
     import oracle
+    use_all_host_threads()
     a, w, l, r = host_inputs(D, d, chi, seed=1)
     best = float("inf")
     for _ in range(reps):
@@ -182,6 +193,7 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle
+    use_all_host_threads()
     steps, warm = args.steps, args.warmup
     D, t512 = pick_cpu_sample(150.0 / max(1, steps + warm))
     a, w, l, r = host_inputs(D, d_HEAD, CHI, seed=1)
