@@ -249,3 +249,41 @@ def test_config2_shape_direct_parity_with_oracle(cuda_lib):
     c = a[:, 0, :].copy()
     got = ptb.apply_local_bond_contraction(cu(c), cu(l), cu(r)).cpu().numpy()
     assert rel(got, oracle.apply_local_bond_contraction(c, l, r)) < TOL
+
+
+def test_headline_shape_properties(cuda_lib):
+    """BASELINE headline shape (two-site XXZ, a (2048,4,2048), l/r (2048,5,2048), complex128), where the CPU oracle
+    would need minutes: size-independent properties of the device matvec -- Hermiticity <x|H y> = <H x|y> for
+    Hermitian environments, linearity, and agreement of the device-resident path with the host-buffer C entry
+    (sliced copy/compute pipeline, accumulated step-1 slices)."""
+    import pytenet_b200 as ptb
+    from bench import xxz_two_site_w
+    D, d, chi = 2048, 4, 5
+    g = torch.Generator(device="cuda").manual_seed(7)
+
+    def crand(*shape):
+        return torch.randn(*shape, dtype=torch.complex128, device="cuda", generator=g)
+
+    def herm_env():
+        e = crand(D, chi, D)
+        return (e + e.conj().permute(2, 1, 0)).contiguous()       # e[:, k, :] Hermitian for every k
+
+    l, r = herm_env(), herm_env()
+    w = xxz_two_site_w()
+    w = np.ascontiguousarray(w + w.transpose(0, 2, 1, 3))           # real, symmetric in (s', s) for every (k, kappa):
+    #                                                                 with Hermitian l[:, k, :], r[:, kappa, :] H_eff is Hermitian
+    wd = torch.from_numpy(w).cuda()
+    x, y = crand(D, d, D), crand(D, d, D)
+    hx = ptb.apply_local_hamiltonian(x, wd, l, r)
+    hy = ptb.apply_local_hamiltonian(y, wd, l, r)
+    lhs = torch.vdot(x.reshape(-1), hy.reshape(-1)).item()
+    rhs = torch.vdot(hx.reshape(-1), y.reshape(-1)).item()
+    scale = (torch.linalg.norm(x) * torch.linalg.norm(hy)).item()
+    assert abs(lhs - rhs) < 1e-12 * scale
+    al, be = 0.3 - 1.1j, -0.7 + 0.2j
+    hz = ptb.apply_local_hamiltonian(al * x + be * y, wd, l, r)
+    assert (torch.linalg.norm(hz - (al * hx + be * hy)) / torch.linalg.norm(hz)).item() < 1e-13
+    del hz, hy, y
+    got = ptb.apply_local_hamiltonian(x.cpu().numpy(), w, l.cpu().numpy(), r.cpu().numpy())
+    assert isinstance(got, np.ndarray)
+    assert rel(got, hx.cpu().numpy()) < 1e-13

@@ -332,3 +332,43 @@ def test_sector_plans_for_environment_updates_and_bond_contraction(cuda_lib):
         bplan = BondSectorPlan(qbl, qbr, qwl, cplx=True)
         got = bplan.apply(cu(c), cu(lb), cu(rb)).cpu().numpy()
         assert rel(got, oracle.apply_local_bond_contraction(c, lb, rb)) < 1e-12, ("bond", Dl, Dr)
+
+
+def test_sector_path_at_config3_shape(cuda_lib):
+    """BASELINE config-3 shape (two-site Fermi-Hubbard, a (2048,16,2048), h2 (6,16,16,6), (N,Sz) sectors): the sector
+    path (banded step 1, masked W step, segmented step 3, work-sorted schedules) equals the dense device matvec,
+    forbidden entries stay exactly zero, and a second application with a new vector on the same plan (structural
+    zeros of the intermediates not rewritten) is still exact."""
+    import pytenet_b200 as ptb
+    from pytenet_b200 import hamiltonian as ham
+    from pytenet_b200.sectors import HeffSectorPlan
+    D = 2048
+    qsite, qb, wbulk, _, _ = ham._fermi_hubbard_bulk(1.0, 4.0, 0.0)
+    qsite = np.array(qsite); qb = np.array(qb)
+    qs2 = np.add.outer(qsite, qsite).reshape(-1)
+    w2 = np.einsum("kpqm,mrsn->kprqsn", wbulk, wbulk).reshape(6, 16, 16, 6)
+    cand = [(dn, ds) for dn in range(-4, 5) for ds in range(-4, 5) if (dn + ds) % 2 == 0]
+    wts = np.array([np.exp(-(dn ** 2 + ds ** 2) / (2 * 1.6 ** 2)) for dn, ds in cand])
+    sizes = np.floor(wts / wts.sum() * D).astype(int)
+    sizes[np.argmax(sizes)] += D - sizes.sum()
+    q = np.sort(np.concatenate([np.full(sz, ptb.encode_quantum_number_pair(32 + dn, ds))
+                                for (dn, ds), sz in zip(cand, sizes)]))
+    g = torch.Generator(device="cuda").manual_seed(3)
+
+    def tensor(shape, qn):
+        t = torch.randn(*shape, dtype=torch.complex128, device="cuda", generator=g)
+        ptb.enforce_qsparsity(t, qn)
+        return t
+
+    l = tensor((D, 6, D), [q, qb, -q]); r = tensor((D, 6, D), [q, qb, -q])
+    w = torch.from_numpy(w2).cuda()
+    plan = HeffSectorPlan(q, qs2, q, qb, qb, cplx=True)
+    for _ in range(2):
+        a = tensor((D, 16, D), [q, qs2, -q])
+        got = plan.apply(a, w, l, r)
+        want = ptb.apply_local_hamiltonian(a, w, l, r)
+        assert (torch.linalg.norm(got - want) / torch.linalg.norm(want)).item() < 1e-13
+        mask = (torch.from_numpy(q).cuda()[:, None, None] + torch.from_numpy(qs2).cuda()[None, :, None]
+                - torch.from_numpy(q).cuda()[None, None, :]) != 0
+        assert not bool(torch.any((got != 0) & mask).item())
+        del a, got, want, mask
