@@ -87,3 +87,77 @@ def test_tile_k_ranges_bounds():
     assert list(tab[1, 1]) == [1, 3]
     # rows tile 0 ([0,3)) with cols tile 1 ([3,9)): empty
     assert list(tab[0, 1]) == [0, 0]
+
+
+def emulate_lean(plan, a, w, l, r, t1, t2):
+    """NumPy emulation of the lean sector path as the device executes it: step 1 stores only tiles with a
+    non-empty k range (in the scheduled order), the W step obeys the row-activity flags, step 3 sums the
+    per-tile segment lists.  `t1`, `t2` are persistent buffers whose structural zeros are never rewritten."""
+    Dl, d, Dr, cl, cr, dout, Dlp, Drp = plan.dims
+    bm, bn, bk = plan.tile
+    rm = r.reshape(Dr, cr * Drp)
+    tab = plan.tab1_host
+    tiles_m, tiles_n = tab.shape[1], tab.shape[2]
+    assert sorted(plan.order1_host.tolist()) == list(range(tab[..., 0].size))
+    for t in plan.order1_host:                                      # (batch s, tile row, tile column) in table order
+        s, rem = divmod(int(t), tiles_m * tiles_n)
+        tm, tn = divmod(rem, tiles_n)
+        lo, hi = tab[s, tm, tn] * bk
+        if hi <= lo:
+            continue                                                # accumulate == 2: empty tiles are left untouched
+        ms = slice(tm * bm, min((tm + 1) * bm, Dl)); ns = slice(tn * bn, min((tn + 1) * bn, cr * Drp))
+        t1[ms, s, ns] = a[ms, s, lo:hi] @ rm[lo:hi, ns]
+    # W step with flags per (bm-row block of i, 128-column block of j')
+    wm = w.reshape(cl * dout, d * cr)
+    ina = plan.in_active_host
+    t1v = t1.reshape(Dl, d * cr, Drp)
+    for ib in range(ina.shape[0]):
+        for jb in range(ina.shape[1]):
+            isl = slice(ib * bm, min((ib + 1) * bm, Dl)); jsl = slice(jb * 128, min((jb + 1) * 128, Drp))
+            fin = ina[ib, jb]
+            fout = np.any((wm != 0) & fin[None, :], axis=1)         # what _w_flags derives from W's pattern
+            for m in np.nonzero(fout)[0]:
+                cols = np.nonzero((wm[m] != 0) & fin)[0]
+                t2[isl, m, jsl] = np.einsum("c,icj->ij", wm[m, cols], t1v[isl][:, cols][:, :, jsl])
+    # step 3: segments
+    out = np.zeros((Dlp, dout, Drp), dtype=complex)
+    t2v = t2.reshape(Dl, cl, dout, Drp)
+    sp_, segs = plan.seg_ptr_host, plan.segs_host
+    t3m, t3n = -(-Dlp // bm), -(-Drp // bn)
+    assert sorted(plan.order3_host.tolist()) == list(range(dout * t3m * t3n))
+    for t in plan.order3_host:
+        b, rem = divmod(int(t), t3m * t3n)
+        tm, tn = divmod(rem, t3n)
+        ms = slice(tm * bm, min((tm + 1) * bm, Dlp)); ns = slice(tn * bn, min((tn + 1) * bn, Drp))
+        for lo, hi, k, _ in segs[sp_[t]:sp_[t + 1]]:
+            assert plan.sel_off_host[k, 0] == k * Dlp and plan.sel_off_host[k, 1] == k * dout * Drp
+            out[ms, b, ns] += l[lo * bk:hi * bk, k, ms].T @ t2v[lo * bk:hi * bk, k, b, ns]
+    return out
+
+
+def test_lean_segmented_path_with_persistent_intermediates(cuda_lib):
+    """Structural zeros written once: the emulated lean path stays exact over several vectors and MPO tensors
+    on the same persistent t1 / t2 buffers (stale entries of earlier applications must never leak)."""
+    rng = np.random.default_rng(11)
+    (a, w, l, r), (ql, qs, qr, qwl, qwr) = make_case(rng, 300, 3, 280, 5, 4, sort=True, spread=4)
+    plan = HeffSectorPlan(ql, qs, qr, qwl, qwr, cplx=True)
+    Dl, d, Dr, cl, cr, dout, Dlp, Drp = plan.dims
+    t1 = np.zeros((Dl, d, cr * Drp), dtype=complex)
+    t2 = np.zeros((Dl, cl * dout, Drp), dtype=complex)
+    assert plan.in_active_host.mean() < 0.9                         # the flags actually skip rows
+    for trial in range(3):
+        a2 = crand(rng, a.shape); ob.enforce_qsparsity(a2, [ql, qs, -qr])
+        got = emulate_lean(plan, a2, w, l, r, t1, t2)
+        ref = oracle.apply_local_hamiltonian(a2, w, l, r)
+        assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref)
+    fc = plan.flop_counts(nnz_w=int(np.count_nonzero(w)))
+    assert 0 < fc["exact"] <= fc["visited"] <= 8.0 * (Dl * d * Dr * cr * Drp + Dlp * Dl * cl * dout * Drp) * 4
+
+
+def test_plan_cache_returns_same_plan(cuda_lib):
+    from pytenet_b200 import _sweep
+    q = np.sort(np.random.default_rng(0).integers(-2, 3, size=300)); qs = np.array([0, 1]); qw = np.array([0, 1, -1])
+    p1 = _sweep._cached_plan(HeffSectorPlan, True, q, qs, q, qw, qw)
+    p2 = _sweep._cached_plan(HeffSectorPlan, True, q.copy(), qs, q, qw, qw)
+    p3 = _sweep._cached_plan(HeffSectorPlan, False, q, qs, q, qw, qw)
+    assert p1 is p2 and p3 is not p1 and p3.cplx is False
