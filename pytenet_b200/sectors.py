@@ -373,9 +373,11 @@ class HeffSectorPlan:
 # ---------------------------------------------------------------------------------------------
 
 def _banded(lib, dt, ta, tb, cj, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, batch, sa, sb, sc, acc, tab, stream,
-            what):
-    st = lib.ptb_gemm_banded(dt, ta, tb, cj, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, batch, sa, sb, sc,
-                             int(acc), tab.data_ptr(), stream)
+            what, order=None):
+    tabs = _lib.SectorTables(tab.data_ptr(), None, None, None,
+                             order.data_ptr() if (order is not None and _ORDERED) else None)
+    st = lib.ptb_gemm_sector(dt, ta, tb, cj, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, batch, sa, sb, sc,
+                             int(acc), ctypes.byref(tabs), stream)
     _lib.check(st, what)
 
 
@@ -415,13 +417,21 @@ class EnvSectorPlan:
         self.R3 = [np.ascontiguousarray(np.stack(
             [tile_k_ranges(ql_ + qwl_[k] + qs_[sp], ql_ + qs_[sp], qr_, bm, bn, bk) for k in range(cl)]))
             for sp in range(d)]
+        # (L3) as one segmented launch over s (selector s: offsets s*Dr into a, s*cr*Dr into t2); work-sorted
+        # schedules for the banded launches
+        self.L3_seg = segment_tables(self.L3)
+        self.L3_off = np.stack([np.arange(d) * Dr, np.arange(d) * cr * Dr], axis=1).astype(np.int64)
         self._dev = None
+        self._aux = None
 
     def _upload(self, device):
         if self._dev is None or self._dev[0] != device:
             up = lambda t: torch.from_numpy(np.ascontiguousarray(t)).to(device)      # noqa: E731
             self._dev = (device, [up(t) for t in self.L1], [up(t) for t in self.L3], up(self.R1),
                          [up(t) for t in self.R3])
+            self._aux = {"L1": [up(banded_order(t)) for t in self.L1], "R1": up(banded_order(self.R1)),
+                         "R3": [up(banded_order(t)) for t in self.R3],
+                         "L3": tuple(up(t) for t in self.L3_seg) + (up(self.L3_off),)}
         return self._dev[1:]
 
     def _prep(self, a, w, env):
@@ -467,11 +477,20 @@ class EnvSectorPlan:
             if not _active(self.L1[k]):
                 continue
             _banded(lib, dt, 0, 0, 1, Dl, Dr, Dl, l.data_ptr() + k * Dl * es, cl * Dl, a.data_ptr(), d * Dr,
-                    t.data_ptr() + k * d * Dr * es, cl * d * Dr, d, 0, Dr, Dr, False, L1[k], stream, "step_left(1)")
+                    t.data_ptr() + k * d * Dr * es, cl * d * Dr, d, 0, Dr, Dr, False, L1[k], stream, "step_left(1)",
+                    self._aux["L1"][k])
         self._w_step(lib, dt, cplx, w, True, t, t2, Dl, d * cr, cl * d, Dr, stream)     # (L2)
         out = torch.empty((Dr, cr, Dr), dtype=a.dtype, device=a.device)
+        if _SEGMENTED:                                                                 # (L3), one launch
+            seg_ptr, segs, order, off = self._aux["L3"]
+            tabs = _lib.SectorTables(None, seg_ptr.data_ptr(), segs.data_ptr(), off.data_ptr(),
+                                     order.data_ptr() if _ORDERED else None)
+            st = lib.ptb_gemm_sector(dt, 1, 0, 0, Dr, cr * Dr, Dl, a.data_ptr(), d * Dr, t2.data_ptr(), d * cr * Dr,
+                                     out.data_ptr(), cr * Dr, 1, 0, 0, 0, 0, ctypes.byref(tabs), stream)
+            _lib.check(st, "step_left(3)")
+            return out
         first = True
-        for s in range(d):                                                             # (L3)
+        for s in range(d):                                                             # (L3), one launch per s
             if not _active(self.L3[s]):
                 continue
             _banded(lib, dt, 1, 0, 0, Dr, cr * Dr, Dl, a.data_ptr() + s * Dr * es, d * Dr,
@@ -497,7 +516,7 @@ class EnvSectorPlan:
         t1 = torch.empty((Dl, d * cr, Dr), dtype=a.dtype, device=a.device)
         t2 = torch.empty((Dl, cl * d, Dr), dtype=a.dtype, device=a.device)
         _banded(lib, dt, 0, 0, 0, Dl, cr * Dr, Dr, a.data_ptr(), d * Dr, r.data_ptr(), cr * Dr, t1.data_ptr(),
-                d * cr * Dr, d, Dr, 0, cr * Dr, False, R1, stream, "step_right(1)")                       # (R1)
+                d * cr * Dr, d, Dr, 0, cr * Dr, False, R1, stream, "step_right(1)", self._aux["R1"])      # (R1)
         self._w_step(lib, dt, cplx, w, False, t1, t2, Dl, cl * d, d * cr, Dr, stream)                    # (R2)
         out = torch.empty((Dl, cl, Dl), dtype=a.dtype, device=a.device)
         first = True
@@ -506,7 +525,7 @@ class EnvSectorPlan:
                 continue
             _banded(lib, dt, 0, 1, 1, Dl, Dl, Dr, t2.data_ptr() + sp * Dr * es, cl * d * Dr,
                     a.data_ptr() + sp * Dr * es, d * Dr, out.data_ptr(), cl * Dl, cl, d * Dr, 0, Dl, not first,
-                    R3[sp], stream, "step_right(3)")
+                    R3[sp], stream, "step_right(3)", self._aux["R3"][sp])
             first = False
         if first:
             out.zero_()
