@@ -280,6 +280,20 @@ int ptb_krylov_expm_apply(int v_dtype, int64_t n, int numiter, const void* v, in
                           double dt_re, double dt_im, int out_is_complex, void* coeff_ws, void* out, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Batched per-sector QR of a block-sparse matrix        pytenet/block_sparse_util.py:106-180
+ * One launch factorises `nsec` gathered blocks A[rows_s, cols_s] (one CTA each, block held in shared memory,
+ * unblocked Householder QR with LAPACK's zgeqr2 / zung2r conventions: real diagonal of R) and scatters
+ *   q[rows_s[i], pos_s + j] = Q_s[i, j],   r[pos_s + i, cols_s[j]] = R_s[i, j]   (j >= i),   i, j < min(m_s, n_s)
+ * into the caller's zero-initialised row-major outputs q (ldq) and r (ldr).  a is row-major with leading dimension
+ * lda.  meta: 8 int32 per sector {m, n, offset into rowidx, offset into colidx, pos, 0, 0, 0}; every block must
+ * satisfy m*n <= max_block_elems and max_block_elems * element size <= ptb_block_qr_max_block_bytes() (larger
+ * blocks are the caller's: cuSOLVER).  All tables are device arrays.
+ * ------------------------------------------------------------------------- */
+size_t ptb_block_qr_max_block_bytes(void);
+int ptb_block_qr(int dtype, const void* a, int64_t lda, int nsec, const int32_t* meta, int max_block_elems,
+                 const int32_t* rowidx, const int32_t* colidx, void* q, int64_t ldq, void* r, int64_t ldr, void* stream);
+
+/* ---------------------------------------------------------------------------
  * A whole Lanczos run on the local effective Hamiltonian in ONE call
  *   pytenet/krylov.py:12-57 driven by the closures tdvp.py:223-229 (site), tdvp.py:232-238 (bond),
  *   dmrg.py:181-189.

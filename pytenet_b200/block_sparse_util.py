@@ -1,9 +1,11 @@
 """
 Quantum-number (block-sparse) helpers around the hot path, device-resident
 (pytenet/block_sparse_util.py).  Quantum numbers are small host-side integer
-arrays; tensors are CUDA torch tensors.  Sector-wise QR / SVD run on the device
+arrays; tensors are CUDA torch tensors.  Sector-wise SVD / eigh run on the device
 through cuSOLVER (torch.linalg), which north_star names as "not the
-optimisation target"; sector order, the stable grouping of indices and the
+optimisation target"; sector-wise QR uses one launch of the batched Householder
+kernel (csrc/block_qr.cu) for all sectors that fit in shared memory and cuSOLVER
+for the rest; sector order, the stable grouping of indices and the
 number of bond indices each sector contributes follow the reference exactly
 (block_sparse_util.py:33-37, 82-83, 151-169, 288-303).
 """
@@ -13,12 +15,15 @@ import numpy as np
 import torch
 
 from . import _device as dev
+from . import _lib
 
 __all__ = ["qnumber_outer_sum", "common_qnumbers", "qnumber_flatten", "is_qsparse", "enforce_qsparsity",
            "block_sparse_qr", "block_sparse_eigh", "block_sparse_svd"]
 
 # SVD driver for cuSOLVER: "gesvd" (QR iteration, closest to LAPACK) unless overridden
 _SVD_DRIVER = os.environ.get("PYTENET_B200_SVD_DRIVER", "gesvd")
+# batched per-sector QR kernel (csrc/block_qr.cu) for sector blocks that fit in shared memory; "0" = cuSOLVER only
+_BATCHED_QR = os.environ.get("PYTENET_B200_BATCHED_QR", "1") != "0"
 
 
 def qnumber_outer_sum(qnums):
@@ -107,6 +112,59 @@ def _block(a, ri, ci):
     return a.index_select(0, rt).index_select(1, ct)
 
 
+class _QRPlan:
+    """Everything block_sparse_qr derives from the quantum numbers alone: sectors, index sets, positions on the
+    intermediate bond, which sectors the batched kernel takes, and the kernel's tables on the device.  Cached per
+    (q0, q1): sweeps factorise the same bonds again every time step, and a cached plan means no host->device
+    transfer (a synchronisation point) on the way."""
+
+    def __init__(self, q0, q1, shape, es, device):
+        self.sectors, self.rows, self.cols = _sector_plan(q0, q1)
+        rows, cols = self.rows, self.cols
+        self.sizes = [min(len(ri), len(ci)) for ri, ci in zip(rows, cols)]
+        self.nb = int(sum(self.sizes))
+        self.starts = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
+        self.qinterm = np.zeros(self.nb, dtype=q0.dtype)
+        for qn, p0, sz in zip(self.sectors, self.starts[:-1], self.sizes):
+            self.qinterm[p0:p0 + sz] = qn
+        limit = _lib.load().ptb_block_qr_max_block_bytes() // es if _BATCHED_QR else 0
+        self.one_dense = (len(self.sectors) == 1 and _is_identity_range(rows[0], shape[0])
+                          and _is_identity_range(cols[0], shape[1]))
+        n = len(self.sectors)
+        self.small = [i for i in range(n) if len(rows[i]) * len(cols[i]) <= limit]
+        self.large = [i for i in range(n) if len(rows[i]) * len(cols[i]) > limit]
+        self.tab = None
+        if self.small:
+            meta = np.zeros((len(self.small), 8), dtype=np.int32)
+            ro = co = 0
+            for j, i in enumerate(self.small):
+                meta[j, :5] = (len(rows[i]), len(cols[i]), ro, co, self.starts[i])
+                ro += len(rows[i]); co += len(cols[i])
+            tables = np.concatenate([meta.reshape(-1)] + [np.asarray(rows[i], dtype=np.int32) for i in self.small]
+                                    + [np.asarray(cols[i], dtype=np.int32) for i in self.small])
+            self.tab = torch.from_numpy(tables).to(device)
+            self.row_off = 4 * meta.size
+            self.col_off = 4 * (meta.size + ro)
+            self.max_elems = int(max(len(rows[i]) * len(cols[i]) for i in self.small))
+        self.large_idx = None
+        if self.large and not self.one_dense:
+            self.large_idx = _device_indices([rows[i] for i in self.large] + [cols[i] for i in self.large], device)
+
+
+_qr_plans = {}
+
+
+def _qr_plan(q0, q1, shape, es, device):
+    key = (q0.tobytes(), q1.tobytes(), q0.dtype.str, q1.dtype.str, es, device.index)
+    plan = _qr_plans.get(key)
+    if plan is None:
+        if len(_qr_plans) >= 1024:
+            _qr_plans.clear()
+        plan = _QRPlan(q0, q1, shape, es, device)
+        _qr_plans[key] = plan
+    return plan
+
+
 def block_sparse_qr(a, q0, q1):
     """
     Sector-wise reduced QR of a block-sparse matrix (`a[i, j] != 0` only if
@@ -114,34 +172,41 @@ def block_sparse_qr(a, q0, q1):
     each sector (:106-180, incl. the no-common-sector case :124-134).
     """
     assert a.ndim == 2
-    q0 = np.asarray(q0); q1 = np.asarray(q1)
+    q0 = np.ascontiguousarray(q0); q1 = np.ascontiguousarray(q1)
     assert len(q0) == a.shape[0] and len(q1) == a.shape[1]
     assert is_qsparse(a, [q0, -q1])
-    sectors, rows, cols = _sector_plan(q0, q1)
-    if len(sectors) == 0:
+    plan = _qr_plan(q0, q1, tuple(a.shape), a.element_size(), a.device)
+    if len(plan.sectors) == 0:
         assert float(torch.linalg.norm(a)) == 0
         q = torch.zeros((a.shape[0], 1), dtype=a.dtype, device=a.device)
         r = torch.zeros((1, a.shape[1]), dtype=a.dtype, device=a.device)
         q[0, 0] = 1
         return q, r, q0[:1]
-    sizes = [min(len(ri), len(ci)) for ri, ci in zip(rows, cols)]
-    nb = int(sum(sizes))
-    if len(sectors) == 1 and _is_identity_range(rows[0], a.shape[0]) and _is_identity_range(cols[0], a.shape[1]):
-        qs, rs = torch.linalg.qr(a, mode="reduced")          # dense fast path: one sector, no gather
-        return qs, rs, np.full(nb, sectors[0], dtype=q0.dtype)
+    if plan.one_dense and plan.large:
+        qs, rs = torch.linalg.qr(a, mode="reduced")          # dense fast path: one large sector, no gather
+        return qs, rs, plan.qinterm.copy()
+    a = dev.dense(a)
+    nb = plan.nb
     q = torch.zeros((a.shape[0], nb), dtype=a.dtype, device=a.device)
     r = torch.zeros((nb, a.shape[1]), dtype=a.dtype, device=a.device)
-    qinterm = np.zeros(nb, dtype=q0.dtype)
-    pos = 0
-    dix = _device_indices(list(rows) + list(cols), a.device)
-    rts, cts = dix[:len(rows)], dix[len(rows):]
-    for qn, rt, ct, sz in zip(sectors, rts, cts, sizes):
-        qs, rs = torch.linalg.qr(a.index_select(0, rt).index_select(1, ct), mode="reduced")
-        q[rt, pos:pos + sz] = qs
-        r[pos:pos + sz, ct] = rs
-        qinterm[pos:pos + sz] = qn
-        pos += sz
-    return q, r, qinterm
+    if plan.small:
+        # all sectors that fit in shared memory: ONE launch of the batched Householder kernel (csrc/block_qr.cu),
+        # which gathers each block, factorises it with LAPACK's conventions and scatters Q and R into place
+        tab = plan.tab
+        st = _lib.load().ptb_block_qr(_lib.PTB_COMPLEX128 if a.dtype.is_complex else _lib.PTB_REAL64, a.data_ptr(),
+                                      a.shape[1], len(plan.small), tab.data_ptr(), plan.max_elems,
+                                      tab.data_ptr() + plan.row_off, tab.data_ptr() + plan.col_off, q.data_ptr(), nb,
+                                      r.data_ptr(), a.shape[1], dev.stream_ptr(a.device))
+        _lib.check(st, "ptb_block_qr")
+    if plan.large:
+        nl = len(plan.large)
+        for j, i in enumerate(plan.large):
+            rt, ct = plan.large_idx[j], plan.large_idx[nl + j]
+            qs, rs = torch.linalg.qr(a.index_select(0, rt).index_select(1, ct), mode="reduced")
+            p0, sz = plan.starts[i], plan.sizes[i]
+            q[rt, p0:p0 + sz] = qs
+            r[p0:p0 + sz, ct] = rs
+    return q, r, plan.qinterm.copy()
 
 
 def block_sparse_eigh(a, q0):

@@ -91,3 +91,37 @@ def test_from_vector(case, tag):
     m = ptb.MPS.from_vector(3, 5, z["fv/input"], tol=float(z[f"{tag}/tol"]))
     assert m.bond_dims == list(z[f"{tag}/bond_dims"])
     assert rel(m.to_vector(), z[f"{tag}/vec"]) < 1e-12
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+def test_batched_sector_qr_matches_lapack(cuda_lib, cplx):
+    """block_sparse_qr with the batched Householder kernel (csrc/block_qr.cu): same conventions as LAPACK's
+    geqr2 / ung2r, so q, r and the intermediate quantum numbers equal the oracle's (NumPy / LAPACK per sector) to
+    rounding -- tall, wide, square and 1 x 1 sector blocks, a zero column, unsorted quantum numbers, and a block too
+    large for shared memory that takes the cuSOLVER route in the same call."""
+    import oracle.blocksparse as ob
+    import pytenet_b200 as ptb
+    rng = np.random.default_rng(31 + int(cplx))
+    # sector sizes (rows, cols): tall, wide, square, 1x1, large (cuSOLVER route), rows-only, cols-only
+    spec = {-2: (40, 7), -1: (5, 19), 0: (33, 33), 1: (1, 1), 2: (700, 300), 3: (4, 0), 5: (0, 6)}
+    q0 = np.concatenate([np.full(m, s) for s, (m, n) in spec.items()])
+    q1 = np.concatenate([np.full(n, s) for s, (m, n) in spec.items()])
+    q0 = q0[rng.permutation(len(q0))]; q1 = q1[rng.permutation(len(q1))]
+    a = rng.normal(size=(len(q0), len(q1)))
+    if cplx:
+        a = a + 1j * rng.normal(size=a.shape)
+    a[:, np.nonzero(q1 == -2)[0][3]] = 0                       # a zero column inside a sector
+    ob.enforce_qsparsity(a, [q0, -q1])
+    wq, wr, wqi = ob.block_sparse_qr(a, q0, q1)
+    gq, gr, gqi = ptb.block_sparse_qr(torch.from_numpy(a).cuda(), q0, q1)
+    assert np.array_equal(gqi, wqi)
+    gq, gr = gq.cpu().numpy(), gr.cpu().numpy()
+    assert gq.shape == wq.shape and gr.shape == wr.shape
+    assert rel(gq @ gr, a) < 1e-13
+    assert rel(gq.conj().T @ gq, np.eye(gq.shape[1])) < 1e-13
+    assert rel(gr, wr) < 1e-11 and rel(gq, wq) < 1e-11
+    # diagonal of R real (LAPACK convention; the sweeps read the norm from it, mps.py:157)
+    for s in np.unique(wqi):
+        rows = np.nonzero(wqi == s)[0]; cols = np.nonzero(q1 == s)[0]
+        d = np.diag(gr[np.ix_(rows, cols[:len(rows)])])
+        assert np.all(np.abs(d.imag) < 1e-14 * (1 + np.abs(d)))
