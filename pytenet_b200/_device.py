@@ -193,6 +193,12 @@ def w_csr_from_host(w_host, device):
     return _csr_arrays(mat, device)
 
 
+class _Nnz(int):
+    """Number of non-zeros that also carries the sparsity pattern (row pointers + column indices as bytes): a
+    content-based key for everything derived from W's pattern (pointer / version keys can be recycled)."""
+    pattern = b""
+
+
 def _csr_arrays(mat, device):
     rows, cols = np.nonzero(mat)
     if len(rows) > _CSR_MAX_NNZ:
@@ -204,8 +210,10 @@ def _csr_arrays(mat, device):
     if len(rows) == 0:                           # all-zero MPO tensor: keep the arrays non-empty (non-null pointers)
         cols = np.zeros(1, dtype=np.int64)
         vals = np.zeros(1, dtype=mat.dtype)
+    nnz = _Nnz(len(rows))
+    nnz.pattern = rowptr.tobytes() + cols.astype(np.int32).tobytes()
     return (torch.from_numpy(rowptr).to(device), torch.from_numpy(cols.astype(np.int32)).to(device),
-            torch.from_numpy(vals).to(device), len(rows))
+            torch.from_numpy(vals).to(device), nnz)
 
 
 def csr_arrays_any(mat):

@@ -241,10 +241,11 @@ class HeffSectorPlan:
         hit = self._flag_cache.get(key)
         if hit is not None:
             return hit
-        rowptr = csr[0].cpu().numpy().astype(np.int64)
+        r_out = self.dims[3] * self.dims[5]
+        pat = np.frombuffer(csr[3].pattern, dtype=np.int32)
+        rowptr = pat[:r_out + 1].astype(np.int64)
         nnz = int(rowptr[-1])
-        col = csr[1].cpu().numpy().astype(np.int64)[:nnz]
-        r_out = len(rowptr) - 1
+        col = pat[r_out + 1:].astype(np.int64)[:nnz]
         ina = self.in_active_host                                                 # (nib, ncb, r_in)
         rows = np.repeat(np.arange(r_out), np.diff(rowptr))
         outa = np.zeros(ina.shape[:2] + (r_out,), dtype=bool)
@@ -310,7 +311,7 @@ class HeffSectorPlan:
         lean = _SKIP_EMPTY and csr is not None
         if lean:
             key = (device.index, stream)
-            owner = (self._uid, ws.data_ptr(), nbytes, w.data_ptr(), w._version)
+            owner = (self._uid, ws.data_ptr(), nbytes, csr[3].pattern)
             if dev.ws_owner.get(key) != owner:
                 ws[:nbytes].zero_()
                 dev.ws_owner[key] = owner
@@ -326,7 +327,7 @@ class HeffSectorPlan:
         #     the usual sparse MPO tensors, dense small GEMM otherwise
         if lean:
             rowptr, col, val, _ = csr
-            flags = self._w_flags(csr, (w.data_ptr(), w._version), device)
+            flags = self._w_flags(csr, csr[3].pattern, device)
             st = lib.ptb_wapply_csr_masked(dt, int(w.dtype.is_complex), cl * dout, d * cr, Drp, rowptr.data_ptr(),
                                            col.data_ptr(), val.data_ptr(), t1.data_ptr(), t2.data_ptr(), Dl,
                                            flags.data_ptr(), self.tile[0], stream)
