@@ -294,6 +294,21 @@ int ptb_block_qr(int dtype, const void* a, int64_t lda, int nsec, const int32_t*
                  const int32_t* rowidx, const int32_t* colidx, void* q, int64_t ldq, void* r, int64_t ldr, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Batched per-sector SVD of a block-sparse matrix        pytenet/block_sparse_util.py:244-319
+ * One launch factorises `nsec` gathered blocks A[rows_s, cols_s] = U_s diag(sigma_s) V_s^H (one CTA each, one-sided
+ * Jacobi in shared memory, singular values in descending order) and scatters
+ *   u[rows_s[i], pos_s + j] = U_s[i, j],   s[pos_s + j] = sigma_s[j],   vh[pos_s + j, cols_s[c]] = conj(V_s[c, j])
+ * for j < min(m_s, n_s) into the caller's zero-initialised row-major outputs u (ldu), vh (ldv) and the device
+ * vector s.  meta as for ptb_block_qr; every block must satisfy
+ *   max(m,n)*min(m,n) + min(m,n)^2 <= max_work_elems,  max_work_elems * element size <= ptb_block_svd_max_block_bytes().
+ * Columns belonging to exactly zero singular values are left zero.  All tables are device arrays.
+ * ------------------------------------------------------------------------- */
+size_t ptb_block_svd_max_block_bytes(void);
+int ptb_block_svd(int dtype, const void* a, int64_t lda, int nsec, const int32_t* meta, int max_work_elems,
+                  const int32_t* rowidx, const int32_t* colidx, void* u, int64_t ldu, double* s, void* vh, int64_t ldv,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------
  * A whole Lanczos run on the local effective Hamiltonian in ONE call
  *   pytenet/krylov.py:12-57 driven by the closures tdvp.py:223-229 (site), tdvp.py:232-238 (bond),
  *   dmrg.py:181-189.

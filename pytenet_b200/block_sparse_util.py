@@ -24,6 +24,8 @@ __all__ = ["qnumber_outer_sum", "common_qnumbers", "qnumber_flatten", "is_qspars
 _SVD_DRIVER = os.environ.get("PYTENET_B200_SVD_DRIVER", "gesvd")
 # batched per-sector QR kernel (csrc/block_qr.cu) for sector blocks that fit in shared memory; "0" = cuSOLVER only
 _BATCHED_QR = os.environ.get("PYTENET_B200_BATCHED_QR", "1") != "0"
+# batched per-sector one-sided Jacobi SVD kernel (csrc/block_svd.cu) for small sector blocks; "0" = cuSOLVER only
+_BATCHED_SVD = os.environ.get("PYTENET_B200_BATCHED_SVD", "1") != "0"
 
 
 def qnumber_outer_sum(qnums):
@@ -149,6 +151,43 @@ class _QRPlan:
         self.large_idx = None
         if self.large and not self.one_dense:
             self.large_idx = _device_indices([rows[i] for i in self.large] + [cols[i] for i in self.large], device)
+        self._all_idx = None
+        self._svd = None
+        self.device = device
+
+    def svd_tables(self, es):
+        """Sectors the batched Jacobi kernel takes (block + right vectors fit in shared memory) and its tables."""
+        if self._svd is None:
+            limit = _lib.load().ptb_block_svd_max_block_bytes() // es if _BATCHED_SVD else 0
+            rows, cols = self.rows, self.cols
+
+            def work(i):
+                m, n = len(rows[i]), len(cols[i])
+                return max(m, n) * min(m, n) + min(m, n) ** 2
+            n = len(self.sectors)
+            small = [i for i in range(n) if work(i) <= limit]
+            large = [i for i in range(n) if work(i) > limit]
+            tab = None
+            row_off = col_off = max_work = 0
+            if small:
+                meta = np.zeros((len(small), 8), dtype=np.int32)
+                ro = co = 0
+                for j, i in enumerate(small):
+                    meta[j, :5] = (len(rows[i]), len(cols[i]), ro, co, self.starts[i])
+                    ro += len(rows[i]); co += len(cols[i])
+                tables = np.concatenate([meta.reshape(-1)] + [np.asarray(rows[i], dtype=np.int32) for i in small]
+                                        + [np.asarray(cols[i], dtype=np.int32) for i in small])
+                tab = torch.from_numpy(tables).to(self.device)
+                row_off, col_off = 4 * meta.size, 4 * (meta.size + ro)
+                max_work = int(max(work(i) for i in small))
+            self._svd = (small, large, tab, row_off, col_off, max_work)
+        return self._svd
+
+    def all_indices(self):
+        """Device index tensors of every sector (rows then columns), uploaded once (used by the per-sector SVD)."""
+        if self._all_idx is None:
+            self._all_idx = _device_indices(list(self.rows) + list(self.cols), self.device)
+        return self._all_idx
 
 
 _qr_plans = {}
@@ -243,35 +282,43 @@ def block_sparse_svd(a, q0, q1):
     float64 array ordered sector-ascending, sigma-descending inside a sector (:244-319).
     """
     assert a.ndim == 2
-    q0 = np.asarray(q0); q1 = np.asarray(q1)
+    q0 = np.ascontiguousarray(q0); q1 = np.ascontiguousarray(q1)
     assert len(q0) == a.shape[0] and len(q1) == a.shape[1]
     assert is_qsparse(a, [q0, -q1])
-    sectors, rows, cols = _sector_plan(q0, q1)
-    if len(sectors) == 0:
+    plan = _qr_plan(q0, q1, tuple(a.shape), a.element_size(), a.device)       # same sector structure as the QR
+    if len(plan.sectors) == 0:
         assert float(torch.linalg.norm(a)) == 0
         u = torch.zeros((a.shape[0], 1), dtype=a.dtype, device=a.device)
         v = torch.zeros((1, a.shape[1]), dtype=a.dtype, device=a.device)
         if a.shape[0] > 0:
             u[0, 0] = 1
         return u, np.zeros(1), v, q0[:1]
-    sizes = [min(len(ri), len(ci)) for ri, ci in zip(rows, cols)]
-    nb = int(sum(sizes))
-    if len(sectors) == 1 and _is_identity_range(rows[0], a.shape[0]) and _is_identity_range(cols[0], a.shape[1]):
+    nb = plan.nb
+    small, large, tab, row_off, col_off, max_work = plan.svd_tables(a.element_size())
+    if plan.one_dense and large:
         us, ss, vs = torch.linalg.svd(a, full_matrices=False, driver=_SVD_DRIVER)
-        return us, ss.cpu().numpy(), vs, np.full(nb, sectors[0], dtype=q0.dtype)
+        return us, ss.cpu().numpy(), vs, plan.qinterm.copy()
+    a = dev.dense(a)
     u = torch.zeros((a.shape[0], nb), dtype=a.dtype, device=a.device)
     v = torch.zeros((nb, a.shape[1]), dtype=a.dtype, device=a.device)
     s_dev = torch.zeros(nb, dtype=dev.F64, device=a.device)
-    q = np.zeros(nb, dtype=q0.dtype)
-    pos = 0
-    dix = _device_indices(list(rows) + list(cols), a.device)
-    rts, cts = dix[:len(rows)], dix[len(rows):]
-    for qn, rt, ct, sz in zip(sectors, rts, cts, sizes):
-        us, ss, vs = torch.linalg.svd(a.index_select(0, rt).index_select(1, ct), full_matrices=False,
-                                      driver=_SVD_DRIVER)
-        u[rt, pos:pos + sz] = us
-        v[pos:pos + sz, ct] = vs
-        s_dev[pos:pos + sz] = ss
-        q[pos:pos + sz] = qn
-        pos += sz
-    return u, s_dev.cpu().numpy(), v, q
+    if small:
+        # all sectors whose block and right vectors fit in shared memory: ONE launch of the batched one-sided
+        # Jacobi kernel (csrc/block_svd.cu), singular values descending per sector as LAPACK returns them
+        st = _lib.load().ptb_block_svd(_lib.PTB_COMPLEX128 if a.dtype.is_complex else _lib.PTB_REAL64, a.data_ptr(),
+                                       a.shape[1], len(small), tab.data_ptr(), max_work, tab.data_ptr() + row_off,
+                                       tab.data_ptr() + col_off, u.data_ptr(), nb, s_dev.data_ptr(), v.data_ptr(),
+                                       a.shape[1], dev.stream_ptr(a.device))
+        _lib.check(st, "ptb_block_svd")
+    if large:
+        dix = plan.all_indices()
+        nsec = len(plan.sectors)
+        for i in large:
+            rt, ct = dix[i], dix[nsec + i]
+            p0, sz = plan.starts[i], plan.sizes[i]
+            us, ss, vs = torch.linalg.svd(a.index_select(0, rt).index_select(1, ct), full_matrices=False,
+                                          driver=_SVD_DRIVER)
+            u[rt, p0:p0 + sz] = us
+            v[p0:p0 + sz, ct] = vs
+            s_dev[p0:p0 + sz] = ss
+    return u, s_dev.cpu().numpy(), v, plan.qinterm.copy()

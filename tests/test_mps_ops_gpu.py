@@ -125,3 +125,44 @@ def test_batched_sector_qr_matches_lapack(cuda_lib, cplx):
         rows = np.nonzero(wqi == s)[0]; cols = np.nonzero(q1 == s)[0]
         d = np.diag(gr[np.ix_(rows, cols[:len(rows)])])
         assert np.all(np.abs(d.imag) < 1e-14 * (1 + np.abs(d)))
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+def test_batched_sector_svd(cuda_lib, cplx):
+    """block_sparse_svd with the batched one-sided Jacobi kernel (csrc/block_svd.cu): singular values equal the
+    oracle's (NumPy / LAPACK per sector) to 1e-13 of the largest one, in the same sector-ascending /
+    sigma-descending order with identical bond quantum numbers; u s v reconstructs the matrix; left / right vectors
+    of non-zero singular values are orthonormal -- tall, wide, square and 1 x 1 blocks, a zero column (exactly zero
+    singular value), unsorted quantum numbers, and a block too large for shared memory (cuSOLVER route)."""
+    import oracle.blocksparse as ob
+    import pytenet_b200 as ptb
+    rng = np.random.default_rng(41 + int(cplx))
+    spec = {-2: (40, 7), -1: (5, 19), 0: (33, 33), 1: (1, 1), 2: (300, 260), 3: (4, 0), 5: (0, 6), 7: (64, 50)}
+    q0 = np.concatenate([np.full(m, s) for s, (m, n) in spec.items()])
+    q1 = np.concatenate([np.full(n, s) for s, (m, n) in spec.items()])
+    q0 = q0[rng.permutation(len(q0))]; q1 = q1[rng.permutation(len(q1))]
+    a = rng.normal(size=(len(q0), len(q1)))
+    if cplx:
+        a = a + 1j * rng.normal(size=a.shape)
+    a[:, np.nonzero(q1 == -2)[0][3]] = 0
+    # graded singular values in one sector (exercise the relative accuracy of the Jacobi sweeps)
+    r7, c7 = np.nonzero(q0 == 7)[0], np.nonzero(q1 == 7)[0]
+    a[np.ix_(r7, c7)] *= np.logspace(0, -9, len(c7))[None, :]
+    ob.enforce_qsparsity(a, [q0, -q1])
+    wu, ws, wv, wq = ob.block_sparse_svd(a, q0, q1)
+    gu, gs, gv, gq = ptb.block_sparse_svd(torch.from_numpy(a).cuda(), q0, q1)
+    assert np.array_equal(gq, wq) and gs.shape == ws.shape
+    assert np.max(np.abs(gs - ws)) < 1e-13 * ws.max()
+    keep = ws > 1e-12 * ws.max()
+    assert np.max(np.abs(gs[keep] - ws[keep]) / ws[keep]) < 1e-9        # small singular values relatively accurate
+    gu, gv = gu.cpu().numpy(), gv.cpu().numpy()
+    assert rel((gu * gs) @ gv, a) < 1e-13
+    nz = gs > 0
+    assert rel(gu[:, nz].conj().T @ gu[:, nz], np.eye(nz.sum())) < 1e-12
+    assert rel(gv[nz] @ gv[nz].conj().T, np.eye(nz.sum())) < 1e-12
+    for s in np.unique(wq):                                             # descending inside every sector
+        ss = gs[wq == s]
+        assert np.all(np.diff(ss) <= 0)
+    # the truncated split used by the sweeps keeps the same indices as the oracle
+    for tol in (0.0, 1e-10, 1e-3):
+        assert np.array_equal(ptb.retained_bond_indices(gs, tol), ob.retained_bond_indices(ws, tol))
