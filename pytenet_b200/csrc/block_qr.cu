@@ -108,7 +108,10 @@ __global__ void __launch_bounds__(QR_THREADS) sector_qr_kernel(const double* __r
                     w.re += p.re; w.im += p.im;
                 }
                 w.re = warp_sum(w.re); w.im = warp_sum(w.im);
-                const Cx top = ld<CPLX>(a, c * m + j);
+                // the row-j element of column c is read and written by lane 0 only (broadcast by shuffle)
+                Cx top = {0.0, 0.0};
+                if (lane == 0) top = ld<CPLX>(a, c * m + j);
+                top.re = __shfl_sync(0xffffffffu, top.re, 0); top.im = __shfl_sync(0xffffffffu, top.im, 0);
                 w.re += top.re; w.im += top.im;                       // v_j = 1
                 const Cx f = cmul(tc, w);
                 if (lane == 0) st<CPLX>(a, c * m + j, Cx{top.re - f.re, top.im - f.im});
@@ -145,7 +148,9 @@ __global__ void __launch_bounds__(QR_THREADS) sector_qr_kernel(const double* __r
                     w.re += p.re; w.im += p.im;
                 }
                 w.re = warp_sum(w.re); w.im = warp_sum(w.im);
-                const Cx top = ld<CPLX>(a, c * m + j);
+                Cx top = {0.0, 0.0};
+                if (lane == 0) top = ld<CPLX>(a, c * m + j);
+                top.re = __shfl_sync(0xffffffffu, top.re, 0); top.im = __shfl_sync(0xffffffffu, top.im, 0);
                 w.re += top.re; w.im += top.im;
                 const Cx f = cmul(t, w);
                 if (lane == 0) st<CPLX>(a, c * m + j, Cx{top.re - f.re, top.im - f.im});
