@@ -22,6 +22,8 @@ ap.add_argument("--L", type=int, default=12)
 ap.add_argument("--D", type=int, default=2048)
 ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--dense", type=int, default=1)
+ap.add_argument("--algo", default="one", choices=["one", "two"])
+ap.add_argument("--tol", type=float, default=1e-8)
 args = ap.parse_args()
 L, D = args.L, args.D
 h = ptb.fermi_hubbard_1d_mpo(L, 1.0, 4.0, 0.0)
@@ -31,7 +33,8 @@ psi0.orthonormalize(mode="left"); psi0.orthonormalize(mode="right")
 big = int(np.argmax(psi0.bond_dims))
 vals, cnt = np.unique(psi0.qbonds[big], return_counts=True)
 dt = 0.02j
-res = {"model": f"Fermi-Hubbard L={L}, sector (N={L}, Sz=0)", "bond_dims": psi0.bond_dims, "k": args.k,
+res = {"model": f"Fermi-Hubbard L={L}, sector (N={L}, Sz=0)", "algo": "tdvp_" + args.algo + "site", "tol_split": args.tol,
+       "bond_dims": psi0.bond_dims, "k": args.k,
        "largest_bond_sectors": int(len(vals)), "largest_bond_sector_sizes_median_max": [float(np.median(cnt)), int(cnt.max())]}
 finals = {}
 for mode in (["auto", "0"] if args.dense else ["auto"]):
@@ -40,8 +43,12 @@ for mode in (["auto", "0"] if args.dense else ["auto"]):
     tag = "sector_path" if mode == "auto" else "dense_path"
     for rep in ("first_step", "later_step"):        # later steps reuse the cached sector plans
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        ptb.tdvp_singlesite(h, psi, dt, 1, numiter_lanczos=args.k)
+        if args.algo == "one":
+            ptb.tdvp_singlesite(h, psi, dt, 1, numiter_lanczos=args.k)
+        else:
+            ptb.tdvp_twosite(h, psi, dt, 1, numiter_lanczos=args.k, tol_split=args.tol)
         torch.cuda.synchronize()
+        res[f"bond_dims_{tag}_{rep}"] = psi.bond_dims
         res[f"seconds_{tag}_{rep}"] = time.perf_counter() - t0
     finals[mode] = psi
 if args.dense:
