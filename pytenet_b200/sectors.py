@@ -50,23 +50,31 @@ def _tile_shape(cplx):
     return bm.value, bn.value, bk.value
 
 
+class KIndex:
+    """First / last position of every value of the contraction index's quantum numbers `qk`, computed once per
+    plan (every work list of a plan looks up the same `qk` dozens of times)."""
+
+    def __init__(self, qk):
+        qk = np.asarray(qk, dtype=np.int64)
+        self.vals, inv = np.unique(qk, return_inverse=True)
+        pos = np.arange(len(qk))
+        self.first = np.full(len(self.vals), _EMPTY_LO, dtype=np.int64)
+        self.last = np.full(len(self.vals), _EMPTY_HI, dtype=np.int64)
+        np.minimum.at(self.first, inv, pos)
+        np.maximum.at(self.last, inv, pos + 1)
+
+
 def _support(need, qk):
     """For every entry of `need` the bounding interval [lo, hi) of positions k with qk[k] == need
-    (empty -> (_EMPTY_LO, _EMPTY_HI))."""
-    qk = np.asarray(qk, dtype=np.int64)
+    (empty -> (_EMPTY_LO, _EMPTY_HI)).  `qk` is an array or a prepared KIndex."""
+    kx = qk if isinstance(qk, KIndex) else KIndex(qk)
     need = np.asarray(need, dtype=np.int64)
-    vals, inv = np.unique(qk, return_inverse=True)
-    pos = np.arange(len(qk))
-    first = np.full(len(vals), _EMPTY_LO, dtype=np.int64)
-    last = np.full(len(vals), _EMPTY_HI, dtype=np.int64)
-    np.minimum.at(first, inv, pos)
-    np.maximum.at(last, inv, pos + 1)
-    if len(vals) == 0:
+    if len(kx.vals) == 0:
         return np.full(len(need), _EMPTY_LO, dtype=np.int64), np.full(len(need), _EMPTY_HI, dtype=np.int64)
-    idx_c = np.clip(np.searchsorted(vals, need), 0, len(vals) - 1)
-    found = vals[idx_c] == need
-    lo = np.where(found, first[idx_c], _EMPTY_LO)
-    hi = np.where(found, last[idx_c], _EMPTY_HI)
+    idx_c = np.clip(np.searchsorted(kx.vals, need), 0, len(kx.vals) - 1)
+    found = kx.vals[idx_c] == need
+    lo = np.where(found, kx.first[idx_c], _EMPTY_LO)
+    hi = np.where(found, kx.last[idx_c], _EMPTY_HI)
     return lo, hi
 
 
@@ -77,17 +85,53 @@ def _tile_reduce(lo, hi, tile):
     return np.minimum.reduceat(lo, starts), np.maximum.reduceat(hi, starts)
 
 
-def tile_k_ranges(need_rows, need_cols, qk, bm, bn, bk):
-    """(tiles_m, tiles_n, 2) int32 array of k-TILE ranges [lo, hi): row m of the output only receives
-    contributions from k with qk[k] == need_rows[m], column n from k with qk[k] == need_cols[n]."""
-    rlo, rhi = _tile_reduce(*_support(need_rows, qk), bm)
-    clo, chi = _tile_reduce(*_support(need_cols, qk), bn)
-    lo = np.maximum(rlo[:, None], clo[None, :])
-    hi = np.minimum(rhi[:, None], chi[None, :])
+def shifted_tile_support(base, shifts, kx, tile):
+    """Per batch entry b the bounding k interval of every block of `tile` consecutive indices whose required
+    quantum number is base[i] + shifts[b]:  (lo, hi) arrays of shape (len(shifts), n_tiles).  Equal shifts are
+    looked up once."""
+    base = np.asarray(base, dtype=np.int64)
+    shifts = np.asarray(shifts, dtype=np.int64).reshape(-1)
+    ush, inv = np.unique(shifts, return_inverse=True)
+    need = base[None, :] + ush[:, None]
+    lo, hi = _support(need.reshape(-1), kx)
+    lo = lo.reshape(need.shape); hi = hi.reshape(need.shape)
+    starts = np.arange(0, need.shape[1], tile)
+    return np.minimum.reduceat(lo, starts, axis=1)[inv], np.maximum.reduceat(hi, starts, axis=1)[inv]
+
+
+def combine_tile_ranges(rlo, rhi, clo, chi, bk):
+    """k-TILE ranges [lo, hi) from row-tile and column-tile supports (broadcast over leading axes):
+    (..., tiles_m) x (..., tiles_n) -> (..., tiles_m, tiles_n, 2) int32."""
+    lo = np.maximum(rlo[..., :, None], clo[..., None, :])
+    hi = np.minimum(rhi[..., :, None], chi[..., None, :])
     empty = hi <= lo
     lo_t = np.where(empty, 0, lo // bk)
     hi_t = np.where(empty, 0, -(-hi // bk))
     return np.stack([lo_t, hi_t], axis=-1).astype(np.int32)
+
+
+def tile_k_ranges_batched(need_rows, need_cols, qk, bm, bn, bk):
+    """Batched form of tile_k_ranges: `need_rows` (B or 1, M) and `need_cols` (B or 1, N) -> (B, tiles_m, tiles_n, 2)
+    int32 k-TILE ranges [lo, hi), one table per batch entry, all looked up in one vectorised pass."""
+    kx = qk if isinstance(qk, KIndex) else KIndex(qk)
+    need_rows = np.atleast_2d(np.asarray(need_rows, dtype=np.int64))
+    need_cols = np.atleast_2d(np.asarray(need_cols, dtype=np.int64))
+
+    def reduced(need, tile):
+        lo, hi = _support(need.reshape(-1), kx)
+        lo = lo.reshape(need.shape); hi = hi.reshape(need.shape)
+        starts = np.arange(0, need.shape[1], tile)
+        return np.minimum.reduceat(lo, starts, axis=1), np.maximum.reduceat(hi, starts, axis=1)
+
+    rlo, rhi = reduced(need_rows, bm)
+    clo, chi = reduced(need_cols, bn)
+    return combine_tile_ranges(rlo, rhi, clo, chi, bk)
+
+
+def tile_k_ranges(need_rows, need_cols, qk, bm, bn, bk):
+    """(tiles_m, tiles_n, 2) int32 array of k-TILE ranges [lo, hi): row m of the output only receives
+    contributions from k with qk[k] == need_rows[m], column n from k with qk[k] == need_cols[n]."""
+    return tile_k_ranges_batched(need_rows, need_cols, qk, bm, bn, bk)[0]
 
 
 def segment_tables(tabs):
@@ -149,20 +193,20 @@ class HeffSectorPlan:
         # step 1, batched over s:  t1[i, s, (K, j')] = sum_j a[i, s, j] r[j, (K, j')]
         #   row i (batch s) needs  qr[j] = ql[i] + qs[s];  column (K, j') needs  qr[j] = qr'[j'] - qwr[K]
         cols1 = (self.qrp[None, :] - self.qwr[:, None]).reshape(-1)
-        self.tab1_host = np.ascontiguousarray(np.stack(
-            [tile_k_ranges(self.ql + self.qs_in[s], cols1, self.qr, bm, bn, bk) for s in range(d)]))
+        kx_r, kx_l = KIndex(self.qr), KIndex(self.ql)
+        r1 = shifted_tile_support(self.ql, self.qs_in, kx_r, bm)                          # (d, tiles_m)
+        c1 = shifted_tile_support(cols1, [0], kx_r, bn)                                   # (1, tiles_n)
+        self.tab1_host = np.ascontiguousarray(combine_tile_ranges(r1[0], r1[1], c1[0], c1[1], bk))
 
         # step 3, one launch per left MPO index k, batched over s':
         #   out[i', s', j'] += sum_i l[i, k, i'] t2[i, k, s', j']
         #   row i' needs  ql[i] = ql'[i'] - qwl[k];  column j' (batch s') needs  ql[i] = qr'[j'] - qs[s'] - qwl[k]
-        self.tab3_host = []
-        self.k_active = []
-        for k in range(cl):
-            tabs = np.ascontiguousarray(np.stack(
-                [tile_k_ranges(self.qlp - self.qwl[k], self.qrp - self.qs_out[sp] - self.qwl[k], self.ql,
-                               bm, bn, bk) for sp in range(dout)]))
-            self.k_active.append(bool(np.any(tabs[..., 1] > tabs[..., 0])))
-            self.tab3_host.append(tabs)
+        r3 = shifted_tile_support(self.qlp, -self.qwl, kx_l, bm)                          # (cl, tiles_m)
+        c3 = shifted_tile_support(self.qrp, -(self.qs_out[None, :] + self.qwl[:, None]), kx_l, bn)   # (cl*dout, tiles_n)
+        all3 = combine_tile_ranges(r3[0][:, None, :], r3[1][:, None, :], c3[0].reshape(cl, dout, -1),
+                                   c3[1].reshape(cl, dout, -1), bk)                         # (cl, dout, tm, tn, 2)
+        self.tab3_host = [np.ascontiguousarray(all3[k]) for k in range(cl)]
+        self.k_active = [bool(np.any(t[..., 1] > t[..., 0])) for t in self.tab3_host]
         self.tab1 = None
         self.tab3 = None
         # step 3 as ONE segmented launch (ptb_gemm_segmented): per output tile the list of (k-tile range, left MPO
@@ -403,21 +447,30 @@ class EnvSectorPlan:
         self.dims = (Dl, d, Dr, cl, cr)
         self.supported = cplx or (Dl % 2 == 0 and Dr % 2 == 0)
         ql_, qr_, qs_, qwl_, qwr_ = self.ql, self.qr, self.qs, self.qwl, self.qwr
+        kxl, kxr = KIndex(ql_), KIndex(qr_)
         # ---- step_left ----
         # (L1) per k, batch s':  t[i,k,s',j'] = sum_i' l[i,k,i'] conj(b[i',s',j'])      K index i' (left bond)
-        self.L1 = [np.ascontiguousarray(np.stack(
-            [tile_k_ranges(ql_ + qwl_[k], qr_ - qs_[sp], ql_, bm, bn, bk) for sp in range(d)])) for k in range(cl)]
+        rl = shifted_tile_support(ql_, qwl_, kxl, bm)                       # rows need ql[i'] = ql[i] + qwl[k]
+        cl_ = shifted_tile_support(qr_, -qs_, kxl, bn)                      # cols need ql[i'] = qr[j'] - qs[s']
+        L1 = combine_tile_ranges(rl[0][:, None, :], rl[1][:, None, :], cl_[0][None, :, :], cl_[1][None, :, :], bk)
+        self.L1 = [np.ascontiguousarray(L1[k]) for k in range(cl)]
         # (L3) per s:  l_next[j,(K,j')] += sum_i a[i,s,j] t2[i,s,K,j']                   K index i
         cols = (qr_[None, :] - qwr_[:, None]).reshape(-1)
-        self.L3 = [tile_k_ranges(qr_ - qs_[s], cols - qs_[s], ql_, bm, bn, bk)[None] for s in range(d)]
+        r3 = shifted_tile_support(qr_, -qs_, kxl, bm)
+        c3 = shifted_tile_support(cols, -qs_, kxl, bn)
+        L3 = combine_tile_ranges(r3[0], r3[1], c3[0], c3[1], bk)            # (d, tiles_m, tiles_n, 2)
+        self.L3 = [np.ascontiguousarray(L3[s][None]) for s in range(d)]
         # ---- step_right ----
         # (R1) batch s:  t1[i,s,(K,j')] = sum_j a[i,s,j] r[j,(K,j')]                      K index j
-        self.R1 = np.ascontiguousarray(np.stack(
-            [tile_k_ranges(ql_ + qs_[s], cols, qr_, bm, bn, bk) for s in range(d)]))
+        r1 = shifted_tile_support(ql_, qs_, kxr, bm)
+        c1 = shifted_tile_support(cols, [0], kxr, bn)
+        self.R1 = np.ascontiguousarray(combine_tile_ranges(r1[0], r1[1], c1[0], c1[1], bk))
         # (R3) per s', batch k:  r_next[i,k,i'] += sum_j' t2[i,k,s',j'] conj(b[i',s',j'])   K index j'
-        self.R3 = [np.ascontiguousarray(np.stack(
-            [tile_k_ranges(ql_ + qwl_[k] + qs_[sp], ql_ + qs_[sp], qr_, bm, bn, bk) for k in range(cl)]))
-            for sp in range(d)]
+        rr = shifted_tile_support(ql_, (qs_[:, None] + qwl_[None, :]), kxr, bm)          # (d*cl, tiles_m)
+        cr_ = shifted_tile_support(ql_, qs_, kxr, bn)                                    # (d, tiles_n)
+        R3 = combine_tile_ranges(rr[0].reshape(d, cl, -1), rr[1].reshape(d, cl, -1), cr_[0][:, None, :],
+                                 cr_[1][:, None, :], bk)                                 # (d, cl, tm, tn, 2)
+        self.R3 = [np.ascontiguousarray(R3[sp]) for sp in range(d)]
         # (L3) as one segmented launch over s (selector s: offsets s*Dr into a, s*cr*Dr into t2); work-sorted
         # schedules for the banded launches
         self.L3_seg = segment_tables(self.L3)
@@ -549,10 +602,11 @@ class BondSectorPlan:
         self.supported = cplx or (Dl % 2 == 0 and Dr % 2 == 0)
         cols = (self.qbr[None, :] - self.qw[:, None]).reshape(-1)
         # (1) t[i,(k,j')] = sum_j c[i,j] r[j,(k,j')]: row i needs qbr[j] = qbl[i]; column (k,j') needs qbr[j] = qbr[j'] - qw[k]
-        self.B1 = tile_k_ranges(self.qbl, cols, self.qbr, bm, bn, bk)[None]
+        kxl, kxr = KIndex(self.qbl), KIndex(self.qbr)
+        self.B1 = tile_k_ranges(self.qbl, cols, kxr, bm, bn, bk)[None]
         # (2) per k: out[i',j'] += sum_i l[i,k,i'] t[i,k,j']: row i' needs qbl[i] = qbl[i'] - qw[k];
         #     column j' needs qbl[i] = qbr[j'] - qw[k]
-        self.B2 = [tile_k_ranges(self.qbl - self.qw[k], self.qbr - self.qw[k], self.qbl, bm, bn, bk)[None]
+        self.B2 = [tile_k_ranges(self.qbl - self.qw[k], self.qbr - self.qw[k], kxl, bm, bn, bk)[None]
                    for k in range(chi)]
         # step 2 as one segmented launch (selector k: offsets k*Dl into l, k*Dr into t), work-sorted schedules
         self.seg_ptr_host, self.segs_host, self.order2_host = segment_tables(self.B2)
