@@ -161,3 +161,32 @@ def test_plan_cache_returns_same_plan(cuda_lib):
     p2 = _sweep._cached_plan(HeffSectorPlan, True, q.copy(), qs, q, qw, qw)
     p3 = _sweep._cached_plan(HeffSectorPlan, False, q, qs, q, qw, qw)
     assert p1 is p2 and p3 is not p1 and p3.cplx is False
+
+
+def test_vectorised_tables_equal_their_definitions(cuda_lib):
+    """The plans build their work lists by shift-deduplicated, batched lookups; every table must equal the
+    one-at-a-time definition through tile_k_ranges."""
+    from pytenet_b200.sectors import EnvSectorPlan, BondSectorPlan
+    rng = np.random.default_rng(1)
+    ql = np.sort(rng.integers(-3, 4, size=300)); qr = np.sort(rng.integers(-3, 4, size=260))
+    qs = np.array([0, 1, -1, 2]); qwl = np.array([0, 1, -1, 0, 2]); qwr = np.array([0, -1, 1])
+    d, cl, cr = len(qs), len(qwl), len(qwr)
+    hp = HeffSectorPlan(ql, qs, qr, qwl, qwr)
+    bm, bn, bk = hp.tile
+    cols = (qr[None, :] - qwr[:, None]).reshape(-1)
+    for s in range(d):
+        assert np.array_equal(hp.tab1_host[s], tile_k_ranges(ql + qs[s], cols, qr, bm, bn, bk))
+    for k in range(cl):
+        for sp in range(d):
+            assert np.array_equal(hp.tab3_host[k][sp], tile_k_ranges(ql - qwl[k], qr - qs[sp] - qwl[k], ql, bm, bn, bk))
+    ep = EnvSectorPlan(ql, qs, qr, qwl, qwr)
+    for k in range(cl):
+        for sp in range(d):
+            assert np.array_equal(ep.L1[k][sp], tile_k_ranges(ql + qwl[k], qr - qs[sp], ql, bm, bn, bk))
+    for s in range(d):
+        assert np.array_equal(ep.L3[s][0], tile_k_ranges(qr - qs[s], cols - qs[s], ql, bm, bn, bk))
+        assert np.array_equal(ep.R1[s], tile_k_ranges(ql + qs[s], cols, qr, bm, bn, bk))
+        for k in range(cl):
+            assert np.array_equal(ep.R3[s][k], tile_k_ranges(ql + qwl[k] + qs[s], ql + qs[s], qr, bm, bn, bk))
+    bp = BondSectorPlan(ql, ql, qwl)
+    assert bp.seg_ptr_host[-1] == sum(int(np.sum(t[..., 1] > t[..., 0])) for t in bp.B2)
