@@ -106,6 +106,9 @@ int apply_local_hamiltonian_impl(const void* a, const void* w, bool w_cplx, cons
     const size_t n1 = (size_t)Dl * d * cr * Drp, n2 = (size_t)Dl * cl * dout * Drp;
     if (ws_bytes < align16(n1 * es) + align16(n2 * es) || !ws) return PTB_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(ws) % 16) return PTB_ERR_ALIGNMENT;
+    // launch-latency regime: the whole contraction in one kernel (csrc/heff_small.cu)
+    if (g_engine == 0 && heff_small_applicable(CPLX, true, w_cplx, Dl, d, Dr, cl, cr, dout, Dlp, Drp))
+        return heff_small_launch(CPLX, a, w, w_cplx, l, r, out, Dl, d, Dr, cl, cr, dout, Dlp, Drp, st);
     char* t1 = static_cast<char*>(ws);
     char* t2 = t1 + align16(n1 * es);
     char* part = t2 + align16(n2 * es);
@@ -160,6 +163,8 @@ int bond_impl(const void* c, const void* l, const void* r, void* out, int64_t Dl
     const size_t n1 = (size_t)Dl * chi * Drp;
     if (ws_bytes < align16(n1 * es) || !ws) return PTB_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(ws) % 16) return PTB_ERR_ALIGNMENT;
+    if (g_engine == 0 && heff_small_applicable(CPLX, false, false, Dl, 1, Dr, chi, chi, 1, Dlp, Drp))
+        return heff_small_launch(CPLX, c, nullptr, false, l, r, out, Dl, 1, Dr, chi, chi, 1, Dlp, Drp, st);
     // (1) t[i,(k,j')] = c[i,j] r[j,(k,j')]                                  chain_ops.py:314
     int rc = gemm<CPLX>(0, 0, 0, Dl, chi * Drp, Dr, c, Dr, r, chi * Drp, ws, chi * Drp, 1, 0, 0, 0, 0, st);
     if (rc) return rc;

@@ -69,4 +69,11 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
+// fused small-D matvec (csrc/heff_small.cu)
+bool heff_small_applicable(bool cplx, bool has_w, bool w_cplx, int64_t Dl, int64_t d, int64_t Dr, int64_t cl,
+                           int64_t cr, int64_t dout, int64_t Dlp, int64_t Drp);
+int heff_small_launch(bool cplx, const void* a, const void* w, bool w_cplx, const void* l, const void* r, void* out,
+                      int64_t Dl, int64_t d, int64_t Dr, int64_t cl, int64_t cr, int64_t dout, int64_t Dlp, int64_t Drp,
+                      cudaStream_t st);
+
 }  // namespace ptb

@@ -74,7 +74,10 @@ int ptb_heff_lanczos(int dtype, const void* x, const void* w, int w_is_complex, 
     char* mws = wvec + nvec;
     const size_t mws_bytes = workspace_bytes - nvec;
     const bool cplx = dtype == PTB_COMPLEX128;
-    const bool csr = w_rowptr && w_col && w_val;
+    // small bond dimensions: the dense-w entry dispatches to the fused one-kernel matvec (csrc/heff_small.cu)
+    const bool small = w != nullptr &&
+                       heff_small_applicable(cplx, true, w_is_complex != 0, Dl, d, Dr, chi_l, chi_r, d, Dl, Dr);
+    const bool csr = !small && w_rowptr && w_col && w_val;
     auto matvec = [&](const void* vin, void* vout) -> int {
         if (csr) {
             return cplx ? ptb_apply_local_hamiltonian_csr_z(vin, w_rowptr, w_col, w_val, w_is_complex, l, r, vout, Dl, d,

@@ -287,3 +287,38 @@ def test_headline_shape_properties(cuda_lib):
     got = ptb.apply_local_hamiltonian(x.cpu().numpy(), w, l.cpu().numpy(), r.cpu().numpy())
     assert isinstance(got, np.ndarray)
     assert rel(got, hx.cpu().numpy()) < 1e-13
+
+
+@pytest.mark.parametrize("cplx,w_cplx", [(True, False), (True, True), (False, False)])
+@pytest.mark.parametrize("dims", [(16, 2, 28, 5, 5, 2, 16, 28), (1, 2, 2, 1, 4, 2, 1, 2), (33, 3, 17, 4, 6, 3, 29, 21),
+                                  (64, 2, 64, 5, 5, 2, 64, 64), (7, 4, 9, 3, 3, 4, 250, 8), (20, 16, 12, 2, 3, 16, 20, 12)])
+def test_fused_small_matvec_kernel(cuda_lib, cplx, w_cplx, dims):
+    """The one-kernel matvec of the launch-latency regime (csrc/heff_small.cu), reached through the dense-w C entry
+    and through the zero-site entry, against the oracle on ragged small shapes (non-square H, d_out up to 16)."""
+    from pytenet_b200 import _lib, _device as dev
+    lib = cuda_lib
+    Dl, d, Dr, cl, cr, dout, Dlp, Drp = dims
+    rng = np.random.default_rng(sum(dims) + int(cplx) + 2 * int(w_cplx))
+    a = rnd(rng, (Dl, d, Dr), cplx); l = rnd(rng, (Dl, cl, Dlp), cplx); r = rnd(rng, (Dr, cr, Drp), cplx)
+    w = rnd(rng, (cl, dout, d, cr), w_cplx)
+    ad, wd, ld, rd = cu(a), cu(w), cu(l), cu(r)
+    out = torch.full((Dlp, dout, Drp), 3.0, dtype=ad.dtype, device="cuda")
+    dt = 1 if cplx else 0
+    nbytes = lib.ptb_apply_local_hamiltonian_workspace_bytes(dt, Dl, d, Dr, cl, cr, dout, Dlp, Drp)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    if cplx:
+        st = lib.ptb_apply_local_hamiltonian_z(ad.data_ptr(), wd.data_ptr(), int(w_cplx), ld.data_ptr(), rd.data_ptr(),
+                                               out.data_ptr(), Dl, d, Dr, cl, cr, dout, Dlp, Drp, ws.data_ptr(), nbytes,
+                                               stream)
+    else:
+        st = lib.ptb_apply_local_hamiltonian_d(ad.data_ptr(), wd.data_ptr(), ld.data_ptr(), rd.data_ptr(),
+                                               out.data_ptr(), Dl, d, Dr, cl, cr, dout, Dlp, Drp, ws.data_ptr(), nbytes,
+                                               stream)
+    assert st == 0
+    assert rel(out.cpu().numpy(), oracle.apply_local_hamiltonian(a, w, l, r)) < TOL
+    # zero-site form: c (Dl, Dr), l (Dl, chi, Dlp), r (Dr, chi, Drp)
+    import pytenet_b200 as ptb
+    c = rnd(rng, (Dl, Dr), cplx); r2 = rnd(rng, (Dr, cl, Drp), cplx)
+    got = ptb.apply_local_bond_contraction(cu(c), ld, cu(r2)).cpu().numpy()
+    assert rel(got, oracle.apply_local_bond_contraction(c, l, r2)) < TOL

@@ -184,7 +184,14 @@ def test_fused_lanczos_run_equals_stepwise(cuda_lib, cplx, dims):
     op = _sweep.HeffOperator(cu(w), cu(l), cu(r), (Dl, d, Dr))
     n1, al1, be1, V1 = krylov._lanczos_core(op, cu(a).reshape(-1), k)
     n2, al2, be2, V2 = krylov._lanczos_core(lambda x: op(x), cu(a).reshape(-1), k)
-    assert n1 == n2 and np.array_equal(al1, al2) and np.array_equal(be1, be2) and torch.equal(V1, V2)
+    if Dl * d * Dr > 20000:
+        # same kernels on both paths: bit-identical
+        assert n1 == n2 and np.array_equal(al1, al2) and np.array_equal(be1, be2) and torch.equal(V1, V2)
+    else:
+        # small bond dimensions: the fused run uses the one-kernel matvec (csrc/heff_small.cu), the step-by-step
+        # path the three-kernel chain -- same numbers up to summation order
+        assert n1 == n2 and np.allclose(al1, al2, rtol=1e-12, atol=1e-12 * np.abs(al2).max())
+        assert np.allclose(be1, be2, rtol=1e-11) and rel(V1.cpu().numpy(), V2.cpu().numpy()) < 1e-10
     oal, obe, oV = oracle.lanczos_iteration(
         lambda x: oracle.apply_local_hamiltonian(x.reshape(Dl, d, Dr), w, l, r).reshape(-1), a.reshape(-1), k)
     assert np.allclose(al1, oal, rtol=1e-9, atol=1e-9 * np.abs(oal).max()) and np.allclose(be1, obe, rtol=1e-8)
@@ -194,7 +201,7 @@ def test_fused_lanczos_run_equals_stepwise(cuda_lib, cplx, dims):
     bop = _sweep.BondOperator(cu(l), cu(r2), (Dl, Dr))
     n1, al1, be1, V1 = krylov._lanczos_core(bop, cu(c).reshape(-1), k)
     n2, al2, be2, V2 = krylov._lanczos_core(lambda x: bop(x), cu(c).reshape(-1), k)
-    assert n1 == n2 and np.array_equal(al1, al2) and np.array_equal(be1, be2) and torch.equal(V1, V2)
+    assert n1 == n2 and np.array_equal(al1, al2) and np.array_equal(be1, be2) and torch.equal(V1, V2)   # same entry point
     oal, obe, oV = oracle.lanczos_iteration(
         lambda x: oracle.apply_local_bond_contraction(x.reshape(Dl, Dr), l, r2).reshape(-1), c.reshape(-1), k)
     assert np.allclose(al1, oal, rtol=1e-9, atol=1e-9 * np.abs(oal).max()) and np.allclose(be1, obe, rtol=1e-8)
