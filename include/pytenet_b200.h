@@ -127,11 +127,14 @@ int ptb_gemm_multicast(int dtype, int trans_a, int trans_b, int conj_b, int64_t 
                        const void* a, int64_t lda, const void* b, int64_t ldb, void* const* c_list, int n_dst,
                        int64_t ldc, void* stream);
 
-/* Engine selection for every GEMM-shaped step (process-wide; for A/B measurements and tests):
+/* ptb_gemm with an explicit kernel generation (for A/B measurements and tests; an argument, so the
+ * library keeps no process-wide mode -- every other entry point selects automatically):
  *   0 = automatic: warp-specialised TMA/mbarrier kernel when operands meet its 16-byte
  *       granularity, else the cp.async kernel;  1 = cp.async kernel only;
  *   2 = warp-specialised kernel required (PTB_ERR_ALIGNMENT if it cannot run). */
-int ptb_set_gemm_engine(int engine);
+int ptb_gemm_engine(int engine, int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k,
+                    const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t batch,
+                    int64_t stride_a, int64_t stride_b, int64_t stride_c, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------
  * apply_local_hamiltonian(a, w, l, r)            pytenet/chain_ops.py:237-279

@@ -135,11 +135,12 @@ def release_workspaces():
 _GEMM_SCRATCH_BYTES = 32 << 20
 
 
-def gemm(a, b, trans_a=False, trans_b=False, conj_b=False, out=None):
+def gemm(a, b, trans_a=False, trans_b=False, conj_b=False, out=None, engine=0):
     """2-D GEMM through the DMMA engine on contiguous device matrices.
 
     op(a) (M x K) @ op(b) (K x N) -> (M x N).  Used for the small GEMM-shaped steps
-    that sit between the hot contractions (merge, gauge absorption).
+    that sit between the hot contractions (merge, gauge absorption).  `engine` != 0 pins the
+    kernel generation (ptb_gemm_engine; measurements only).
     """
     lib = _lib.load()
     cplx = any_complex(a, b)
@@ -155,6 +156,12 @@ def gemm(a, b, trans_a=False, trans_b=False, conj_b=False, out=None):
         return out
     if k == 0:
         return out.zero_()
+    if engine:
+        st = lib.ptb_gemm_engine(int(engine), _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, int(trans_a),
+                                 int(trans_b), int(conj_b), m, n, k, a.data_ptr(), a.shape[1], b.data_ptr(),
+                                 b.shape[1], out.data_ptr(), n, 1, 0, 0, 0, 0, stream_ptr(a.device))
+        _lib.check(st, "ptb_gemm_engine")
+        return out
     # a fixed 32 MB scratch lets the engine split K when the output has few tiles, and split the tiles of
     # the last partial wave of large outputs (both deterministic; see csrc/gemm_ws.cuh)
     ws = workspace(_GEMM_SCRATCH_BYTES, a.device, tag="gemm")

@@ -23,7 +23,8 @@ _DIMS8 = [_i64] * 8
 SIGNATURES = {
     "ptb_version": (_int, []),
     "ptb_status_string": (ctypes.c_char_p, [_int]),
-    "ptb_set_gemm_engine": (_int, [_int]),
+    "ptb_gemm_engine": (_int, [_int, _int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
+                               _i64, _i64, _i64, _i64, _int, _ptr]),
     "ptb_gemm_splitk": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                                _i64, _i64, _i64, _i64, _int, _int, _ptr, _sz, _ptr]),
     "ptb_gemm_banded": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,

@@ -206,22 +206,14 @@ int ptb_block_qr(int dtype, const void* a, int64_t lda, int nsec, const int32_t*
     const size_t ntau = max_block_elems < 1024 ? (size_t)max_block_elems : 1024;
     const size_t smem_need = ((size_t)max_block_elems + ntau) * es;
     if (cplx) {
-        static bool configured = false;
-        if (!configured) {
-            PTB_CUDA_TRY(cudaFuncSetAttribute(sector_qr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              220 * 1024));
-            configured = true;
-        }
+        static DeviceFlags configured;
+        PTB_TRY(ensure_dynamic_smem(configured, sector_qr_kernel<true>, 220 * 1024));
         sector_qr_kernel<true><<<nsec, QR_THREADS, smem_need, st>>>(
             static_cast<const double*>(a), lda, meta, rowidx, colidx, static_cast<double*>(q), ldq,
             static_cast<double*>(r), ldr);
     } else {
-        static bool configured = false;
-        if (!configured) {
-            PTB_CUDA_TRY(cudaFuncSetAttribute(sector_qr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              220 * 1024));
-            configured = true;
-        }
+        static DeviceFlags configured;
+        PTB_TRY(ensure_dynamic_smem(configured, sector_qr_kernel<false>, 220 * 1024));
         sector_qr_kernel<false><<<nsec, QR_THREADS, smem_need, st>>>(
             static_cast<const double*>(a), lda, meta, rowidx, colidx, static_cast<double*>(q), ldq,
             static_cast<double*>(r), ldr);

@@ -198,22 +198,14 @@ int ptb_block_svd(int dtype, const void* a, int64_t lda, int nsec, const int32_t
     // shared memory: G (rows x k) + V (k x k) = max_work_elems elements, then k singular values and k ranks
     const size_t smem_need = (size_t)max_work_elems * es + (size_t)SVD_MAX_K * 12 + 64;
     if (cplx) {
-        static bool configured = false;
-        if (!configured) {
-            PTB_CUDA_TRY(cudaFuncSetAttribute(sector_svd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              220 * 1024));
-            configured = true;
-        }
+        static DeviceFlags configured;
+        PTB_TRY(ensure_dynamic_smem(configured, sector_svd_kernel<true>, 220 * 1024));
         sector_svd_kernel<true><<<nsec, SVD_THREADS, smem_need, st>>>(
             static_cast<const double*>(a), lda, meta, rowidx, colidx, static_cast<double*>(u), ldu, s,
             static_cast<double*>(vh), ldv);
     } else {
-        static bool configured = false;
-        if (!configured) {
-            PTB_CUDA_TRY(cudaFuncSetAttribute(sector_svd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              220 * 1024));
-            configured = true;
-        }
+        static DeviceFlags configured;
+        PTB_TRY(ensure_dynamic_smem(configured, sector_svd_kernel<false>, 220 * 1024));
         sector_svd_kernel<false><<<nsec, SVD_THREADS, smem_need, st>>>(
             static_cast<const double*>(a), lda, meta, rowidx, colidx, static_cast<double*>(u), ldu, s,
             static_cast<double*>(vh), ldv);

@@ -21,8 +21,6 @@ using namespace ptb;
 
 namespace {
 
-int g_engine = 0;
-
 inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
 inline bool bad_dims(std::initializer_list<int64_t> v) {
@@ -41,7 +39,7 @@ inline bool fits_int(std::initializer_list<int64_t> v) {
 template <bool CPLX>
 int gemm(int ta, int tb, int cj, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
          int64_t ldb, void* C, int64_t ldc, int64_t batch, int64_t sA, int64_t sB, int64_t sC, int acc,
-         cudaStream_t st, int split_k = 1, void* part_ws = nullptr, size_t part_ws_bytes = 0) {
+         cudaStream_t st, int split_k = 1, void* part_ws = nullptr, size_t part_ws_bytes = 0, int engine = 0) {
     if (!fits_int({M, N, K, batch})) return PTB_ERR_TOO_LARGE;
     GemmParams p;
     p.A = static_cast<const double*>(A);
@@ -54,12 +52,12 @@ int gemm(int ta, int tb, int cj, int64_t M, int64_t N, int64_t K, const void* A,
     p.accumulate = acc ? 1 : 0;
     p.tiles_m = p.tiles_n = 0;
     if (M == 0 || N == 0 || batch == 0) return PTB_OK;
-    // engine selection: 0 = auto (warp-specialised TMA kernel when it applies), 1 = first-generation
-    // cp.async kernel only, 2 = warp-specialised kernel required
-    if (g_engine != 1 && K > 0) {
+    // engine selection (an argument, never process state): 0 = auto (warp-specialised TMA kernel when it
+    // applies), 1 = first-generation cp.async kernel only, 2 = warp-specialised kernel required
+    if (engine != 1 && K > 0) {
         const int rc = try_launch_ws<CPLX>(ta, tb, cj, p, st, 0, nullptr, split_k, part_ws, part_ws_bytes);
         if (rc != 1) return rc;
-        if (g_engine == 2) return PTB_ERR_ALIGNMENT;
+        if (engine == 2) return PTB_ERR_ALIGNMENT;
     }
     return launch_gemm<CPLX>(ta, tb, cj, p, st);
 }
@@ -83,7 +81,7 @@ int apply_w(bool w_cplx, int trans_w, int64_t rows_out, int64_t rows_in, int64_t
 constexpr int MAX_SPLIT = 8;
 
 constexpr int FIRST_SPLIT = 4;                       // split factor budgeted for the first GEMM
-constexpr int64_t FIRST_SPLIT_MAX_ELEMS = 6 * 148 * 128 * 64;   // only when it has fewer than ~6 waves of tiles
+constexpr int64_t FIRST_SPLIT_MAX_ELEMS = 6 * 148 * 128 * 64;   // workspace budget only: fewer than ~6 waves of tiles on a 148-SM part
 
 size_t two_buffers(int dtype, int64_t n1, int64_t n2, int64_t nout = 0, int64_t nfirst = 0) {
     const size_t es = dtype == PTB_COMPLEX128 ? 16 : 8;
@@ -107,7 +105,7 @@ int apply_local_hamiltonian_impl(const void* a, const void* w, bool w_cplx, cons
     if (ws_bytes < align16(n1 * es) + align16(n2 * es) || !ws) return PTB_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(ws) % 16) return PTB_ERR_ALIGNMENT;
     // launch-latency regime: the whole contraction in one kernel (csrc/heff_small.cu)
-    if (g_engine == 0 && heff_small_applicable(CPLX, true, w_cplx, Dl, d, Dr, cl, cr, dout, Dlp, Drp))
+    if (heff_small_applicable(CPLX, true, w_cplx, Dl, d, Dr, cl, cr, dout, Dlp, Drp))
         return heff_small_launch(CPLX, a, w, w_cplx, l, r, out, Dl, d, Dr, cl, cr, dout, Dlp, Drp, st);
     char* t1 = static_cast<char*>(ws);
     char* t2 = t1 + align16(n1 * es);
@@ -163,7 +161,7 @@ int bond_impl(const void* c, const void* l, const void* r, void* out, int64_t Dl
     const size_t n1 = (size_t)Dl * chi * Drp;
     if (ws_bytes < align16(n1 * es) || !ws) return PTB_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(ws) % 16) return PTB_ERR_ALIGNMENT;
-    if (g_engine == 0 && heff_small_applicable(CPLX, false, false, Dl, 1, Dr, chi, chi, 1, Dlp, Drp))
+    if (heff_small_applicable(CPLX, false, false, Dl, 1, Dr, chi, chi, 1, Dlp, Drp))
         return heff_small_launch(CPLX, c, nullptr, false, l, r, out, Dl, 1, Dr, chi, chi, 1, Dlp, Drp, st);
     // (1) t[i,(k,j')] = c[i,j] r[j,(k,j')]                                  chain_ops.py:314
     int rc = gemm<CPLX>(0, 0, 0, Dl, chi * Drp, Dr, c, Dr, r, chi * Drp, ws, chi * Drp, 1, 0, 0, 0, 0, st);
@@ -232,11 +230,6 @@ extern "C" {
 
 int ptb_version(void) { return 101; }
 
-int ptb_set_gemm_engine(int engine) {
-    if (engine < 0 || engine > 2) return PTB_ERR_BAD_ARG;
-    g_engine = engine;
-    return PTB_OK;
-}
 
 const char* ptb_status_string(int status) {
     switch (status) {
@@ -265,6 +258,21 @@ int ptb_gemm(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t
     if (dtype == PTB_REAL64)
         return gemm<false>(trans_a, trans_b, 0, m, n, k, a, lda, b, ldb, c, ldc, batch, stride_a, stride_b,
                            stride_c, accumulate, st);
+    return PTB_ERR_BAD_DTYPE;
+}
+
+int ptb_gemm_engine(int engine, int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k,
+                    const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t batch,
+                    int64_t stride_a, int64_t stride_b, int64_t stride_c, int accumulate, void* stream) {
+    if (!a || !b || !c) return PTB_ERR_BAD_ARG;
+    if (engine < 0 || engine > 2 || m < 0 || n < 0 || k < 0 || batch < 0) return PTB_ERR_BAD_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == PTB_COMPLEX128)
+        return gemm<true>(trans_a, trans_b, conj_b, m, n, k, a, lda, b, ldb, c, ldc, batch, stride_a, stride_b,
+                          stride_c, accumulate, st, 1, nullptr, 0, engine);
+    if (dtype == PTB_REAL64)
+        return gemm<false>(trans_a, trans_b, 0, m, n, k, a, lda, b, ldb, c, ldc, batch, stride_a, stride_b,
+                           stride_c, accumulate, st, 1, nullptr, 0, engine);
     return PTB_ERR_BAD_DTYPE;
 }
 

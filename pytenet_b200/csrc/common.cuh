@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <initializer_list>
 #include "../../include/pytenet_b200.h"
 
@@ -19,6 +20,53 @@ static inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? PTB_OK 
     do {                                                \
         cudaError_t _e = (expr);                        \
         if (_e != cudaSuccess) return (int)_e;          \
+    } while (0)
+
+// ---- per-device launch configuration ------------------------------------------------
+// Function attributes (opt-in dynamic shared memory) and the SM count belong to a device, not to the
+// process: a host that drives several GPUs from one process (or several threads) must get them per
+// device.  `DeviceFlags` is one flag per device ordinal, set after the attribute call succeeded; a
+// race between two threads only repeats an idempotent cudaFuncSetAttribute.
+constexpr int PTB_MAX_DEVICES = 64;
+
+struct DeviceFlags {
+    std::atomic<unsigned char> done[PTB_MAX_DEVICES];
+};
+
+static inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev;
+}
+
+// number of SMs of the current device (cached per device ordinal)
+static inline int device_sm_count() {
+    static std::atomic<int> sms[PTB_MAX_DEVICES];
+    const int dev = current_device();
+    const int slot = dev < PTB_MAX_DEVICES ? dev : PTB_MAX_DEVICES - 1;
+    int n = dev < PTB_MAX_DEVICES ? sms[slot].load(std::memory_order_relaxed) : 0;
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        if (dev < PTB_MAX_DEVICES) sms[slot].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
+// opt a kernel into `bytes` of dynamic shared memory on the current device (once per device)
+template <class Kernel>
+static inline int ensure_dynamic_smem(DeviceFlags& flags, Kernel kern, int bytes) {
+    const int dev = current_device();
+    if (dev < PTB_MAX_DEVICES && flags.done[dev].load(std::memory_order_acquire)) return PTB_OK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < PTB_MAX_DEVICES) flags.done[dev].store(1, std::memory_order_release);
+    return PTB_OK;
+}
+
+#define PTB_TRY(expr)                                   \
+    do {                                                \
+        int _s = (expr);                                \
+        if (_s != PTB_OK) return _s;                    \
     } while (0)
 
 // ---- async copy (LDGSTS) with zero fill -----------------------------------------

@@ -271,11 +271,8 @@ template <bool CPLX, bool A_KC, bool B_KC, bool CONJB, int VEC_D>
 static int launch_gemm_inst(const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<CPLX>;
     auto kern = gemm_dmma_kernel<CPLX, A_KC, B_KC, CONJB, VEC_D>;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        PTB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    static DeviceFlags configured;  // per instantiation and device
+    PTB_TRY(ensure_dynamic_smem(configured, kern, Cfg::SMEM_BYTES));
     GemmParams q = p;
     int done = 0;
     while (done < p.batch) {  // gridDim.y limit

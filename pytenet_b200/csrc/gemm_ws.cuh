@@ -577,15 +577,9 @@ template <bool CPLX, bool A_KC, bool B_KC, bool CONJB, bool SEG = false>
 static int launch_ws_inst(const WsParams& p, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
     using Cfg = WsCfg<CPLX>;
     auto kern = gemm_ws_kernel<CPLX, A_KC, B_KC, CONJB, SEG>;
-    static bool configured = false;
-    static int num_sms = 0;
-    if (!configured) {
-        PTB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        int devid = 0;
-        PTB_CUDA_TRY(cudaGetDevice(&devid));
-        PTB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid));
-        configured = true;
-    }
+    static DeviceFlags configured;  // per instantiation and device
+    PTB_TRY(ensure_dynamic_smem(configured, kern, Cfg::SMEM_BYTES));
+    const int num_sms = device_sm_count();
     const long long total_tiles = (long long)p.tiles_m * p.tiles_n * p.batch;
     const long long total = p.split_k > 1 ? total_tiles * p.split_k
                           : (p.tail_split > 1 ? p.tail_begin + (total_tiles - p.tail_begin) * p.tail_split
@@ -601,7 +595,7 @@ static int launch_ws_inst(const WsParams& p, const CUtensorMap& ta, const CUtens
         const int ND = p.N * Cfg::E;
         const int64_t per = (int64_t)p.M * ND;
         int gx = (int)((per + 255) / 256);
-        if (gx > 148 * 8) gx = 148 * 8;
+        if (gx > num_sms * 8) gx = num_sms * 8;
         if (gx < 1) gx = 1;
         splitk_reduce_kernel<<<dim3(gx, p.batch), 256, 0, stream>>>(p.Cpart, p.C, p.M, ND, p.ldc * Cfg::E,
                                                                      p.sC * Cfg::E, p.split_k, p.accumulate);
@@ -615,9 +609,10 @@ static int launch_ws_inst(const WsParams& p, const CUtensorMap& ta, const CUtens
 // per output element of a complex GEMM at HBM speed).  Per output element the time saved is
 // (8 K / peak) (1/eff(1) - 1/eff(S)); S is chosen to maximise the net gain and only accepted when
 // the saving is at least twice the extra traffic.  At least 4 k-tiles (one pipeline depth) per unit.
-static int choose_split_k(long long tiles, int KT, int K, int num_sms = 148) {
+static int choose_split_k(long long tiles, int KT, int K, int num_sms) {
     if (tiles >= 6LL * num_sms) return 1;
-    const double flop_time = 8.0 * (double)K / 37.0e12;   // seconds per output element at the FP64 peak
+    // seconds per output element at the FP64 tensor peak: 128 flop / clk / SM (DMMA), ~1.96 GHz boost
+    const double flop_time = 8.0 * (double)K / (128.0 * 1.96e9 * num_sms);
     const double byte_time = 32.0 / 6.0e12;               // write + read of one complex partial element
     auto eff = [&](int sk) {
         const long long units = tiles * sk;
@@ -676,7 +671,8 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     if (ktab != nullptr && (reinterpret_cast<uintptr_t>(ktab) % 8) != 0) return PTB_ERR_ALIGNMENT;
     if (split_k != 1 && n_extra == 0 && part_ws != nullptr && ktab == nullptr) {
         const int KT = (gp.K + Cfg::BK - 1) / Cfg::BK;
-        int sk = split_k > 1 ? split_k : choose_split_k((long long)p.tiles_m * p.tiles_n * p.batch, KT, gp.K);
+        const int num_sms = device_sm_count();
+        int sk = split_k > 1 ? split_k : choose_split_k((long long)p.tiles_m * p.tiles_n * p.batch, KT, gp.K, num_sms);
         if (sk > KT) sk = KT;
         const size_t need = (size_t)p.batch * sk * p.M * p.N * E * 8;
         if (sk > 1 && need <= part_ws_bytes && al16(part_ws)) {
@@ -685,9 +681,6 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
         }
         // no global split: split only the tiles of the last, partially filled wave
         if (p.split_k == 1 && split_k == 0 && al16(part_ws)) {
-            int num_sms = 148;
-            int devid = 0;
-            if (cudaGetDevice(&devid) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid);
             const long long total_tiles = (long long)p.tiles_m * p.tiles_n * p.batch;
             const long long tail = total_tiles % num_sms;
             if (total_tiles > num_sms && tail > 0 && tail <= num_sms / 2) {

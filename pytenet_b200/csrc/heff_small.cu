@@ -185,11 +185,8 @@ int heff_small_launch(bool cplx, const void* a, const void* w, bool w_cplx, cons
                       cudaStream_t st) {
     const size_t smem = heff_small_smem(cplx, w != nullptr, w_cplx, Dl, d, Dr, cl, cr, dout, Dlp);
     auto launch = [&](auto kern, int slot) -> int {
-        static bool configured[4] = {false, false, false, false};
-        if (!configured[slot]) {
-            PTB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            configured[slot] = true;
-        }
+        static DeviceFlags configured[4];
+        PTB_TRY(ensure_dynamic_smem(configured[slot], kern, 160 * 1024));
         kern<<<(unsigned)Drp, HS_THREADS, smem, st>>>(static_cast<const double*>(a), static_cast<const double*>(w),
                                                       static_cast<const double*>(l), static_cast<const double*>(r),
                                                       static_cast<double*>(out), (int)Dl, (int)d, (int)Dr, (int)cl,

@@ -21,7 +21,7 @@ def rnd(rng, shape, cplx):
     return x
 
 
-def run_gemm(lib, cplx, ta, tb, cj, M, N, K, rng, batch=1, accumulate=False, pad=(0, 0, 0)):
+def run_gemm(lib, cplx, ta, tb, cj, M, N, K, rng, batch=1, accumulate=False, pad=(0, 0, 0), engine=0):
     from pytenet_b200 import _lib
     lda = (M if ta else K) + pad[0]
     ldb = (K if tb else N) + pad[1]
@@ -30,10 +30,10 @@ def run_gemm(lib, cplx, ta, tb, cj, M, N, K, rng, batch=1, accumulate=False, pad
     B = rnd(rng, (batch, N if tb else K, ldb), cplx)
     C0 = rnd(rng, (batch, M, ldc), cplx)
     dA, dB, dC = (torch.from_numpy(x).cuda() for x in (A, B, C0))
-    st = lib.ptb_gemm(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, ta, tb, cj, M, N, K,
-                      dA.data_ptr(), lda, dB.data_ptr(), ldb, dC.data_ptr(), ldc, batch,
-                      A.shape[1] * lda, B.shape[1] * ldb, M * ldc, int(accumulate),
-                      torch.cuda.current_stream().cuda_stream)
+    st = lib.ptb_gemm_engine(engine, _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, ta, tb, cj, M, N, K,
+                             dA.data_ptr(), lda, dB.data_ptr(), ldb, dC.data_ptr(), ldc, batch,
+                             A.shape[1] * lda, B.shape[1] * ldb, M * ldc, int(accumulate),
+                             torch.cuda.current_stream().cuda_stream)
     assert st == 0, lib.ptb_status_string(st)
     torch.cuda.synchronize()
     got = dC.cpu().numpy()
@@ -51,10 +51,9 @@ def run_gemm(lib, cplx, ta, tb, cj, M, N, K, rng, batch=1, accumulate=False, pad
 
 @pytest.fixture(params=[0, 1, 2], ids=["engine-auto", "engine-cpasync", "engine-tma"])
 def engine(request, cuda_lib):
-    """Run every GEMM case on both kernel generations (2 = warp-specialised TMA kernel required)."""
-    assert cuda_lib.ptb_set_gemm_engine(request.param) == 0
-    yield request.param
-    cuda_lib.ptb_set_gemm_engine(0)
+    """Run every GEMM case on both kernel generations (2 = warp-specialised TMA kernel required); the engine is an
+    argument of ptb_gemm_engine -- the library holds no process-wide mode."""
+    return request.param
 
 
 SHAPES = [(1, 1, 1), (3, 5, 7), (8, 8, 4), (17, 9, 33), (128, 64, 8), (129, 65, 9), (130, 200, 77),
@@ -70,7 +69,7 @@ def test_gemm_layouts_and_ragged_shapes(cuda_lib, engine, cplx, ta, tb):
     rng = np.random.default_rng(100 + 4 * cplx + 2 * ta + tb)
     for (M, N, K) in SHAPES:
         for cj in ([0, 1] if cplx else [0]):
-            e = run_gemm(cuda_lib, cplx, ta, tb, cj, M, N, K, rng)
+            e = run_gemm(cuda_lib, cplx, ta, tb, cj, M, N, K, rng, engine=engine)
             assert e < TOL, (cplx, ta, tb, cj, M, N, K, e)
 
 
@@ -81,15 +80,15 @@ def test_gemm_batched_accumulate_and_leading_dims(cuda_lib, engine, cplx):
     pads = [(0, 0, 0), (1, 3, 5), (2, 2, 2)] if (cplx or engine != 2) else []
     for pad in pads:
         for (ta, tb) in [(0, 0), (1, 0), (0, 1), (1, 1)]:
-            e = run_gemm(cuda_lib, cplx, ta, tb, 0, 37, 45, 29, rng, batch=5, accumulate=True, pad=pad)
+            e = run_gemm(cuda_lib, cplx, ta, tb, 0, 37, 45, 29, rng, batch=5, accumulate=True, pad=pad, engine=engine)
             assert e < TOL, (cplx, pad, ta, tb, e)
-    e = run_gemm(cuda_lib, cplx, 0, 0, 0, 10, 130, 10, rng, batch=300)
+    e = run_gemm(cuda_lib, cplx, 0, 0, 0, 10, 130, 10, rng, batch=300, engine=engine)
     assert e < TOL
     # float64 with even extents is eligible for the TMA kernel in every layout
     for (ta, tb) in [(0, 0), (1, 0), (0, 1), (1, 1)]:
-        e = run_gemm(cuda_lib, cplx, ta, tb, 0, 70, 36, 50, rng, batch=3, accumulate=True, pad=(2, 4, 6))
+        e = run_gemm(cuda_lib, cplx, ta, tb, 0, 70, 36, 50, rng, batch=3, accumulate=True, pad=(2, 4, 6), engine=engine)
         assert e < TOL, (cplx, ta, tb, e)
-        e = run_gemm(cuda_lib, cplx, ta, tb, 0, 200, 300, 40, rng)
+        e = run_gemm(cuda_lib, cplx, ta, tb, 0, 200, 300, 40, rng, engine=engine)
         assert e < TOL, (cplx, ta, tb, e)
 
 
@@ -107,11 +106,13 @@ def test_gemm_exact_zeros_preserved(cuda_lib):
 
 def test_gemm_large_against_torch(cuda_lib, engine):
     """Full-size sanity (size-independent check): 2048 x 1280 x 1024 complex, T/N layout, vs torch fp64."""
-    from pytenet_b200 import _device as dev
     g = torch.Generator(device="cuda").manual_seed(1)
     a = torch.randn(1024, 2048, dtype=torch.complex128, device="cuda", generator=g)
     b = torch.randn(1024, 1280, dtype=torch.complex128, device="cuda", generator=g)
-    c = dev.gemm(a, b, trans_a=True)
+    c = torch.empty(2048, 1280, dtype=torch.complex128, device="cuda")
+    st = cuda_lib.ptb_gemm_engine(engine, 1, 1, 0, 0, 2048, 1280, 1024, a.data_ptr(), 2048, b.data_ptr(), 1280,
+                                  c.data_ptr(), 1280, 1, 0, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
+    assert st == 0
     ref = a.T @ b
     assert (torch.linalg.norm(c - ref) / torch.linalg.norm(ref)).item() < TOL
 

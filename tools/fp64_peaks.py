@@ -68,15 +68,14 @@ def main():
     # this repository's engines on the matvec shapes (D, d, chi): 1 = cp.async kernel, 2 = TMA kernel
     shapes = []
     for eng, (D, d, chi) in [(e, s) for e in (1, 2) for s in [(1024, 4, 5), (2048, 2, 5), (2048, 4, 5)]]:
-        assert lib.ptb_set_gemm_engine(eng) == 0
         a = torch.randn(D * d, D, dtype=torch.complex128, device="cuda")
         r = torch.randn(D, chi * D, dtype=torch.complex128, device="cuda")
         t1 = torch.empty(D * d, chi * D, dtype=torch.complex128, device="cuda")
-        ms1 = time_ms(lambda: dev.gemm(a, r, out=t1), warm=1, reps=3)
+        ms1 = time_ms(lambda: dev.gemm(a, r, out=t1, engine=eng), warm=1, reps=3)
         l = torch.randn(D * chi, D, dtype=torch.complex128, device="cuda")
         t2 = torch.randn(D * chi, d * D, dtype=torch.complex128, device="cuda")
         o = torch.empty(D, d * D, dtype=torch.complex128, device="cuda")
-        ms3 = time_ms(lambda: dev.gemm(l, t2, trans_a=True, out=o), warm=1, reps=3)
+        ms3 = time_ms(lambda: dev.gemm(l, t2, trans_a=True, out=o, engine=eng), warm=1, reps=3)
         f = 8.0 * D * d * D * chi * D
         cub1 = time_ms(lambda: torch.matmul(a, r, out=t1), warm=1, reps=3)
         cub3 = time_ms(lambda: torch.matmul(l.T, t2, out=o), warm=1, reps=3)
@@ -86,14 +85,12 @@ def main():
         del a, r, t1, l, t2, o
     res["engine"] = shapes
     for eng in (1, 2):
-        lib.ptb_set_gemm_engine(eng)
         n = 8192
         a = torch.randn(n, n, dtype=torch.float64, device="cuda"); b = torch.randn(n, n, dtype=torch.float64, device="cuda")
         c = torch.empty(n, n, dtype=torch.float64, device="cuda")
-        ms = time_ms(lambda: dev.gemm(a, b, out=c), warm=1, reps=3)
+        ms = time_ms(lambda: dev.gemm(a, b, out=c, engine=eng), warm=1, reps=3)
         res[f"engine{eng}_dgemm_8192_tflops"] = 2 * n ** 3 / ms / 1e9
         del a, b, c
-    lib.ptb_set_gemm_engine(0)
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device="cuda"); b = torch.randn(n, n, dtype=torch.float64, device="cuda")
     c = torch.empty(n, n, dtype=torch.float64, device="cuda")
