@@ -25,6 +25,7 @@ _SVD_DRIVER = os.environ.get("PYTENET_B200_SVD_DRIVER", "gesvd")
 # batched per-sector QR kernel (csrc/block_qr.cu) for sector blocks that fit in shared memory; "0" = cuSOLVER only
 _BATCHED_QR = os.environ.get("PYTENET_B200_BATCHED_QR", "1") != "0"
 # batched per-sector one-sided Jacobi SVD kernel (csrc/block_svd.cu) for small sector blocks; "0" = cuSOLVER only
+_RANK_EPS = 4 * np.finfo(float).eps       # sigma_min <= _RANK_EPS * max(m, n) * sigma_max: numerically rank deficient
 _BATCHED_SVD = os.environ.get("PYTENET_B200_BATCHED_SVD", "1") != "0"
 
 
@@ -321,4 +322,26 @@ def block_sparse_svd(a, q0, q1):
             u[rt, p0:p0 + sz] = us
             v[p0:p0 + sz, ct] = vs
             s_dev[p0:p0 + sz] = ss
-    return u, s_dev.cpu().numpy(), v, plan.qinterm.copy()
+    s_host = s_dev.cpu().numpy()
+    if small:
+        # A numerically rank-deficient block leaves the Jacobi kernel with column norms that are exactly zero (a
+        # structurally zero column: zero singular vector) or pure rounding noise (vectors not reliably
+        # orthogonal), where LAPACK -- the reference, block_sparse_util.py:294 -- returns noise of order
+        # eps * sigma_max together with a completed orthonormal basis; `retained_bond_indices` (cumsum > tol)
+        # keeps such an index at tol = 0.  Those (rare) blocks are refactorised by cuSOLVER so that the retained
+        # indices and the isometry of u / v equal the reference's.  An all-zero block has sigma == 0 in LAPACK
+        # too and stays.
+        dix = None
+        for i in small:
+            p0, sz = plan.starts[i], plan.sizes[i]
+            blk = s_host[p0:p0 + sz]
+            if sz > 0 and blk[0] > 0 and blk[-1] <= _RANK_EPS * max(len(plan.rows[i]), len(plan.cols[i])) * blk[0]:
+                if dix is None:
+                    dix = plan.all_indices()
+                rt, ct = dix[i], dix[len(plan.sectors) + i]
+                us, ss, vs = torch.linalg.svd(a.index_select(0, rt).index_select(1, ct), full_matrices=False,
+                                              driver=_SVD_DRIVER)
+                u[rt, p0:p0 + sz] = us
+                v[p0:p0 + sz, ct] = vs
+                s_host[p0:p0 + sz] = ss.cpu().numpy()
+    return u, s_host, v, plan.qinterm.copy()

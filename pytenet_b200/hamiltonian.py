@@ -16,7 +16,7 @@ import numpy as np
 from .mpo import MPO
 from .scalars import encode_quantum_number_pair
 
-__all__ = ["heisenberg_xxz_1d_mpo", "ising_1d_mpo", "fermi_hubbard_1d_mpo"]
+__all__ = ["heisenberg_xxz_1d_mpo", "ising_1d_mpo", "fermi_hubbard_1d_mpo", "load_cached_mpo"]
 
 
 def _chain_tensors(qbond, wbulk, nsites, first_row, last_col):
@@ -133,3 +133,29 @@ def fermi_hubbard_1d_mpo(nsites: int, t: float, u: float, mu: float, device=None
     """
     qsite, qb, w, first, last = _fermi_hubbard_bulk(t, u, mu)
     return _chain_mpo(qsite, qb, w, nsites, first, last, device)
+
+
+def cached_mpo_tensors(path):
+    """Host side of `load_cached_mpo`: (qsite, qbonds, dense NumPy tensors) rebuilt from the sparse cache file."""
+    z = np.load(path)
+    nsites = len([k for k in z.files if k.endswith("_shape")])
+    tensors = []
+    for i in range(nsites):
+        shape = tuple(int(x) for x in z[f"w{i}_shape"])
+        flat = np.zeros(int(np.prod(shape)), dtype=z[f"w{i}_val"].dtype)
+        flat[z[f"w{i}_idx"].astype(np.int64)] = z[f"w{i}_val"]
+        tensors.append(flat.reshape(shape))
+    qbonds = [z[f"qb{i}"] for i in range(nsites + 1)]
+    return z["qsite"], qbonds, tensors
+
+
+def load_cached_mpo(path, device=None):
+    """
+    MPO from a sparse cache file written by `tests/golden/make_molecular_mpo.py` (per site: tensor shape, flat
+    indices and values of the non-zero entries; plus `qsite` and the bond quantum numbers).  This is how
+    BASELINE config 4 -- `molecular_hamiltonian_mpo(tkin, vint, optimize=False)` on 32 orbitals
+    (pytenet/hamiltonian/molecular.py:612), a nine-minute symbolic host construction in the reference -- reaches
+    a GPU box without a reference checkout: the tensors are the reference's own, bit for bit.
+    """
+    qsite, qbonds, tensors = cached_mpo_tensors(path)
+    return MPO.from_tensors(qsite, qbonds, tensors, device=device)
