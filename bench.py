@@ -154,65 +154,93 @@ def use_all_host_threads():
         pass
 
 
-def cpu_time_matvec(D, d, chi, reps=1):
-    import oracle
+def reference_chain_ops():
+    """(module, kind): the reference's own `chain_ops` when an install of it travels with the repo
+    (`baseline/_ref`, written by `pip install --no-deps --target baseline/_ref /root/reference`, or a checkout on
+    PYTHONPATH), else the oracle restatement.  pytenet 1.3.0's packaging lists `packages = ["pytenet"]` only, so
+    the installed tree lacks the `pytenet.hamiltonian` sub-package and `import pytenet` fails in its __init__;
+    the hot-path module is therefore loaded from the unmodified installed file under a stub parent package."""
+    import importlib
+    import types
+    for base in (os.path.join(ROOT, "baseline", "_ref"),):
+        pkg = os.path.join(base, "pytenet")
+        if os.path.exists(os.path.join(pkg, "chain_ops.py")):
+            try:
+                if "pytenet" not in sys.modules:
+                    stub = types.ModuleType("pytenet")
+                    stub.__path__ = [pkg]
+                    sys.modules["pytenet"] = stub
+                return importlib.import_module("pytenet.chain_ops"), "reference"
+            except Exception:
+                sys.modules.pop("pytenet", None)
+    try:
+        import pytenet.chain_ops as co           # a full checkout on PYTHONPATH
+        return co, "reference"
+    except Exception:
+        import oracle
+        return oracle, "port"
+
+
+def cpu_time_matvec(D, d, chi, reps=1, impl=None):
+    impl = impl or reference_chain_ops()[0]
     use_all_host_threads()
     a, w, l, r = host_inputs(D, d, chi, seed=1)
     best = float("inf")
     for _ in range(reps):
         t0 = time.perf_counter()
-        oracle.apply_local_hamiltonian(a, w, l, r)
+        impl.apply_local_hamiltonian(a, w, l, r)
         best = min(best, time.perf_counter() - t0)
     return best
 
 
-def pick_cpu_sample(budget_s):
-    """Largest D in {2048, 1024, 512} whose predicted matvec time fits the budget (D^3 scaling
-    from a D=512 probe)."""
-    t512 = cpu_time_matvec(512, d_HEAD, CHI, reps=2)
-    for D in (2048, 1024):
-        if t512 * (D / 512) ** 3 <= budget_s:
-            return D, t512
-    return 512, t512
-
-
-def cpu_baseline_block(budget_s=25.0):
-    D, t512 = pick_cpu_sample(budget_s)
-    t = t512 if D == 512 else cpu_time_matvec(D, d_HEAD, CHI, reps=1)
+def cpu_baseline_block():
+    """The reference's CPU path on the SAME workload as the GPU arm (D = 2048, always): one matvec, 2.5-6 s."""
+    impl, kind = reference_chain_ops()
+    cpu_time_matvec(256, d_HEAD, CHI, impl=impl)          # BLAS pool warm-up
+    t = cpu_time_matvec(D_HEAD, d_HEAD, CHI, reps=1, impl=impl)
+    src = ("pytenet 1.3.0 chain_ops.apply_local_hamiltonian from baseline/_ref" if kind == "reference"
+           else "oracle/ NumPy restatement of pytenet/chain_ops.py:237-279")
     return {
-        "value": f_alg(D, d_HEAD, CHI) / t / 1e9, "unit": "GFLOP/s", "cores": cpu_threads(), "kind": "port",
-        "sample": f"1 matvec of the same operator at D={D}, d={d_HEAD}, chi={CHI} (oracle/ NumPy+OpenBLAS "
-                  f"restatement of pytenet/chain_ops.py:237-279, {t:.2f} s)",
+        "value": f_alg(D_HEAD, d_HEAD, CHI) / t / 1e9, "unit": "GFLOP/s", "cores": cpu_threads(), "kind": kind,
+        "sample": f"1 matvec of the bench workload itself: D={D_HEAD}, d={d_HEAD}, chi={CHI} ({src}, NumPy + "
+                  f"OpenBLAS on all host threads, {t:.2f} s)",
         "seconds": t,
     }
 
 
 def run_reference(args):
-    """--impl reference: K timed steps of the CPU path on a bounded sample (rank 0 only)."""
+    """--impl reference: K timed steps of the reference's CPU path on the bench workload (D = 2048; rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
+    impl, kind = reference_chain_ops()
     use_all_host_threads()
     steps, warm = args.steps, args.warmup
-    D, t512 = pick_cpu_sample(150.0 / max(1, steps + warm))
+    D = D_HEAD
     a, w, l, r = host_inputs(D, d_HEAD, CHI, seed=1)
-    for _ in range(warm):
-        oracle.apply_local_hamiltonian(a, w, l, r)
+    t0 = time.perf_counter()
+    impl.apply_local_hamiltonian(a, w, l, r)
+    t_first = time.perf_counter() - t0
+    # keep the whole run within a few minutes on a slow host: the untimed warm-up shrinks first, never the workload
+    warm_done = 1
+    while warm_done < warm and t_first * (steps + warm_done + 1) < 240.0:
+        impl.apply_local_hamiltonian(a, w, l, r)
+        warm_done += 1
     t0 = time.perf_counter()
     for _ in range(steps):
-        oracle.apply_local_hamiltonian(a, w, l, r)
+        impl.apply_local_hamiltonian(a, w, l, r)
     dt = (time.perf_counter() - t0) / steps
     val = f_alg(D, d_HEAD, CHI) / dt / 1e9
-    sample = (f"each step = 1 matvec at D={D}, d={d_HEAD}, chi={CHI} (bounded sample of the D=2048 workload; "
-              f"GFLOP/s is size-comparable, F_alg/time)")
+    sample = (f"each step = 1 matvec of the bench workload itself (D={D}, d={d_HEAD}, chi={CHI}); "
+              f"{warm_done} of {warm} warm-up steps run")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_D": D, "d": d_HEAD, "chi": CHI,
-                   "note": "reference is pure NumPy (no GPU path); timed on the host cores"},
-        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "a": [D, d_HEAD, D], "w": [CHI, d_HEAD, d_HEAD, CHI], "l": [D, CHI, D],
+                   "r": [D, CHI, D], "flops_per_step": f_alg(D, d_HEAD, CHI),
+                   "note": "reference is pure NumPy (no GPU path); timed on the host cores, all BLAS threads"},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cpu_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -273,19 +301,84 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def sharded_block(torch, dist, device, world, rank, D=1024, d=2, cl=562, cr=501, reps=3):
-    """One effective-H matvec at the centre-site shape of the 32-orbital molecular MPO
-    (w (562,2,2,501) real, 16.8 % dense; a (1024,2,1024)), MPO bond split over all ranks:
-    fixed total work, so ms_per_matvec across N = 1, 2, 4, 8 is the strong-scaling curve."""
-    from pytenet_b200.sharded import ShardedEffectiveHamiltonian, PrecontractedShardedHamiltonian
+def sharded_parity(torch, dist, device, world):
+    """Correctness of the sharded operator on THIS run's ranks (what the timed kernels compute is checked where it
+    is timed): a small same-seeded problem on every rank -- sharded matvec vs the unsharded device matvec, and the
+    lowest Ritz value of a 12-step Lanczos run on the sharded vs the unsharded operator.  Max over ranks."""
+    import pytenet_b200 as ptb
+    from pytenet_b200.sharded import PrecontractedShardedHamiltonian, ShardedEffectiveHamiltonian
+    g = torch.Generator(device=device).manual_seed(5)
+    Dl, d, Dr, cl, cr = 96, 2, 80, 37, 29
+    a = torch.randn(Dl, d, Dr, dtype=torch.complex128, device=device, generator=g)
+    l = torch.randn(Dl, cl, Dl, dtype=torch.complex128, device=device, generator=g)
+    r = torch.randn(Dr, cr, Dr, dtype=torch.complex128, device=device, generator=g)
+    w = torch.randn(cl, d, d, cr, dtype=torch.float64, device=device, generator=g)
+    w = w * (torch.rand(cl, d, d, cr, device=device, generator=g) < 0.2)
+    cls = PrecontractedShardedHamiltonian if world > 1 else ShardedEffectiveHamiltonian
+    ref = ptb.apply_local_hamiltonian(a, w, l, r)
+    err = (torch.linalg.norm(cls.from_full(w, l, r).matvec(a) - ref) / torch.linalg.norm(ref)).item()
+    lh = l + l.conj().permute(2, 1, 0); rh = r + r.conj().permute(2, 1, 0); wh = w + w.permute(0, 2, 1, 3)
+    hs = cls.from_full(wh, lh, rh)
+    ev, _ = ptb.eigh_krylov(lambda x: hs.matvec(x.reshape(Dl, d, Dr)).reshape(-1), a.reshape(-1), 12, 1)
+    ev0, _ = ptb.eigh_krylov(lambda x: ptb.apply_local_hamiltonian(x.reshape(Dl, d, Dr), wh, lh, rh).reshape(-1),
+                             a.reshape(-1), 12, 1)
+    t = torch.tensor([err, abs(ev[0] - ev0[0]) / abs(ev0[0])], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"parity_rel_err": t[0].item(), "ritz_value_rel_diff": t[1].item(), "ritz_value": float(ev[0]),
+            "parity_problem": f"a ({Dl},{d},{Dr}), w ({cl},{d},{d},{cr}) 20% dense, vs unsharded device matvec",
+            "parity_ok": bool(t[0].item() < 1e-12 and t[1].item() < 1e-9)}
+
+
+def molecular_centre_w():
+    """Centre tensor w (562,2,2,501) of the reference-built 32-orbital molecular MPO (tests/golden cache)."""
+    from pytenet_b200.hamiltonian import cached_mpo_tensors
+    path = os.path.join(ROOT, "tests", "golden", "molecular_mpo_N32.npz")
+    _, _, ws = cached_mpo_tensors(path)
+    return ws[16]
+
+
+def sharded_block(torch, dist, device, world, rank, D=1024, d=2, reps=3):
+    """One effective-H matvec at the centre site of the 32-orbital molecular MPO (BASELINE config 4): the MPO
+    tensor is the reference's own w (562,2,2,501) (real, 16.8 % dense, from the committed cache), a (1024,2,1024),
+    random environments of the right shape; MPO bond split over all ranks.  Fixed total work, so ms_per_matvec
+    across N = 1, 2, 4, 8 is the strong-scaling curve.  Carries its own multi-rank parity check."""
+    from pytenet_b200.sharded import ShardedEffectiveHamiltonian, PrecontractedShardedHamiltonian, _CudaOps
+    parity = sharded_parity(torch, dist, device, world)
+    w = molecular_centre_w()
+    cl, _, _, cr = w.shape
+    gen = torch.Generator(device=device).manual_seed(1 + 7919 * rank)
+    scale = 1.0 / np.sqrt(D)
     setup_ms = 0.0
     if world > 1:
-        # all-reduce-only variant: LW_g precontracted once per site, two GEMMs per matvec
-        heff, setup_ms = PrecontractedShardedHamiltonian.synthetic(D, d, D, cl, cr, density=0.168, seed=1,
-                                                                  device=device)
+        # all-reduce-only variant: LW_g precontracted once per site from the full left block, two GEMMs per matvec
+        P = -(-cr // world)
+        q0, q1 = rank * P, min((rank + 1) * P, cr)
+        l_full = torch.randn((D, cl, D), dtype=torch.complex128, device=device,
+                             generator=torch.Generator(device=device).manual_seed(1)) * scale
+        r_shard = torch.zeros((D, P, D), dtype=torch.complex128, device=device)
+        r_shard[:, :q1 - q0, :] = torch.randn((D, q1 - q0, D), dtype=torch.complex128, device=device,
+                                              generator=gen) * scale
+        w3 = np.zeros((d, P, d, cl))
+        w3[:, :q1 - q0] = w[:, :, :, q0:q1].transpose(2, 3, 1, 0)          # [(s, kappa_loc, s'), k]
+        w3 = torch.from_numpy(w3.reshape(d * P * d, cl)).to(device)
+        ops = _CudaOps()
+        lw = torch.empty((D, d * P * d, D), dtype=torch.complex128, device=device)
+        torch.cuda.synchronize(device)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.precontract(w3, l_full, lw)
+        e1.record()
+        torch.cuda.synchronize(device)
+        setup_ms = e0.elapsed_time(e1)
+        del l_full
+        heff = PrecontractedShardedHamiltonian(lw.reshape(D * d * P, d, D), r_shard, (D, d, D, d, D, D, P), ops=ops)
     else:
         # one GPU: the three-step contraction (fewer flops) is the baseline the N > 1 runs scale against
-        heff = ShardedEffectiveHamiltonian.synthetic(D, d, D, cl, cr, density=0.168, seed=1, device=device)
+        l = torch.randn((D, cl, D), dtype=torch.complex128, device=device, generator=gen) * scale
+        r = torch.randn((D, cr, D), dtype=torch.complex128, device=device, generator=gen) * scale
+        heff = ShardedEffectiveHamiltonian.from_full(torch.from_numpy(w).to(device), l, r)
+        del l, r
     x = torch.randn(D, d, D, dtype=torch.complex128, device=device) / np.sqrt(D * d * D)
     for _ in range(2):
         heff.matvec(x)
@@ -301,20 +394,202 @@ def sharded_block(torch, dist, device, world, rank, D=1024, d=2, cl=562, cr=501,
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        t = torch.tensor([ms, setup_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
+        ms, setup_ms = t.tolist()
     fa = 8.0 * (D * d * D * cr * D + cl * d * d * cr * D * D + D * D * cl * d * D)
     gather, red = heff.exchange_bytes_per_rank()
-    blk = {"workload": f"molecular-shape heff matvec: a ({D},{d},{D}), w ({cl},{d},{d},{cr}) real 16.8% dense, "
-                       f"l ({D},{cl},{D}), r ({D},{cr},{D}); MPO bonds split over {world} rank(s)",
+    blk = {"workload": f"config-4 centre-site heff matvec: a ({D},{d},{D}), w ({cl},{d},{d},{cr}) = site 16 of the "
+                       f"reference-built 32-orbital molecular MPO (real, {100.0 * np.count_nonzero(w) / w.size:.1f}% "
+                       f"dense), random l ({D},{cl},{D}), r ({D},{cr},{D}); MPO bond split over {world} rank(s)",
            "scaling": "strong", "n_gpus": world, "ms_per_matvec": ms, "gflops_alg": fa / ms / 1e6,
            "flops_alg": fa, "flops_exec_per_rank": heff.flops_per_rank(), "exchange": heff.exchange,
            "allgather_bytes_per_rank": gather, "allreduce_bytes_per_rank": red,
-           "algorithm": type(heff).__name__, "precontract_ms_per_site": setup_ms}
+           "algorithm": type(heff).__name__, "precontract_ms_per_site": setup_ms,
+           "ms_per_matvec_incl_precontract_k25": ms + setup_ms / 25.0, **parity}
     del heff, x
     torch.cuda.empty_cache()
     return blk
+
+
+def sharded_sweep_block(torch, dist, device, world, rank, D=128, k=10):
+    """BASELINE config 4 through its public driver at a bench-sized bond dimension: one sweep of
+    `dmrg_singlesite_sharded` on the reference-built 32-orbital molecular MPO (MPO bonds up to 562), random start
+    state in the half-filling sector with bonds <= D.  Same start state for every N, so `energy` must agree across
+    the N = 1, 2, 4, 8 lines of a scaling run (the all-reduce order differs: agreement to ~1e-10); at N > 1 rank 0
+    also reports psi's drift across ranks.  The full-size run (D = 1024, 8 GPUs) is tools/config4_sweep.py."""
+    import pytenet_b200 as ptb
+    from pytenet_b200.hamiltonian import load_cached_mpo
+    from pytenet_b200.sharded_dmrg import dmrg_singlesite_sharded
+    h = load_cached_mpo(os.path.join(ROOT, "tests", "golden", "molecular_mpo_N32.npz"), device=device)
+    n = h.nsites
+    psi = ptb.MPS.construct_random(n, h.qsite, n // 2, max_vdim=D, dtype="complex", rng=np.random.default_rng(11),
+                                   device=device)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    en = dmrg_singlesite_sharded(h, psi, 1, numiter_lanczos=k)
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    fp = torch.stack([torch.linalg.norm(t).double() for t in psi.a])
+    drift = 0.0
+    stat = torch.tensor([secs], dtype=torch.float64, device=device)
+    if world > 1:
+        ref = fp.clone()
+        dist.broadcast(ref, src=0)
+        dd = (fp - ref).abs().max().reshape(1)
+        dist.all_reduce(dd, op=dist.ReduceOp.MAX)
+        drift = dd.item()
+        dist.all_reduce(stat, op=dist.ReduceOp.MAX)
+    blk = {"workload": f"dmrg_singlesite_sharded, 32-orbital molecular MPO (reference-built, bonds <= "
+                       f"{max(h.bond_dims)}), psi bonds <= {D}, k = {k}, 1 sweep, {world} rank(s)",
+           "n_gpus": world, "seconds_per_sweep": stat.item(), "energy": float(en[-1]),
+           "psi_drift_across_ranks": drift, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+    del h, psi
+    torch.cuda.empty_cache()
+    return blk
+
+
+def _xxz_chain(ptb, L, D, device, seed=42):
+    h = ptb.heisenberg_xxz_1d_mpo(L, 1.0, 0.8, -0.1).zero_qnumbers()
+    bonds = [min(2 ** i, 2 ** (L - i), D) for i in range(L + 1)]
+    psi = ptb.MPS(h.qsite, [np.zeros(b, dtype=int) for b in bonds], fill="random",
+                  rng=np.random.default_rng(seed), device=device)
+    return h, psi, bonds
+
+
+def _cpu_local_problem(kind, D, k_cpu, k):
+    """Seconds the reference's CPU path (oracle restatement: NumPy + OpenBLAS, all host threads) needs for the
+    Lanczos runs of ONE bulk local problem at full bond dimension, measured with `k_cpu` iterations and scaled
+    linearly to `k` (every iteration is one matvec + the same vector updates).  Returns (seconds at k, raw)."""
+    import oracle
+    import oracle.lanczos as ol
+    use_all_host_threads()
+    rng = np.random.default_rng(3)
+
+    def herm(D, chi):
+        e = (rng.normal(size=(D, chi, D)) + 1j * rng.normal(size=(D, chi, D))) / np.sqrt(2 * D)
+        return e + e.conj().transpose(2, 1, 0)
+    t0 = time.perf_counter()
+    if kind == "tdvp1":
+        a, w, _, _ = host_inputs_onesite(D, CHI, seed=5)
+        l, r = herm(D, CHI), herm(D, CHI)
+        w = w + w.transpose(0, 2, 1, 3)
+        t0 = time.perf_counter()
+        ol.expm_krylov(lambda x: oracle.apply_local_hamiltonian(x.reshape(a.shape), w, l, r).reshape(-1),
+                       a.reshape(-1), -0.005j, k_cpu)
+        c = np.ascontiguousarray(a[:, 0, :])
+        ol.expm_krylov(lambda x: oracle.apply_local_bond_contraction(x.reshape(c.shape), l, r).reshape(-1),
+                       c.reshape(-1), 0.005j, k_cpu)
+        raw = time.perf_counter() - t0
+        return raw * k / k_cpu, raw
+    a, w, _, _ = host_inputs(D, d_HEAD, CHI, seed=5)
+    l, r = herm(D, CHI), herm(D, CHI)
+    w = w + w.transpose(0, 2, 1, 3)
+    t0 = time.perf_counter()
+    ol.eigh_krylov(lambda x: oracle.apply_local_hamiltonian(x.reshape(a.shape), w, l, r).reshape(-1),
+                   a.reshape(-1), k_cpu, 1)
+    raw = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    np.linalg.svd(a.reshape(D * 2, 2 * D), full_matrices=False)
+    svd = time.perf_counter() - t1
+    return raw * k / k_cpu + svd, raw + svd
+
+
+def sweeps_block(torch, ptb, device):
+    """The "sweep seconds" half of BASELINE.json's metric, through the PUBLIC drivers, with the device time split
+    by category (CUDA events around the regions of pytenet_b200/_prof.py; "host+other" is what is left of the
+    synchronised wall time) and the reference's CPU path beside it.
+
+    * `tdvp_singlesite` (pytenet/tdvp.py:26-118): XXZ chain L = 24 whose bulk bonds reach D = 2048 (bond profile
+      min(2^i, 2^(L-i), 2048): the public signature has no maximum-bond argument), complex128, k = 25, ONE full
+      symmetric time step (left + right sweep).
+    * `dmrg_twosite` (pytenet/dmrg.py:96-178): XXZ chain L = 22 capped at 1024 (config-2 two-site shape
+      (1024,4,1024) at the centre), k = 25, tol_split = 0, ONE sweep.
+    CPU side: a complete sweep is hours on the host, so the bulk local problem is timed at FULL bond
+    dimension with 3 of the 25 Lanczos iterations (scaled linearly in k) and the sweep is extrapolated over the
+    sites by their flop counts -- labelled "extrapolated"."""
+    from pytenet_b200 import _prof
+    out = {}
+    k = 25
+
+    def run(name, fn, h, psi):
+        torch.cuda.synchronize()
+        _prof.enable(True)
+        t0 = time.perf_counter()
+        fn(h, psi)
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        ph = {kk: v / 1e3 for kk, v in _prof.report().items()}
+        _prof.enable(False)
+        ph["host+other"] = max(0.0, secs - sum(ph.values()))
+        return secs, ph
+
+    def site_flops(bonds, d, two_site):
+        tot = []
+        n = len(bonds) - 1
+        for i in range(n - 1 if two_site else n):
+            Dl, Dr = bonds[i], bonds[i + 2] if two_site else bonds[i + 1]
+            cl = 1 if i == 0 else CHI
+            cr = 1 if (i + (2 if two_site else 1)) == n else CHI
+            tot.append(8.0 * (Dl * d * Dr * cr * Dr + cl * d * d * cr * Dl * Dr + Dl * Dl * cl * d * Dr))
+        return tot
+
+    # ---- single-site TDVP, D = 2048 ----
+    L, D = 24, D_HEAD
+    h, psi, bonds = _xxz_chain(ptb, L, D, device)
+    secs, ph = run("tdvp1", lambda h_, p_: ptb.tdvp_singlesite(h_, p_, 0.01 - 0.05j, 1, numiter_lanczos=k), h, psi)
+    fl = site_flops(bonds, 2, False)
+    bulk = 8.0 * (2 * 2 * CHI * D ** 3 + 4 * CHI * CHI * D * D)
+    # per time step every site problem runs twice (except the last) and every bond once per direction; in units of
+    # the bulk site problem (site matvec + bond matvec) the chain is sum(F_site) / F_bulk
+    units = 2.0 * sum(fl) / bulk
+    cpu_k, cpu_raw = _cpu_local_problem("tdvp1", D, 3, k)
+    out["tdvp_singlesite"] = {
+        "driver": "pytenet_b200.tdvp_singlesite(H, psi, dt=0.01-0.05j, numsteps=1, numiter_lanczos=25)",
+        "workload": f"XXZ L={L}, zero quantum numbers, complex128, bonds min(2^i, 2^(L-i), {D}) "
+                    f"({sum(1 for i in range(L) if bonds[i] == D and bonds[i + 1] == D)} sites with both bonds at {D})",
+        "seconds_per_step": secs, "device_seconds_by_phase": ph,
+        "cpu": {"kind": "port", "cores": cpu_threads(), "bulk_local_problem_seconds_k25": cpu_k,
+                "measured_seconds": cpu_raw,
+                "sample": f"site step + bond step of one bulk site at D={D}: 3 of 25 Lanczos iterations each, "
+                          f"scaled linearly in k",
+                "seconds_per_step_extrapolated": cpu_k * units,
+                "extrapolation": f"bulk local problem x {units:.2f} bulk-equivalents (sum of per-site flops / bulk "
+                                 f"flops, both directions); QR and environment updates not included (favours the CPU)"},
+    }
+    out["tdvp_singlesite"]["speedup_vs_cpu_extrapolated"] = cpu_k * units / secs
+    del h, psi
+    torch.cuda.empty_cache()
+
+    # ---- two-site DMRG at the config-2 shape ----
+    L2, D2 = 22, 1024
+    h, psi, bonds = _xxz_chain(ptb, L2, D2, device, seed=43)
+    secs, ph = run("dmrg2", lambda h_, p_: ptb.dmrg_twosite(h_, p_, 1, numiter_lanczos=k, tol_split=0), h, psi)
+    after = list(psi.bond_dims)
+    fl = site_flops(after, 2 * 2, True)
+    bulk2 = f_alg(D2, d_HEAD, CHI)
+    units2 = 2.0 * sum(fl) / bulk2
+    cpu_k2, cpu_raw2 = _cpu_local_problem("dmrg2", D2, 3, k)
+    out["dmrg_twosite"] = {
+        "driver": "pytenet_b200.dmrg_twosite(H, psi, numsweeps=1, numiter_lanczos=25, tol_split=0)",
+        "workload": f"XXZ L={L2} (config-2 Hamiltonian), complex128, start bonds min(2^i, 2^(L-i), {D2}); "
+                    f"tol_split=0 lets the centre bonds grow: bond dims after the sweep {after}",
+        "seconds_per_sweep": secs, "device_seconds_by_phase": ph,
+        "svd_share": ph.get("svd", 0.0) / secs,
+        "cpu": {"kind": "port", "cores": cpu_threads(), "bulk_local_problem_seconds_k25": cpu_k2,
+                "measured_seconds": cpu_raw2,
+                "sample": f"one (1024,4,1024) two-site problem: 3 of 25 Lanczos iterations scaled linearly in k + "
+                          f"one 2048x2048 complex SVD (LAPACK gesdd)",
+                "seconds_per_sweep_extrapolated": cpu_k2 * units2,
+                "extrapolation": f"bulk pair problem x {units2:.2f} bulk-equivalents (per-pair matvec flops with the "
+                                 f"realised bond dimensions / flops of the (1024,4,1024) pair, both directions)"},
+    }
+    out["dmrg_twosite"]["speedup_vs_cpu_extrapolated"] = cpu_k2 * units2 / secs
+    del h, psi
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -333,6 +608,9 @@ def run_ours(args):
     lib = _lib.load()
     D, d, chi = D_HEAD, d_HEAD, CHI
     steps, warm = args.steps, max(args.warmup, 3)
+    # page-locked staging memory on the GPU-local NUMA node (before anything is pinned)
+    # (N > 1 only: at N = 1 there is no contention, and the CPU baseline of the same process keeps every core)
+    numa = dev.bind_host_to_gpu_numa_node(local) if world > 1 else None
 
     # inputs: pinned host buffers (for e2e) and their device-resident copies (for `value`)
     a_h, w_h, l_h, r_h = host_inputs(D, d, chi, seed=1234 + rank, pinned=True)
@@ -389,14 +667,32 @@ def run_ours(args):
         e2e_s = t.item()
     h2d = a_h.nbytes + w_h.nbytes + l_h.nbytes + r_h.nbytes
     d2h = res.nbytes
+    # the same call as a drop-in NumPy caller makes it: PAGEABLE arrays (the driver stages them through its own
+    # bounce buffer); reported next to the pinned number, never instead of it
+    pg = [np.array(x) for x in (a_h, w_h, l_h, r_h)]
+    res = ptb.apply_local_hamiltonian(*pg)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        res = ptb.apply_local_hamiltonian(*pg)
+    barrier()
+    e2e_pageable_s = (time.perf_counter() - t0) / 2
+    del pg
+    if world > 1:
+        t = torch.tensor([e2e_pageable_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_pageable_s = t.item()
     F = f_alg(D, d, chi)
 
     # ---- MPO-bond-sharded matvec (BASELINE config 4 shape), STRONG scaling over the same N ranks ----
-    sharded = None
+    sharded = sharded_sweep = None
     if os.environ.get("PTB_BENCH_SKIP_SHARDED") != "1":
         del a, l, r, out, res
         torch.cuda.empty_cache()
         sharded = sharded_block(torch, dist, device, world, rank)
+        sharded_sweep = None
+        if os.environ.get("PTB_BENCH_SKIP_SHARDED_SWEEP") != "1":
+            sharded_sweep = sharded_sweep_block(torch, dist, device, world, rank)
         a = torch.from_numpy(a_h).to(device); l = torch.from_numpy(l_h).to(device); r = torch.from_numpy(r_h).to(device)
         out = torch.empty((D, d, D), dtype=torch.complex128, device=device)
 
@@ -453,7 +749,7 @@ def run_ours(args):
     }
 
     # PTB_BENCH_SKIP_CPU=1 only for runs under a profiler (numbers taken there are never bench values)
-    cpu = None if os.environ.get("PTB_BENCH_SKIP_CPU") == "1" else cpu_baseline_block()
+    cpu = None if (os.environ.get("PTB_BENCH_SKIP_CPU") == "1" or world > 1) else cpu_baseline_block()
 
     # ---- other shapes of the same path (device-resident, CUDA events) ----
     del t1, t2
@@ -481,6 +777,11 @@ def run_ours(args):
     block_sparse = None
     if os.environ.get("PTB_BENCH_SKIP_SECTORS") != "1":
         block_sparse = block_sparse_block(torch, ptb, device, time_ms)
+    sweeps = None
+    if world == 1 and os.environ.get("PTB_BENCH_SKIP_SWEEPS") != "1":
+        del a, l, r, out
+        torch.cuda.empty_cache()
+        sweeps = sweeps_block(torch, ptb, device)
 
     line = {
         "metric": METRIC, "value": world * F / (ms / 1e3) / 1e9, "unit": "GFLOP/s", "n_gpus": world,
@@ -492,11 +793,17 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": world * F / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-                "call": "pytenet_b200.apply_local_hamiltonian(a, w, l, r) with pinned NumPy host buffers"},
+                "call": "pytenet_b200.apply_local_hamiltonian(a, w, l, r) with pinned NumPy host buffers",
+                "pageable_inputs": {"ms_per_step": e2e_pageable_s * 1e3,
+                                    "value": world * F / e2e_pageable_s / 1e9,
+                                    "note": "same call with ordinary (pageable) NumPy arrays"},
+                "host_numa_binding": numa},
         "gpu_launches": 3 * steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "sharded": sharded,
+        "sharded_sweep": sharded_sweep,
+        "sweeps": sweeps,
         "other_shapes": other,
         "other_ops": other_ops,
         "block_sparse": block_sparse,

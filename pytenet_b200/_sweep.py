@@ -14,6 +14,7 @@ import torch
 
 from . import _device as dev
 from . import _lib
+from ._prof import region
 from .sectors import HeffSectorPlan, EnvSectorPlan, BondSectorPlan
 from .block_sparse_util import is_qsparse
 from .chain_ops import (apply_local_hamiltonian, apply_local_bond_contraction,
@@ -61,15 +62,17 @@ def _cached_plan(cls, cplx, *qnums):
     return plan
 
 
-def sector_plan(ql, qs, qr, qwl, qwr, like):
-    """HeffSectorPlan for a local problem, or None when the dense path is the right choice."""
+def sector_plan(ql, qs, qr, qwl, qwr, like, *others):
+    """HeffSectorPlan for a local problem, or None when the dense path is the right choice.  The plan's dtype is
+    the promoted dtype of the state tensor `like` and of `others` (environments, MPO tensor), as NumPy promotes."""
     if _SECTOR_MODE == "0":
         return None
     if _SECTOR_MODE != "1" and max(len(ql), len(qr)) < _SECTOR_MIN_BOND:
         return None
     if not (np.any(ql) or np.any(qr) or np.any(qs) or np.any(qwl) or np.any(qwr)):
         return None
-    return _cached_plan(HeffSectorPlan, True if like is None else like.dtype.is_complex, ql, qs, qr, qwl, qwr)
+    cplx = True if like is None else dev.any_complex(like, *[t for t in others if isinstance(t, torch.Tensor)])
+    return _cached_plan(HeffSectorPlan, cplx, ql, qs, qr, qwl, qwr)
 
 
 def _use_sectors(nbond, *qnums):
@@ -85,20 +88,22 @@ def env_step_left(psi, hamiltonian, i, l):
     when the quantum numbers are non-trivial and the bonds large, else the dense contraction."""
     a, w = psi.a[i], hamiltonian.a[i]
     qn = (psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], hamiltonian.qbonds[i], hamiltonian.qbonds[i + 1])
-    if _use_sectors(max(a.shape[0], a.shape[2]), *qn) and isinstance(l, torch.Tensor) and l.shape[0] == a.shape[0]:
-        plan = _cached_plan(EnvSectorPlan, dev.any_complex(a, l, w), *qn)
-        return plan.step_left(a, w, l)
-    return contraction_operator_step_left(a, a, w, l)
+    with region("env"):
+        if _use_sectors(max(a.shape[0], a.shape[2]), *qn) and isinstance(l, torch.Tensor) and l.shape[0] == a.shape[0]:
+            plan = _cached_plan(EnvSectorPlan, dev.any_complex(a, l, w), *qn)
+            return plan.step_left(a, w, l)
+        return contraction_operator_step_left(a, a, w, l)
 
 
 def env_step_right(psi, hamiltonian, i, r):
     """rblocks[i-1] from rblocks[i] and site i (tdvp.py:106,197,216; dmrg.py:83,168); see env_step_left."""
     a, w = psi.a[i], hamiltonian.a[i]
     qn = (psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], hamiltonian.qbonds[i], hamiltonian.qbonds[i + 1])
-    if _use_sectors(max(a.shape[0], a.shape[2]), *qn) and isinstance(r, torch.Tensor) and r.shape[0] == a.shape[2]:
-        plan = _cached_plan(EnvSectorPlan, dev.any_complex(a, r, w), *qn)
-        return plan.step_right(a, w, r)
-    return contraction_operator_step_right(a, a, w, r)
+    with region("env"):
+        if _use_sectors(max(a.shape[0], a.shape[2]), *qn) and isinstance(r, torch.Tensor) and r.shape[0] == a.shape[2]:
+            plan = _cached_plan(EnvSectorPlan, dev.any_complex(a, r, w), *qn)
+            return plan.step_right(a, w, r)
+        return contraction_operator_step_right(a, a, w, r)
 
 
 def bond_plan(qbl, qbr, qw, c, l, r):
@@ -197,23 +202,26 @@ def _heff(w, l, r, shape, plan):
 def local_hamiltonian_step(l, r, w, a, dt, numiter: int, plan=None):
     """exp(-dt H_eff) a for the one- or two-site effective Hamiltonian (tdvp.py:223-229)."""
     shape = tuple(a.shape)
-    return expm_krylov(_heff(w, l, r, shape, plan), a.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
+    with region("lanczos"):
+        return expm_krylov(_heff(w, l, r, shape, plan), a.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
 
 
 def local_bond_step(l, r, c, dt, numiter: int, plan=None):
     """exp(-dt K_eff) c for the zero-site (bond) effective Hamiltonian (tdvp.py:232-238)."""
     shape = tuple(c.shape)
-    if plan is not None and plan.cplx == (c.dtype.is_complex or l.dtype.is_complex or r.dtype.is_complex):
-        def matvec(x):
-            if x.dtype.is_complex != plan.cplx:
-                return apply_local_bond_contraction(x.reshape(shape), l, r).reshape(-1)
-            return plan.apply(x.reshape(shape), l, r).reshape(-1)
-        return expm_krylov(matvec, c.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
-    return expm_krylov(BondOperator(l, r, shape), c.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
+    with region("lanczos"):
+        if plan is not None and plan.cplx == (c.dtype.is_complex or l.dtype.is_complex or r.dtype.is_complex):
+            def matvec(x):
+                if x.dtype.is_complex != plan.cplx:
+                    return apply_local_bond_contraction(x.reshape(shape), l, r).reshape(-1)
+                return plan.apply(x.reshape(shape), l, r).reshape(-1)
+            return expm_krylov(matvec, c.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
+        return expm_krylov(BondOperator(l, r, shape), c.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
 
 
 def minimize_local_energy(w, l, r, a_start, numiter: int, plan=None):
     """Lowest Ritz pair of the local effective Hamiltonian (dmrg.py:181-189)."""
     shape = tuple(a_start.shape)
-    ev, u_ritz = eigh_krylov(_heff(w, l, r, shape, plan), a_start.reshape(-1), numiter, 1)
-    return ev[0], dev.dense(u_ritz[:, 0]).reshape(shape)
+    with region("lanczos"):
+        ev, u_ritz = eigh_krylov(_heff(w, l, r, shape, plan), a_start.reshape(-1), numiter, 1)
+        return ev[0], dev.dense(u_ritz[:, 0]).reshape(shape)

@@ -14,6 +14,7 @@ from .mps import (MPS, mps_local_orthonormalize_left_qr, mps_local_orthonormaliz
 from .mpo import MPO, mpo_merge_tensor_pair
 from ._sweep import prepare_environments, minimize_local_energy, sector_plan, env_step_left, env_step_right
 from .block_sparse_util import qnumber_flatten
+from ._prof import region
 
 __all__ = ["dmrg_singlesite", "dmrg_twosite"]
 
@@ -40,19 +41,22 @@ def dmrg_singlesite(hamiltonian: MPO, psi: MPS, numsweeps: int, numiter_lanczos:
     en_min = np.zeros(numsweeps)
 
     def site_plan(i):
-        return sector_plan(psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], qh[i], qh[i + 1], psi.a[i])
+        return sector_plan(psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], qh[i], qh[i + 1], psi.a[i],
+                           lblocks[i], rblocks[i], ham[i])
 
     for n in range(numsweeps):
         en = 0
         for i in range(nsites - 1):                                          # dmrg.py:65-73
             en, psi.a[i] = minimize_local_energy(ham[i], lblocks[i], rblocks[i], psi.a[i], k, site_plan(i))
-            psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_local_orthonormalize_left_qr(
-                psi.a[i], psi.a[i + 1], psi.qsite, psi.qbonds[i:i + 2])
+            with region("qr"):
+                psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_local_orthonormalize_left_qr(
+                    psi.a[i], psi.a[i + 1], psi.qsite, psi.qbonds[i:i + 2])
             lblocks[i + 1] = env_step_left(psi, hamiltonian, i, lblocks[i])
         for i in reversed(range(1, nsites)):                                 # dmrg.py:76-84
             en, psi.a[i] = minimize_local_energy(ham[i], lblocks[i], rblocks[i], psi.a[i], k, site_plan(i))
-            psi.a[i], psi.a[i - 1], psi.qbonds[i] = mps_local_orthonormalize_right_qr(
-                psi.a[i], psi.a[i - 1], psi.qsite, psi.qbonds[i:i + 2])
+            with region("qr"):
+                psi.a[i], psi.a[i - 1], psi.qbonds[i] = mps_local_orthonormalize_right_qr(
+                    psi.a[i], psi.a[i - 1], psi.qsite, psi.qbonds[i:i + 2])
             rblocks[i - 1] = env_step_right(psi, hamiltonian, i, rblocks[i])
         _renormalize_first_site(psi)
         en_min[n] = en                     # energy of the last local problem of the sweep (dmrg.py:91)
@@ -78,11 +82,14 @@ def dmrg_twosite(hamiltonian: MPO, psi: MPS, numsweeps: int, numiter_lanczos: in
     qs2 = qnumber_flatten([qs, qs])                   # quantum numbers of the merged physical index
 
     def optimize_pair(i, distr):
-        merged = mps_merge_tensor_pair(psi.a[i], psi.a[i + 1])
-        plan = sector_plan(psi.qbonds[i], qs2, psi.qbonds[i + 2], qh[i], qh[i + 2], merged)
+        with region("glue"):
+            merged = mps_merge_tensor_pair(psi.a[i], psi.a[i + 1])
+        plan = sector_plan(psi.qbonds[i], qs2, psi.qbonds[i + 2], qh[i], qh[i + 2], merged,
+                           lblocks[i], rblocks[i + 1], h2[i])
         en, merged = minimize_local_energy(h2[i], lblocks[i], rblocks[i + 1], merged, k, plan)
-        psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_split_tensor_svd(
-            merged, qs, qs, [psi.qbonds[i], psi.qbonds[i + 2]], distr, tol=tol_split)
+        with region("svd"):
+            psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_split_tensor_svd(
+                merged, qs, qs, [psi.qbonds[i], psi.qbonds[i + 2]], distr, tol=tol_split)
         return en
 
     for n in range(numsweeps):

@@ -430,6 +430,9 @@ def _active(tabs):
     return bool(np.any(tabs[..., 1] > tabs[..., 0]))
 
 
+_WT_CACHE = {}        # transposed MPO matrices, one per (tensor, version); values keep the source alive
+
+
 class EnvSectorPlan:
     """
     Sector work lists for `contraction_operator_step_left / _right` (pytenet/chain_ops.py:60-99, 16-57) with
@@ -498,7 +501,16 @@ class EnvSectorPlan:
         """tout[i] = op(W) tin[i]; op = transpose for step_left (chain_ops.py:96)."""
         wmat = w.reshape(w.shape[0] * w.shape[1], w.shape[2] * w.shape[3])
         if transposed:
-            wmat = dev.dense(wmat.T)
+            # one transposed copy per MPO tensor (keyed like dev.w_csr): a fresh copy on every call would defeat the
+            # CSR cache -- a device->host copy of W per environment update inside the otherwise sync-free sweeps
+            key = (w.data_ptr(), w._version, tuple(w.shape), w.dtype)
+            hit = _WT_CACHE.get(key)
+            if hit is None:
+                if len(_WT_CACHE) > 256:
+                    _WT_CACHE.clear()
+                hit = (dev.dense(wmat.T), w)
+                _WT_CACHE[key] = hit
+            wmat = hit[0]
         w4 = wmat.reshape(1, rows_out, rows_in, 1)
         csr = dev.w_csr(w4) if (cplx or not w.dtype.is_complex) else None
         if csr is not None:

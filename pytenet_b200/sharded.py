@@ -162,7 +162,9 @@ class ShardedEffectiveHamiltonian:
         P = -(-cr // world)                                   # common (padded) kappa shard size
         k0, k1 = kparts[rank]
         kg = k1 - k0
-        cplx = l.dtype.is_complex or r.dtype.is_complex
+        # NumPy-style promotion over all operands (the state the operator acts on is promoted in matvec)
+        cplx = bool(l.dtype.is_complex or r.dtype.is_complex
+                    or (w.dtype.is_complex if isinstance(w, torch.Tensor) else np.iscomplexobj(w)))
 
         def dense(x, want_cplx):
             x = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
@@ -258,6 +260,12 @@ class ShardedEffectiveHamiltonian:
     def matvec(self, a):
         """Apply the sharded effective Hamiltonian to `a` (Dl, d, Dr); every rank gets the full result."""
         assert tuple(a.shape) == (self.Dl, self.d_in, self.Dr)
+        if a.dtype.is_complex and not self.l_shard.dtype.is_complex:
+            # a complex state on real shards: promote the operator once (never demote the state)
+            self.l_shard = self.l_shard.to(torch.complex128)
+            self.r_shard = self.r_shard.to(torch.complex128)
+            self._t1 = self._gathered = self._t2 = None
+            self._symm = None
         a = a.to(self.l_shard.dtype) if a.dtype != self.l_shard.dtype else a
         a = a.contiguous()
         t1, gathered, t2 = self._buffers(a)

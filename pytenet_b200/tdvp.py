@@ -15,6 +15,7 @@ from .block_sparse_util import qnumber_flatten, block_sparse_qr
 from ._sweep import (prepare_environments, local_hamiltonian_step, local_bond_step, sector_plan, bond_plan,
                      env_step_left, env_step_right)
 from .krylov import defer_checks
+from ._prof import region
 
 __all__ = ["tdvp_singlesite", "tdvp_twosite"]
 
@@ -40,7 +41,8 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
     qh = hamiltonian.qbonds
 
     def site_plan(i):
-        return sector_plan(psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], qh[i], qh[i + 1], psi.a[i])
+        return sector_plan(psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], qh[i], qh[i + 1], psi.a[i],
+                           lblocks[i], rblocks[i], ham[i])
 
     for _ in range(numsteps):
         # left -> right: half step on each site, backward half step on each bond (tdvp.py:68-84)
@@ -48,15 +50,18 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
             psi.a[i] = local_hamiltonian_step(lblocks[i], rblocks[i], ham[i], psi.a[i], 0.5 * dt, k, site_plan(i))
             b0, d, b1 = psi.a[i].shape
             qold = psi.qbonds[i + 1]
-            q, c, psi.qbonds[i + 1] = block_sparse_qr(
-                psi.a[i].reshape(b0 * d, b1), qnumber_flatten((psi.qbonds[i], psi.qsite)), psi.qbonds[i + 1])
-            psi.a[i] = dev.dense(q.reshape(b0, d, q.shape[1]))
+            with region("qr"):
+                q, c, psi.qbonds[i + 1] = block_sparse_qr(
+                    psi.a[i].reshape(b0 * d, b1), qnumber_flatten((psi.qbonds[i], psi.qsite)), psi.qbonds[i + 1])
+                psi.a[i] = dev.dense(q.reshape(b0, d, q.shape[1]))
             lblocks[i + 1] = env_step_left(psi, hamiltonian, i, lblocks[i])
             c = dev.dense(c)
             c = local_bond_step(lblocks[i + 1], rblocks[i], c, -0.5 * dt, k,
                                 bond_plan(psi.qbonds[i + 1], qold, qh[i + 1], c, lblocks[i + 1], rblocks[i]))
-            nxt = psi.a[i + 1]
-            psi.a[i + 1] = dev.gemm(c, nxt.reshape(nxt.shape[0], -1)).reshape((c.shape[0],) + tuple(nxt.shape[1:]))
+            with region("glue"):
+                nxt = psi.a[i + 1]
+                psi.a[i + 1] = dev.gemm(c, nxt.reshape(nxt.shape[0], -1)).reshape(
+                    (c.shape[0],) + tuple(nxt.shape[1:]))
 
         # full step on the last site (tdvp.py:87-89)
         i = nsites - 1
@@ -64,19 +69,22 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
 
         # right -> left (tdvp.py:92-115)
         for i in reversed(range(1, nsites)):
-            at = dev.dense(psi.a[i].permute(2, 1, 0))
-            b1, d, b0 = at.shape
-            q, c, qbond = block_sparse_qr(
-                at.reshape(b1 * d, b0), qnumber_flatten((-psi.qbonds[i + 1], psi.qsite)), -psi.qbonds[i])
-            qold = psi.qbonds[i]
-            psi.qbonds[i] = -qbond
-            psi.a[i] = dev.dense(q.reshape(b1, d, q.shape[1]).permute(2, 1, 0))
+            with region("qr"):
+                at = dev.dense(psi.a[i].permute(2, 1, 0))
+                b1, d, b0 = at.shape
+                q, c, qbond = block_sparse_qr(
+                    at.reshape(b1 * d, b0), qnumber_flatten((-psi.qbonds[i + 1], psi.qsite)), -psi.qbonds[i])
+                qold = psi.qbonds[i]
+                psi.qbonds[i] = -qbond
+                psi.a[i] = dev.dense(q.reshape(b1, d, q.shape[1]).permute(2, 1, 0))
             rblocks[i - 1] = env_step_right(psi, hamiltonian, i, rblocks[i])
             c = dev.dense(c.T)
             c = local_bond_step(lblocks[i], rblocks[i - 1], c, -0.5 * dt, k,
                                 bond_plan(qold, psi.qbonds[i], qh[i], c, lblocks[i], rblocks[i - 1]))
-            prv = psi.a[i - 1]
-            psi.a[i - 1] = dev.gemm(prv.reshape(-1, prv.shape[2]), c).reshape(tuple(prv.shape[:2]) + (c.shape[1],))
+            with region("glue"):
+                prv = psi.a[i - 1]
+                psi.a[i - 1] = dev.gemm(prv.reshape(-1, prv.shape[2]), c).reshape(
+                    tuple(prv.shape[:2]) + (c.shape[1],))
             psi.a[i - 1] = local_hamiltonian_step(
                 lblocks[i - 1], rblocks[i - 1], ham[i - 1], psi.a[i - 1], 0.5 * dt, k, site_plan(i - 1))
 
@@ -109,14 +117,18 @@ def tdvp_twosite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lanczos:
     qs2 = qnumber_flatten([qs, qs])                   # quantum numbers of the merged physical index
 
     def evolve_pair(i, tau, distr):
-        merged = mps_merge_tensor_pair(psi.a[i], psi.a[i + 1])
-        plan = sector_plan(psi.qbonds[i], qs2, psi.qbonds[i + 2], qh[i], qh[i + 2], merged)
+        with region("glue"):
+            merged = mps_merge_tensor_pair(psi.a[i], psi.a[i + 1])
+        plan = sector_plan(psi.qbonds[i], qs2, psi.qbonds[i + 2], qh[i], qh[i + 2], merged,
+                           lblocks[i], rblocks[i + 1], h2[i])
         merged = local_hamiltonian_step(lblocks[i], rblocks[i + 1], h2[i], merged, tau, k, plan)
-        psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_split_tensor_svd(
-            merged, qs, qs, (psi.qbonds[i], psi.qbonds[i + 2]), distr, tol=tol_split)
+        with region("svd"):
+            psi.a[i], psi.a[i + 1], psi.qbonds[i + 1] = mps_split_tensor_svd(
+                merged, qs, qs, (psi.qbonds[i], psi.qbonds[i + 2]), distr, tol=tol_split)
 
     def backward_site(i):
-        plan = sector_plan(psi.qbonds[i], qs, psi.qbonds[i + 1], qh[i], qh[i + 1], psi.a[i])
+        plan = sector_plan(psi.qbonds[i], qs, psi.qbonds[i + 1], qh[i], qh[i + 1], psi.a[i],
+                           lblocks[i], rblocks[i], ham[i])
         psi.a[i] = local_hamiltonian_step(lblocks[i], rblocks[i], ham[i], psi.a[i], -0.5 * dt, k, plan)
 
     for _ in range(numsteps):

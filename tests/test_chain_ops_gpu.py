@@ -251,9 +251,37 @@ def test_config2_shape_direct_parity_with_oracle(cuda_lib):
     assert rel(got, oracle.apply_local_bond_contraction(c, l, r)) < TOL
 
 
+def test_headline_shape_direct_parity_with_oracle(cuda_lib):
+    """Direct parity at the HEADLINE shape the bench number is quoted on (two-site XXZ, a (2048,4,2048),
+    l/r (2048,5,2048), complex128): all four contractions against the CPU oracle on the same seeded inputs, 1e-12
+    relative.  The oracle needs ~2.5 s per two-site matvec on 16 host cores (BENCH_r01 cpu_baseline), about a
+    minute for everything here on 8."""
+    import pytenet_b200 as ptb
+    from bench import host_inputs
+    a, w, l, r = host_inputs(2048, 4, 5, seed=2048)
+    ld, rd, wd = cu(l), cu(r), cu(w)
+    got = ptb.apply_local_hamiltonian(cu(a), wd, ld, rd).cpu().numpy()
+    want = oracle.apply_local_hamiltonian(a, w, l, r)
+    assert rel(got, want) < TOL
+    # the same call through the host-buffer C entry (sliced copy / compute pipeline)
+    assert rel(ptb.apply_local_hamiltonian(a, w, l, r), want) < TOL
+    del got, want
+    # single-site tensors of the same bond dimension: both environment updates and the zero-site contraction
+    a1 = np.ascontiguousarray(a[:, :2, :]); w1 = np.ascontiguousarray(w[:, :2, :2, :])
+    got = ptb.contraction_operator_step_left(cu(a1), cu(a1), cu(w1), ld).cpu().numpy()
+    assert rel(got, oracle.contraction_operator_step_left(a1, a1, w1, l)) < TOL
+    got = ptb.contraction_operator_step_right(cu(a1), cu(a1), cu(w1), rd).cpu().numpy()
+    assert rel(got, oracle.contraction_operator_step_right(a1, a1, w1, r)) < TOL
+    c = np.ascontiguousarray(a[:, 0, :])
+    got = ptb.apply_local_bond_contraction(cu(c), ld, rd).cpu().numpy()
+    assert rel(got, oracle.apply_local_bond_contraction(c, l, r)) < TOL
+    got = ptb.apply_local_hamiltonian(cu(a1), cu(w1), ld, rd).cpu().numpy()
+    assert rel(got, oracle.apply_local_hamiltonian(a1, w1, l, r)) < TOL
+
+
 def test_headline_shape_properties(cuda_lib):
-    """BASELINE headline shape (two-site XXZ, a (2048,4,2048), l/r (2048,5,2048), complex128), where the CPU oracle
-    would need minutes: size-independent properties of the device matvec -- Hermiticity <x|H y> = <H x|y> for
+    """BASELINE headline shape (two-site XXZ, a (2048,4,2048), l/r (2048,5,2048), complex128): size-independent
+    properties of the device matvec on top of the direct oracle comparison above -- Hermiticity <x|H y> = <H x|y> for
     Hermitian environments, linearity, and agreement of the device-resident path with the host-buffer C entry
     (sliced copy/compute pipeline, accumulated step-1 slices)."""
     import pytenet_b200 as ptb
