@@ -428,6 +428,7 @@ def sharded_sweep_block(torch, dist, device, world, rank, D=128, k=10):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    torch.cuda.reset_peak_memory_stats()
     t0 = time.perf_counter()
     en = dmrg_singlesite_sharded(h, psi, 1, numiter_lanczos=k)
     torch.cuda.synchronize()

@@ -123,6 +123,10 @@ class ShardedSite:
         Dl, d, Dr, dout, Dlp, Drp, P = self.dims
         b = a if b is None else b
         a = a.to(self.dtype).contiguous()
+        # the orthonormalised tensor may have a smaller right bond than the one the local problem was solved on
+        # (a sector-wise QR keeps min(rows, cols) indices per sector)
+        assert a.shape[0] == Dl and a.shape[1] == d and b.shape[0] == Dlp and b.shape[1] == dout
+        Dr = a.shape[2]
         # conj(b) with rows ordered (s', i') to match the column order of LW
         b2 = dev.dense(b.to(self.dtype).permute(1, 0, 2)).reshape(dout * Dlp, b.shape[2])
         x = torch.empty((Dl * d * P, b.shape[2]), dtype=self.dtype, device=a.device)

@@ -148,8 +148,9 @@ def test_batched_sector_svd(cuda_lib, cplx):
     a[:, np.nonzero(q1 == -2)[0][3]] = 0
     # a rank-3 sector block (20 x 12): nine singular values are rounding noise in LAPACK and here
     r9, c9 = np.nonzero(q0 == 9)[0], np.nonzero(q1 == 9)[0]
-    lowrank = rng.normal(size=(len(r9), 3)) @ rng.normal(size=(3, len(c9)))
-    a[np.ix_(r9, c9)] = lowrank + (1j * (rng.normal(size=(len(r9), 3)) @ rng.normal(size=(3, len(c9)))) if cplx else 0)
+    fl = rng.normal(size=(len(r9), 3)) + (1j * rng.normal(size=(len(r9), 3)) if cplx else 0)
+    fr = rng.normal(size=(3, len(c9))) + (1j * rng.normal(size=(3, len(c9))) if cplx else 0)
+    a[np.ix_(r9, c9)] = fl @ fr
     # graded singular values in one sector (exercise the relative accuracy of the Jacobi sweeps)
     r7, c7 = np.nonzero(q0 == 7)[0], np.nonzero(q1 == 7)[0]
     a[np.ix_(r7, c7)] *= np.logspace(0, -9, len(c7))[None, :]
