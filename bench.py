@@ -85,11 +85,13 @@ def host_inputs_onesite(D, chi, seed):
             crandn((D, chi, D)) / np.sqrt(D))
 
 
-def block_sparse_block(torch, ptb, device, time_ms, D=2048):
+def block_sparse_block(torch, ptb, device, time_ms, peak_tflops, D=2048):
     """BASELINE config 3 shape (two-site Fermi-Hubbard, (N,Sz) sectors, bonds grouped by sector as the sweeps
-    leave them): dense device matvec vs the sector-banded matvec (HeffSectorPlan / ptb_gemm_banded)."""
+    leave them): the dense device matvec, the banded work lists over dense-layout tensors (round 1,
+    sectors.HeffSectorPlan) and the sector-packed grouped GEMM (sector_packed.PackedHeffPlan, what the sweeps use)."""
     from pytenet_b200 import hamiltonian as ham
     from pytenet_b200.sectors import HeffSectorPlan
+    from pytenet_b200.sector_packed import PackedHeffPlan
     qsite, qb, wbulk, _, _ = ham._fermi_hubbard_bulk(1.0, 4.0, 0.0)
     qsite = np.array(qsite); qb = np.array(qb)
     d1 = len(qsite)
@@ -110,26 +112,60 @@ def block_sparse_block(torch, ptb, device, time_ms, D=2048):
     l = crand(D, 6, D); ptb.enforce_qsparsity(l, [q, qb, -q])
     r = crand(D, 6, D); ptb.enforce_qsparsity(r, [q, qb, -q])
     w = torch.from_numpy(w2).to(device)
-    plan = HeffSectorPlan(q, qs2, q, qb, qb, cplx=True)
     dense = ptb.apply_local_hamiltonian(a, w, l, r)
-    banded = plan.apply(a, w, l, r)
-    err = (torch.linalg.norm(banded - dense) / torch.linalg.norm(dense)).item()
     ms_d = time_ms(lambda: ptb.apply_local_hamiltonian(a, w, l, r), reps=2)
-    ms_b = time_ms(lambda: plan.apply(a, w, l, r), reps=5)
     fa = f_alg(D, d1 * d1, 6)
+    # ---- round-1 path: banded / segmented GEMMs over the dense layout ----
+    plan = HeffSectorPlan(q, qs2, q, qb, qb, cplx=True)
+    banded = plan.apply(a, w, l, r)
+    err_b = (torch.linalg.norm(banded - dense) / torch.linalg.norm(dense)).item()
+    ms_b = time_ms(lambda: plan.apply(a, w, l, r), reps=5)
     fc = plan.flop_counts(nnz_w=int(np.count_nonzero(w2)))
-    t1_bytes = 16.0 * D * d1 * d1 * 6 * D
-    extra = {"flops_visited": fc["visited"], "flops_exact_sector_blocks": fc["exact"], "flops_w_step": fc["w_step"],
-             "tflops_exec_banded_path": (fc["visited"] + fc["w_step"]) / ms_b / 1e9,
-             "note": "dense-layout intermediates: t1 and t2 (%.1f GB each) are written and read once per matvec "
-                     "(>= %.1f ms at the HBM peak); the GEMMs visit whole k-tiles of whole output tiles "
-                     "(flops_visited), a sector-packed layout would execute flops_exact_sector_blocks"
-                     % (t1_bytes / 1e9, 4 * t1_bytes / 6.5e12 * 1e3)}
-    return {**extra, "workload": f"two-site Fermi-Hubbard heff matvec a ({D},16,{D}), h2 (6,16,16,6), {int((sizes > 0).sum())} "
+    del banded
+    # ---- sector-packed grouped GEMM ----
+    pplan = PackedHeffPlan(q, qs2, q, qb, qb, cplx=True)
+    op = pplan.bind(w, l, r)
+    x = op.pack(a)
+    y = op(x)
+    err_p = (torch.linalg.norm(op.unpack(y) - dense) / torch.linalg.norm(dense)).item()
+    del dense
+    ms_p = time_ms(lambda: op(x), reps=10)
+    pfc = pplan.flop_counts()
+    lib = op.lib
+    st = torch.cuda.current_stream().cuda_stream
+    n1, n3 = len(pplan.tiles1_host), len(pplan.tiles3_host)
+    ms_g1 = time_ms(lambda: lib.ptb_gemm_grouped(op.dt, x.data_ptr(), op.rb.data_ptr(), op.t1.data_ptr(),
+                                                 op.tabs["tiles1"].data_ptr(), n1, st), reps=10)
+    ms_w = time_ms(lambda: op.wtab.run(lib, op.dt, op.t1, op.t2, st), reps=10)
+    ms_g3 = time_ms(lambda: lib.ptb_gemm_grouped(op.dt, op.t2.data_ptr(), op.lp.data_ptr(), op.o.data_ptr(),
+                                                 op.tabs["tiles3"].data_ptr(), n3, st), reps=10)
+    ms_rp = time_ms(lambda: op.tabs["repack"].run(lib, op.dt, op.o, y, st), reps=10)
+    ms_pack = time_ms(lambda: op.pack(a), reps=3)
+    ms_unpack = time_ms(lambda: op.unpack(y), reps=3)
+    # one Lanczos iteration's vector work on the packed vs the dense vector (HBM-bound, 5 passes: krylov.cu)
+    es = 16
+    packed = {
+        "ms_per_matvec": ms_p, "rel_diff_vs_dense_device_matvec": err_p,
+        "flops_exact_sector_blocks": pfc["exact"], "flops_visited": pfc["visited"],
+        "visited_over_exact": pfc["visited"] / pfc["exact"],
+        "tflops_exact": pfc["exact"] / ms_p / 1e9, "frac_of_fp64_peak_on_exact_flops": pfc["exact"] / ms_p / 1e9 / peak_tflops,
+        "tflops_visited_gemm_kernels": pfc["visited"] / (ms_g1 + ms_g3) / 1e9,
+        "gemm_kernels_frac_of_fp64_peak": pfc["visited"] / (ms_g1 + ms_g3) / 1e9 / peak_tflops,
+        "kernel_ms": {"grouped_gemm_step1": ms_g1, "w_gather": ms_w, "grouped_gemm_step3": ms_g3, "repack": ms_rp},
+        "tiles": {"step1": n1, "step3": n3},
+        "once_per_lanczos_run_ms": {"pack": ms_pack, "unpack": ms_unpack},
+        "packed_vector_elements": pplan.nX, "dense_vector_elements": D * d1 * d1 * D,
+        "intermediate_bytes": {"t1": pplan.nT1 * es, "t2": pplan.nT2 * es, "dense_layout_t1": 16.0 * D * d1 * d1 * 6 * D},
+        "speedup_vs_dense": ms_d / ms_p, "speedup_vs_banded_round1": ms_b / ms_p,
+    }
+    return {"workload": f"two-site Fermi-Hubbard heff matvec a ({D},16,{D}), h2 (6,16,16,6), {int((sizes > 0).sum())} "
                         f"(N,Sz) sectors (Gaussian size profile, max {int(sizes.max())})",
-            "tensor_fill": float((a != 0).double().mean().item()), "ms_dense": ms_d, "ms_sector_banded": ms_b,
-            "speedup": ms_d / ms_b, "gflops_alg_dense_path": fa / ms_d / 1e6, "gflops_alg_banded_path": fa / ms_b / 1e6,
-            "rel_diff_banded_vs_dense": err, "k_tile_visit_fraction": list(plan.visit_fraction)}
+            "tensor_fill": float((a != 0).double().mean().item()), "ms_dense": ms_d, "gflops_alg_dense_path": fa / ms_d / 1e6,
+            "sector_packed": packed,
+            "banded_round1": {"ms_per_matvec": ms_b, "rel_diff_vs_dense": err_b, "flops_visited": fc["visited"],
+                              "flops_exact_sector_blocks": fc["exact"], "visited_over_exact": fc["visited"] / fc["exact"],
+                              "tflops_exact": fc["exact"] / ms_b / 1e9, "speedup_vs_dense": ms_d / ms_b},
+            "gflops_alg_packed_path": fa / ms_p / 1e6}
 
 
 # ----------------------------------------------------------------------------------------
@@ -777,7 +813,7 @@ def run_ours(args):
     del ad, wd, ld, rd, cd
     block_sparse = None
     if os.environ.get("PTB_BENCH_SKIP_SECTORS") != "1":
-        block_sparse = block_sparse_block(torch, ptb, device, time_ms)
+        block_sparse = block_sparse_block(torch, ptb, device, time_ms, peak)
     sweeps = None
     if world == 1 and os.environ.get("PTB_BENCH_SKIP_SWEEPS") != "1":
         del a, l, r, out

@@ -337,6 +337,51 @@ int ptb_bond_lanczos(int dtype, const void* c, const void* l, const void* r, int
                      void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Sector-packed block-sparse path (BASELINE config 3: quantum-number sectors as a device-side grouped GEMM)
+ *   sector structure: pytenet/block_sparse_util.py:47-53 (sparsity rule), :151-169 (sector order);
+ *   contraction: pytenet/chain_ops.py:237-279.
+ * With bonds grouped by sector, `a`, `l`, `r` consist of dense blocks.  pytenet_b200/sector_packed.py packs
+ * them so that the three steps become
+ *   (1) per right sector beta:   T1_beta (M x N) = AT_beta^T (M x n_beta) RB_beta (n_beta x N)
+ *   (2) T2 = W . T1 as block gathers with the non-zero MPO entries as coefficients
+ *   (3) per left sector alpha':  O_alpha' (N' x n_alpha') = T2_alpha'^T (N' x K') LP_alpha' (K' x n_alpha')
+ * -- per group two large stacked extents and one sector-sized one, no structural zero stored or multiplied.
+ *
+ * ptb_gemm_grouped: one launch over `ntiles` independent output tiles (device table): C(m x n) (+)= A^T B with A
+ * stored k x m (element (k,m) at a[a_off + k*lda + m]), B stored k x n, C row-major; a_off / b_off / c_off are ELEMENT
+ * offsets from the three base pointers to the tile's origin (so one table serves any buffers of the same layout);
+ * m <= 128, n <= 64 (complex128) / 128 (float64) = ptb_gemm_tile_shape; k >= 1.  The persistent CTAs take the
+ * tiles round-robin in table order (sort by decreasing k).  complex128: any extents; float64: m, n, lda, ldb and
+ * the offsets must be even (16-byte rows).
+ *
+ * ptb_block_gather: dst chunk (rows x cols at dst + dst_off, leading dimension dst_ld) = sum over its terms of
+ * coef * src[src_off + r*src_rs + c*src_cs]; `work` lists {chunk, first row, number of rows, 0} per CTA.  Serves the
+ * W step (coefficients = MPO entries), the packing of a / l / r and the unpacking of the result (one term, coef 1,
+ * strides express transposition).  coef_im is ignored for float64 data.
+ * ------------------------------------------------------------------------- */
+typedef struct ptb_group_tile {
+    int64_t a_off, b_off, c_off;
+    int32_t lda, ldb, ldc;
+    int32_t m, n, k;
+    int32_t accumulate;
+    int32_t reserved[3];
+} ptb_group_tile;                       /* 64 bytes */
+int ptb_gemm_grouped(int dtype, const void* a, const void* b, void* c, const ptb_group_tile* tiles, int ntiles,
+                     void* stream);
+
+typedef struct ptb_gather_chunk {
+    int64_t dst_off;
+    int32_t dst_ld, rows, cols, term_begin, term_end, reserved;
+} ptb_gather_chunk;                     /* 32 bytes */
+typedef struct ptb_gather_term {
+    int64_t src_off;
+    int32_t src_rs, src_cs;
+    double coef_re, coef_im;
+} ptb_gather_term;                      /* 32 bytes */
+int ptb_block_gather(int dtype, const void* src, void* dst, const ptb_gather_chunk* chunks,
+                     const ptb_gather_term* terms, const int32_t* work, int nwork, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Diagnostics: register-resident DMMA.8x8x4 (use_dmma != 0) or DFMA loop on
  * `blocks` CTAs x 256 threads, to measure the FP64 pipe peak that the roofline
  * fractions are quoted against.  `out`: blocks*256 device doubles; *flops

@@ -73,6 +73,8 @@ SIGNATURES = {
     "ptb_block_qr": (_int, [_int, _ptr, _i64, _int, _ptr, _int, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr]),
     "ptb_block_svd_max_block_bytes": (_sz, []),
     "ptb_block_svd": (_int, [_int, _ptr, _i64, _int, _ptr, _int, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr]),
+    "ptb_gemm_grouped": (_int, [_int, _ptr, _ptr, _ptr, _ptr, _int, _ptr]),
+    "ptb_block_gather": (_int, [_int, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _ptr]),
     "ptb_probe_fp64_pipe": (_int, [_int, _int, _int, _ptr, ctypes.POINTER(ctypes.c_double), _ptr]),
 }
 

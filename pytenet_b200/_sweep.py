@@ -16,6 +16,7 @@ from . import _device as dev
 from . import _lib
 from ._prof import region
 from .sectors import HeffSectorPlan, EnvSectorPlan, BondSectorPlan
+from .sector_packed import PackedHeffPlan
 from .block_sparse_util import is_qsparse
 from .chain_ops import (apply_local_hamiltonian, apply_local_bond_contraction,
                         compute_right_operator_blocks, contraction_operator_step_left,
@@ -42,6 +43,7 @@ def prepare_environments(hamiltonian, psi):
 # non-trivial and the bonds are large enough for whole tiles to be skipped; "1" forces it, "0" disables.
 _SECTOR_MODE = os.environ.get("PYTENET_B200_SECTORS", "auto")
 _SECTOR_MIN_BOND = 256
+_PACKED = os.environ.get("PYTENET_B200_PACKED", "1") != "0"
 
 
 # Plans depend on the quantum numbers only.  Sweeps revisit the same bonds (every time step of TDVP, every sweep of
@@ -72,6 +74,12 @@ def sector_plan(ql, qs, qr, qwl, qwr, like, *others):
     if not (np.any(ql) or np.any(qr) or np.any(qs) or np.any(qwl) or np.any(qwr)):
         return None
     cplx = True if like is None else dev.any_complex(like, *[t for t in others if isinstance(t, torch.Tensor)])
+    if _PACKED and cplx:
+        # sector-packed grouped GEMM (sector_packed.py) whenever the bonds are grouped by sector -- every bond a
+        # sweep has orthonormalised is; else the banded work lists over the dense layout (sectors.py)
+        plan = _cached_plan(PackedHeffPlan, cplx, ql, qs, qr, qwl, qwr)
+        if plan.supported:
+            return plan
     return _cached_plan(HeffSectorPlan, cplx, ql, qs, qr, qwl, qwr)
 
 
@@ -189,7 +197,24 @@ class BondOperator:
         return True
 
 
+def _packed(plan, w, l, r, a):
+    """(operator, packed start vector) when `plan` is a sector-packed plan that fits the operands, else None."""
+    if not isinstance(plan, PackedHeffPlan):
+        return None
+    if not all(isinstance(t, torch.Tensor) and t.is_cuda for t in (w, l, r, a)):
+        return None
+    Dl, d, Dr, cl, cr = plan.dims
+    if (tuple(a.shape) != (Dl, d, Dr) or tuple(w.shape) != (cl, d, d, cr) or tuple(l.shape) != (Dl, cl, Dl)
+            or tuple(r.shape) != (Dr, cr, Dr) or w.dtype not in (dev.F64, dev.C128)):
+        return None
+    op = plan.bind(w, l, r)
+    return op, op.pack(a)
+
+
 def _heff(w, l, r, shape, plan):
+    if isinstance(plan, PackedHeffPlan):
+        op = plan.bind(w, l, r)
+        return lambda x: op.apply_dense(x.reshape(shape)).reshape(-1)        # dense-vector form (fallback only)
     if plan is not None:
         def matvec(x):
             if x.dtype.is_complex != plan.cplx:          # a real state turned complex (or vice versa)
@@ -203,6 +228,11 @@ def local_hamiltonian_step(l, r, w, a, dt, numiter: int, plan=None):
     """exp(-dt H_eff) a for the one- or two-site effective Hamiltonian (tdvp.py:223-229)."""
     shape = tuple(a.shape)
     with region("lanczos"):
+        pk = _packed(plan, w, l, r, a)
+        if pk is not None:
+            # the whole Krylov run lives in the packed space: pack once, unpack the result
+            op, xp = pk
+            return op.unpack(expm_krylov(op, xp, -dt, numiter, hermitian=True))
         return expm_krylov(_heff(w, l, r, shape, plan), a.reshape(-1), -dt, numiter, hermitian=True).reshape(shape)
 
 
@@ -223,5 +253,10 @@ def minimize_local_energy(w, l, r, a_start, numiter: int, plan=None):
     """Lowest Ritz pair of the local effective Hamiltonian (dmrg.py:181-189)."""
     shape = tuple(a_start.shape)
     with region("lanczos"):
+        pk = _packed(plan, w, l, r, a_start)
+        if pk is not None:
+            op, xp = pk
+            ev, u_ritz = eigh_krylov(op, xp, numiter, 1)
+            return ev[0], op.unpack(dev.dense(u_ritz[:, 0]))
         ev, u_ritz = eigh_krylov(_heff(w, l, r, shape, plan), a_start.reshape(-1), numiter, 1)
         return ev[0], dev.dense(u_ritz[:, 0]).reshape(shape)

@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(256) tail_reduce_kernel(const WsParams p) {
 
 // Sum the split-K partial tiles in fixed order: C[b][m][n] (+)= sum_s part[b][s][m][n]  (doubles; a complex
 // matrix is 2N doubles per row).
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const double* __restrict__ part, double* __restrict__ C,
+static __global__ void __launch_bounds__(256) splitk_reduce_kernel(const double* __restrict__ part, double* __restrict__ C,
                                                             int M, int ND, int64_t ldcD, int64_t sCD, int SK,
                                                             int accumulate) {
     const int64_t per = (int64_t)M * ND;

@@ -103,8 +103,14 @@ def _lanczos_core(afunc, vstart, numiter):
     """Lanczos run + the one device->host transfer of its scalars.
     Returns (nrm, alpha, beta, Vk) with Vk the first k_eff rows of the resident Lanczos-vector buffer."""
     n, V, scal = _lanczos_device(afunc, vstart, numiter)
-    nrm, alpha, beta = _check_scalars(scal.cpu().numpy(), n, numiter)
+    nrm, alpha, beta = _check_scalars(scal.cpu().numpy(), _threshold_length(afunc, n), numiter)
     return nrm, alpha, beta, V[:len(alpha)]
+
+
+def _threshold_length(afunc, n):
+    """Vector length entering the breakdown threshold 100 n eps (krylov.py:44): operators that iterate in a packed
+    space (sector_packed.PackedHeffOperator) name the length of the dense vector they stand for."""
+    return int(getattr(afunc, "ptb_n_threshold", n))
 
 
 # ---- deferred scalar checks: keeps a TDVP sweep free of device->host round trips -----------------------------
@@ -342,7 +348,7 @@ def _expm_device(afunc, x, dt, numiter):
                                    out.data_ptr(), dev.stream_ptr(V.device))
     _lib.check(st, "krylov_expm_apply")
     if _Deferred.depth > 0:
-        _defer(scal, n, numiter)
+        _defer(scal, _threshold_length(afunc, n), numiter)
     else:
-        _check_scalars(scal.cpu().numpy(), n, numiter)
+        _check_scalars(scal.cpu().numpy(), _threshold_length(afunc, n), numiter)
     return out
