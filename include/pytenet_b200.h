@@ -312,6 +312,20 @@ int ptb_block_svd(int dtype, const void* a, int64_t lda, int nsec, const int32_t
                   void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Large dense SVD of a two-site split          pytenet/bond_ops.py:41-54, block_sparse_util.py:294
+ * A (rows x cols, COLUMN-major, leading dimension lda, destroyed) = U diag(s) V^H by cuSOLVER's polar-decomposition
+ * driver (cusolverDnXgesvdp, economy size): u is rows x min (column-major, ldu), v is cols x min (column-major,
+ * ldv; V itself, not V^H), s descending.  A row-major matrix M (m x n) is passed as its transpose (rows = n, cols =
+ * m): then the `u` buffer read row-major is V_M^H and the `v` buffer read row-major is U_M^H.  `info` is a device
+ * int, `err_sigma` a host double (0 when the result is accurate to working precision).  Workspaces as reported
+ * by ptb_svd_polar_workspace_bytes (device and host part).  cuSOLVER is resolved at run time (dlopen).
+ * ------------------------------------------------------------------------- */
+int ptb_svd_polar_workspace_bytes(int dtype, int64_t rows, int64_t cols, size_t* device_bytes, size_t* host_bytes);
+int ptb_svd_polar(int dtype, int64_t rows, int64_t cols, void* a, int64_t lda, double* s, void* u, int64_t ldu, void* v,
+                  int64_t ldv, void* device_ws, size_t device_bytes, void* host_ws, size_t host_bytes, int* info,
+                  double* err_sigma, void* stream);
+
+/* ---------------------------------------------------------------------------
  * A whole Lanczos run on the local effective Hamiltonian in ONE call
  *   pytenet/krylov.py:12-57 driven by the closures tdvp.py:223-229 (site), tdvp.py:232-238 (bond),
  *   dmrg.py:181-189.

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpytenet_b200.so")
-SOURCES = ["block_qr.cu", "block_svd.cu", "chain_ops.cu", "heff_small.cu", "host_entry.cu", "krylov.cu", "lanczos_heff.cu", "sector_packed.cu", "wapply.cu", "probe.cu"]
+SOURCES = ["block_qr.cu", "block_svd.cu", "chain_ops.cu", "dense_svd.cu", "heff_small.cu", "host_entry.cu", "krylov.cu", "lanczos_heff.cu", "sector_packed.cu", "wapply.cu", "probe.cu"]
 
 
 def _dependencies():
@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

@@ -75,6 +75,9 @@ SIGNATURES = {
     "ptb_block_svd": (_int, [_int, _ptr, _i64, _int, _ptr, _int, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr]),
     "ptb_gemm_grouped": (_int, [_int, _ptr, _ptr, _ptr, _ptr, _int, _ptr]),
     "ptb_block_gather": (_int, [_int, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _ptr]),
+    "ptb_svd_polar_workspace_bytes": (_int, [_int, _i64, _i64, ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
+    "ptb_svd_polar": (_int, [_int, _i64, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _sz, _ptr, _sz, _ptr,
+                             ctypes.POINTER(ctypes.c_double), _ptr]),
     "ptb_probe_fp64_pipe": (_int, [_int, _int, _int, _ptr, ctypes.POINTER(ctypes.c_double), _ptr]),
 }
 
