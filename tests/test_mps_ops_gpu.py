@@ -178,3 +178,33 @@ def test_batched_sector_svd(cuda_lib, cplx):
     for tol in (0.0, 1e-20, 1e-10, 1e-3):
         assert np.array_equal(ptb.retained_bond_indices(gs, tol), ob.retained_bond_indices(ws, tol)), tol
     assert len(ptb.retained_bond_indices(gs, 0.0)) == len(ws)
+
+
+@pytest.mark.parametrize("shape,cplx", [((1024, 1024), True), ((900, 1300), False), ((1500, 800), True)])
+def test_dense_svd_polar_driver(cuda_lib, shape, cplx):
+    """block_sparse_util.dense_svd on large blocks (cuSOLVER's polar-decomposition driver through ptb_svd_polar):
+    singular values equal LAPACK's to 1e-13 of the largest -- also for a spectrum graded over ten decades --, the
+    factors are isometries and reconstruct the matrix; square, wide and tall; complex128 and float64."""
+    from pytenet_b200.block_sparse_util import dense_svd, _POLAR_MIN
+    assert min(shape) >= _POLAR_MIN
+    rng = np.random.default_rng(sum(shape) + int(cplx))
+    m, n = shape
+    k = min(m, n)
+    a = rng.normal(size=shape) + (1j * rng.normal(size=shape) if cplx else 0)
+    for graded in (False, True):
+        if graded:
+            # a = U diag(sigma) V^H with sigma from 1 down to 1e-10
+            qa, _ = np.linalg.qr(a if m >= n else a.conj().T)
+            qb, _ = np.linalg.qr(rng.normal(size=(k, k)) + (1j * rng.normal(size=(k, k)) if cplx else 0))
+            sig = np.logspace(0, -10, k)
+            a = (qa * sig) @ qb.conj().T
+            if m < n:
+                a = a.conj().T
+        u, s, vh = dense_svd(torch.from_numpy(np.ascontiguousarray(a)).cuda())
+        u, s, vh = u.resolve_conj().cpu().numpy(), s.cpu().numpy(), vh.resolve_conj().cpu().numpy()
+        ws = np.linalg.svd(a, compute_uv=False)
+        assert u.shape == (m, k) and vh.shape == (k, n)
+        assert np.max(np.abs(s - ws)) < 1e-13 * ws[0], graded
+        assert np.all(np.diff(s) <= 1e-15 * ws[0])
+        assert rel((u * s) @ vh, a) < 1e-13
+        assert rel(u.conj().T @ u, np.eye(k)) < 1e-12 and rel(vh @ vh.conj().T, np.eye(k)) < 1e-12
