@@ -63,11 +63,16 @@ def _forbidden_mask(qnums, device):
     return total != 0
 
 
+_CAPTURING = False      # set while a sweep step is captured into a CUDA graph (tdvp._StepGraph)
+
+
 def is_qsparse(a, qnums):
     """True iff `a` vanishes wherever the quantum numbers do not sum to zero (:47-53)."""
     if isinstance(a, torch.Tensor) and a.is_cuda:
         if all(not np.any(np.asarray(q)) for q in qnums):
             return True                      # all quantum numbers zero: nothing is forbidden
+        if _CAPTURING:
+            return True                      # a device->host read cannot be captured; the eager steps checked it
         mask = _forbidden_mask(qnums, a.device)
         return not bool(torch.any((a != 0) & mask).item())         # one fused pass, no boolean gather
     mask = qnumber_outer_sum(qnums) != 0

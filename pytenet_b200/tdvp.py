@@ -8,6 +8,10 @@ with Lanczos-based local exponentials.  Every tensor (state, environments,
 two-site MPO tensors, Lanczos vectors) stays on the GPU; per local problem one
 small device->host copy returns the Lanczos coefficients.
 """
+import os
+
+import numpy as np
+
 from . import _device as dev
 from .mps import MPS, mps_merge_tensor_pair, mps_split_tensor_svd
 from .mpo import MPO, mpo_merge_tensor_pair
@@ -18,6 +22,77 @@ from .krylov import defer_checks
 from ._prof import region
 
 __all__ = ["tdvp_singlesite", "tdvp_twosite"]
+
+
+# CUDA graphs for the launch-latency regime (README config: D <= 28): a single-site TDVP
+# time step is a fixed sequence of ~400 small kernels with no host decision in between (bond dimensions cannot
+# change, the tridiagonal problems are solved on the device, breakdown checks are deferred), so from the third
+# time step on the whole step is ONE graph launch.  "auto": when every bond is at most _GRAPH_MAX_BOND.
+_GRAPHS = os.environ.get("PYTENET_B200_GRAPHS", "auto")
+_GRAPH_MAX_BOND = 192
+_GRAPH_MIN_STEPS = 4
+
+
+class _StepGraph:
+    """One symmetric single-site TDVP time step captured as a CUDA graph.
+
+    The graph reads the state (site tensors, environment blocks) from the tensors the Python objects held at
+    capture time, runs the step, and copies the results back into those same tensors as its last nodes -- so the
+    state lives at fixed addresses and `replay()` advances it by one time step.  Scalars of the Lanczos runs land in
+    page-locked slots owned by the graph and are checked after every replay (same warnings / assertions as the
+    eager path)."""
+
+    def __init__(self, psi, lblocks, rblocks, one_step):
+        import torch
+        from . import krylov
+        from . import block_sparse_util as bsu
+        self.ok = False
+        a0, l0, r0 = list(psi.a), list(lblocks), list(rblocks)
+        q0 = [np.array(q) for q in psi.qbonds]
+        krylov._flush_deferred()             # examine what the eager steps left; the ring is then empty
+        meta0 = len(krylov._Deferred.meta)
+        graph = torch.cuda.CUDAGraph()
+        try:
+            bsu._CAPTURING = True
+            with torch.cuda.graph(graph):
+                one_step()
+                for dst, src in zip(a0 + l0 + r0, list(psi.a) + list(lblocks) + list(rblocks)):
+                    if dst is src:
+                        continue
+                    if dst.shape != src.shape or dst.dtype != src.dtype:
+                        raise RuntimeError("state layout changed during the time step")
+                    dst.copy_(src)
+            same_q = all(np.array_equal(x, y) for x, y in zip(q0, psi.qbonds))
+        except Exception:                    # anything not capturable: keep running eagerly
+            same_q = False
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+        finally:
+            bsu._CAPTURING = False
+        # the capture executed nothing: the state is still the one before the step, held by a0 / l0 / r0
+        psi.a[:] = a0
+        lblocks[:] = l0
+        rblocks[:] = r0
+        self.meta = krylov._Deferred.meta[meta0:]
+        self.slot0 = meta0
+        del krylov._Deferred.meta[meta0:]
+        if not same_q:
+            psi.qbonds[:] = q0
+            return
+        self.graph = graph
+        self.ok = True
+
+    def replay(self):
+        import torch
+        from . import krylov
+        self.graph.replay()
+        if self.meta:
+            torch.cuda.current_stream().synchronize()
+            host = krylov._Deferred.ring.numpy()
+            for i, (n, numiter) in enumerate(self.meta):
+                krylov._check_scalars(host[self.slot0 + i], n, numiter)
 
 
 @defer_checks
@@ -44,7 +119,7 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
         return sector_plan(psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], qh[i], qh[i + 1], psi.a[i],
                            lblocks[i], rblocks[i], ham[i])
 
-    for _ in range(numsteps):
+    def one_step():
         # left -> right: half step on each site, backward half step on each bond (tdvp.py:68-84)
         for i in range(nsites - 1):
             psi.a[i] = local_hamiltonian_step(lblocks[i], rblocks[i], ham[i], psi.a[i], 0.5 * dt, k, site_plan(i))
@@ -87,6 +162,32 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
                     tuple(prv.shape[:2]) + (c.shape[1],))
             psi.a[i - 1] = local_hamiltonian_step(
                 lblocks[i - 1], rblocks[i - 1], ham[i - 1], psi.a[i - 1], 0.5 * dt, k, site_plan(i - 1))
+
+    def signature():
+        return tuple((tuple(t.shape), t.dtype) for t in psi.a)
+
+    use_graph = (_GRAPHS == "1" or (_GRAPHS == "auto" and numsteps >= _GRAPH_MIN_STEPS
+                                     and max(psi.bond_dims) <= _GRAPH_MAX_BOND))
+    use_graph = use_graph and numiter_lanczos <= 64 and all(t.is_cuda for t in psi.a)
+    graph = None
+    prev_sig = None
+    step = 0
+    while step < numsteps:
+        if graph is not None:
+            graph.replay()
+            step += 1
+            continue
+        sig = signature()
+        if use_graph and step >= 2 and sig == prev_sig and numsteps - step >= 2:
+            # two eager steps have left shapes and dtypes unchanged: capture the next step and replay it
+            cand = _StepGraph(psi, lblocks, rblocks, one_step)
+            if cand.ok:
+                graph = cand
+                continue
+            use_graph = False
+        prev_sig = sig
+        one_step()
+        step += 1
 
     return nrm
 

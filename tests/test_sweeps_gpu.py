@@ -50,6 +50,37 @@ def test_tdvp_readme_config(cuda_lib, golden_dir):
     assert rel(psi.to_vector(), z["two/vec"]) < 1e-9
 
 
+@pytest.mark.parametrize("fixture,steps_key", [("tdvp_xxz_L10.npz", "nsteps"), ("tdvp_xxz_qnum_L8.npz", "nsteps")])
+def test_tdvp_singlesite_cuda_graph_equals_eager(cuda_lib, golden_dir, monkeypatch, fixture, steps_key):
+    """Launch-latency regime: from the third time step on `tdvp_singlesite` replays one captured CUDA graph per time
+    step.  Same kernels in the same order: the final state is bit-identical to the eager run, equals the reference
+    fixture, and the graph really was used (with and without quantum numbers)."""
+    import pytenet_b200 as ptb
+    from pytenet_b200 import tdvp
+    z = np.load(os.path.join(golden_dir, fixture))
+    h, n = load_mpo(ptb, z)
+    k = int(z["k"]) if "k" in z else 5
+    nsteps = int(z[steps_key])
+    used = []
+    real_init = tdvp._StepGraph.__init__
+
+    def spy(self, *a, **kw):
+        real_init(self, *a, **kw)
+        used.append(self.ok)
+    monkeypatch.setattr(tdvp._StepGraph, "__init__", spy)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setattr(tdvp, "_GRAPHS", mode)
+        psi = load_mps(ptb, z, "psi0", n)
+        nrm = ptb.tdvp_singlesite(h, psi, complex(z["dt"]), nsteps, numiter_lanczos=k)
+        out[mode] = (nrm, psi.to_vector(), [np.array(q) for q in psi.qbonds])
+    assert used == [True], "the graph path must have been taken exactly once (mode 1)"
+    assert out["0"][0] == out["1"][0]
+    assert np.array_equal(out["0"][1], out["1"][1])
+    assert all(np.array_equal(x, y) for x, y in zip(out["0"][2], out["1"][2]))
+    assert rel(out["1"][1], z["single/vec"]) < 1e-9
+
+
 def test_tdvp_quantum_numbers_bit_exact_sectors(cuda_lib, golden_dir):
     import pytenet_b200 as ptb
     z = np.load(os.path.join(golden_dir, "tdvp_xxz_qnum_L8.npz"))
