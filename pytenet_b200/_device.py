@@ -263,17 +263,10 @@ def bind_host_to_gpu_numa_node(device_index=None):
     import os
     try:
         idx = torch.cuda.current_device() if device_index is None else int(device_index)
-        bus = torch.cuda.get_device_properties(idx).pci_bus_id.lower() if hasattr(
-            torch.cuda.get_device_properties(idx), "pci_bus_id") else None
-        if bus is None:
-            import ctypes
-            buf = ctypes.create_string_buffer(32)
-            rt = ctypes.CDLL("libcudart.so.12")
-            if rt.cudaDeviceGetPCIBusId(buf, 32, idx) != 0:
-                return None
-            bus = buf.value.decode().lower()
-        if len(bus.split(":")[0]) == 8:           # CUDA prints an 8-digit domain, sysfs uses 4
-            bus = bus[4:]
+        props = torch.cuda.get_device_properties(idx)
+        # torch exposes the PCI address as three integers (domain, bus, device); sysfs wants dddd:bb:dd.f
+        bus = "%04x:%02x:%02x.0" % (int(getattr(props, "pci_domain_id", 0)), int(props.pci_bus_id),
+                                    int(props.pci_device_id))
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
         if node < 0:
             return None
