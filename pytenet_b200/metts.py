@@ -64,13 +64,14 @@ def collapse_random_cps(psi: MPS, rng: np.random.Generator):
 
 
 def metts_energy_samples(hamiltonian, beta, nsamples, rng, numsteps=20, numiter_lanczos=10, tol_split=1e-10,
-                         start=None, observable=None):
+                         start=None, observable=None, stats=None):
     """
     Run a chain of `nsamples` METTS and return the per-sample energies <phi|H|phi> (or
     <phi|observable|phi> when an MPO `observable` is given) as a NumPy array.
 
     Each sample: |phi> = exp(-beta H / 2)|cps> / norm  by `numsteps` two-site TDVP steps with real time
-    step beta / (2 numsteps), then the next |cps> is drawn by `collapse_random_cps(phi)`.
+    step beta / (2 numsteps), then the next |cps> is drawn by `collapse_random_cps(phi)`.  A dict passed as
+    `stats` collects the realised bond dimensions per sample.
     """
     nsites = hamiltonian.nsites
     if start is None:
@@ -82,6 +83,9 @@ def metts_energy_samples(hamiltonian, beta, nsamples, rng, numsteps=20, numiter_
         phi = product_state_mps(cps, device=hamiltonian.device)
         tdvp_twosite(hamiltonian, phi, 0.5 * beta / numsteps, numsteps, numiter_lanczos=numiter_lanczos,
                      tol_split=tol_split)
+        if stats is not None:                    # realised bond dimensions of the thermal state |phi>
+            stats.setdefault("max_bond", []).append(int(max(phi.bond_dims)))
+            stats.setdefault("mean_bond", []).append(float(np.mean(phi.bond_dims)))
         phi.orthonormalize(mode="left")          # normalise: drop the norm accumulated by exp(-beta H / 2)
         values[n] = mpo_average(phi, op)
         cps = collapse_random_cps(phi, rng)

@@ -33,22 +33,27 @@ rng = np.random.default_rng(1000 + rank)
 ptb.metts_energy_samples(h, args.beta, 1, rng, numsteps=args.steps, numiter_lanczos=args.k, tol_split=args.tol)  # warm-up
 torch.cuda.synchronize()
 t0 = time.perf_counter()
+stats = {}
 vals = ptb.metts_energy_samples(h, args.beta, args.samples, rng, numsteps=args.steps, numiter_lanczos=args.k,
-                                tol_split=args.tol)
+                                tol_split=args.tol, stats=stats)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 allv = [None] * world
 if world > 1:
-    dist.all_gather_object(allv, (vals.real.tolist(), dt))
+    dist.all_gather_object(allv, (vals.real.tolist(), dt, stats))
 else:
-    allv = [(vals.real.tolist(), dt)]
+    allv = [(vals.real.tolist(), dt, stats)]
 if rank == 0:
-    e = np.concatenate([np.array(v) for v, _ in allv])
-    tmax = max(t for _, t in allv)
+    e = np.concatenate([np.array(v) for v, _, _ in allv])
+    tmax = max(t for _, t, _ in allv)
+    mb = np.concatenate([np.array(st["max_bond"]) for _, _, st in allv])
     print(json.dumps({"metts": {"L": args.L, "beta": args.beta, "n_gpus": world, "samples_per_gpu": args.samples,
                                 "seconds": tmax, "samples_per_s_total": len(e) / tmax,
                                 "energy_per_site_mean": float(e.mean() / args.L),
                                 "energy_per_site_stderr": float(e.std() / np.sqrt(len(e)) / args.L),
+                                "samples_per_s_per_gpu": len(e) / tmax / world,
+                                "realised_max_bond_dim": {"max": int(mb.max()), "median": float(np.median(mb)),
+                                                          "min": int(mb.min())},
                                 "tdvp_steps": args.steps, "k": args.k, "tol_split": args.tol}}))
 if world > 1:
     dist.destroy_process_group()
