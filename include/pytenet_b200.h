@@ -117,16 +117,6 @@ int ptb_gemm_segmented(int dtype, int conj_b, int64_t m, int64_t n, int64_t k, c
                        const int64_t* sel_off, void* stream);
 
 
-/* Fused GEMM + all-gather: C = op(A) op(B) is written to n_dst (1..8) output buffers of identical
- * layout in the kernel's epilogue.  c_list is a HOST array of device pointers; entries beyond the
- * first are typically peer-mapped buffers of the other GPUs of the box (CUDA IPC / symmetric
- * memory), so the tiles travel over NVLink while the tensor pipe keeps working.  Used by the
- * MPO-bond-sharded matvec (step 1 on each rank's kappa range lands in every rank's gathered t1).
- * Needs 16-byte operand granularity (always true for complex128). */
-int ptb_gemm_multicast(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k,
-                       const void* a, int64_t lda, const void* b, int64_t ldb, void* const* c_list, int n_dst,
-                       int64_t ldc, void* stream);
-
 /* ptb_gemm with an explicit kernel generation (for A/B measurements and tests; an argument, so the
  * library keeps no process-wide mode -- every other entry point selects automatically):
  *   0 = automatic: warp-specialised TMA/mbarrier kernel when operands meet its 16-byte
@@ -310,6 +300,48 @@ size_t ptb_block_svd_max_block_bytes(void);
 int ptb_block_svd(int dtype, const void* a, int64_t lda, int nsec, const int32_t* meta, int max_work_elems,
                   const int32_t* rowidx, const int32_t* colidx, void* u, int64_t ldu, double* s, void* vh, int64_t ldv,
                   void* stream);
+
+/* ---------------------------------------------------------------------------
+ * MPO-bond-sharded contractions (SURVEY.md 8(b) minimum list, 8(e); BASELINE config 4)
+ *   the sum over MPO-bond index pairs of pytenet/chain_ops.py:237-279 / :282-317 / :60-99 split over the ranks
+ *   of a communicator; see csrc/sharded.cu for the scheme.  One process per GPU.
+ *
+ * ptb_comm: opaque handle around an NCCL communicator (libnccl resolved at run time).  Rank 0 obtains a 128-byte
+ * id with ptb_comm_unique_id and distributes it by any means (MPI, sockets, a file, torch.distributed); every rank
+ * then calls ptb_comm_init on its current device (collective).  comm == NULL everywhere means a single rank.
+ * This handle is the only process-level state of the library; all entries are asynchronous on `stream`.
+ *
+ * Shapes: a (Dl, d_in, Dr); lw (Dl*d_in*P, d_out, Dlp) from ptb_sharded_precontract with
+ * w3[(s, kappa_loc, s'), k] = w[k, s', s, kappa] on this rank's zero-padded range of P = ceil(chi_r / nranks)
+ * right-bond indices and l (Dl, chi_l, Dlp) the FULL left block; r_shard (Dr, P, Drp) the rank's range of the right
+ * block; out (Dlp, d_out, Drp), identical on every rank after the all-reduce.
+ * env_step_left_sharded: b (Dlp, d_out, Drb) the bra tensor; l_next (Dr, P, Drb) = this rank's range of the next
+ * left block -- no communication.  The right-to-left direction applies the same entries to mirrored tensors.
+ * bond contraction: c (Dl, Dr), l_shard (Dl, P, Dlp), r_shard (Dr, P, Drp) ranges of the SAME MPO bond.
+ * ------------------------------------------------------------------------- */
+typedef struct ptb_comm ptb_comm;
+int ptb_comm_unique_id(void* id128);
+int ptb_comm_init(ptb_comm** comm, int nranks, int rank, const void* id128);
+int ptb_comm_destroy(ptb_comm* comm);
+int ptb_comm_info(const ptb_comm* comm, int* nranks, int* rank);
+int ptb_allreduce_sum(ptb_comm* comm, int dtype, void* buf, int64_t count, void* stream);
+int ptb_sharded_precontract(int dtype, int w_is_complex, const void* w3, const void* l, void* lw, int64_t Dl,
+                            int64_t chi_l, int64_t Dlp, int64_t R, void* stream);
+size_t ptb_apply_local_hamiltonian_sharded_workspace_bytes(int dtype, int64_t Dl, int64_t d_in, int64_t Dr, int64_t P,
+                                                           int64_t d_out, int64_t Dlp, int64_t Drp);
+int ptb_apply_local_hamiltonian_sharded(ptb_comm* comm, int dtype, const void* a, const void* lw, const void* r_shard,
+                                        void* out, int64_t Dl, int64_t d_in, int64_t Dr, int64_t P, int64_t d_out,
+                                        int64_t Dlp, int64_t Drp, void* workspace, size_t workspace_bytes,
+                                        void* stream);
+size_t ptb_env_step_left_sharded_workspace_bytes(int dtype, int64_t Dl, int64_t d_in, int64_t P, int64_t Drb);
+int ptb_env_step_left_sharded(int dtype, const void* a, const void* b, const void* lw, void* l_next, int64_t Dl,
+                              int64_t d_in, int64_t Dr, int64_t P, int64_t d_out, int64_t Dlp, int64_t Drb,
+                              void* workspace, size_t workspace_bytes, void* stream);
+size_t ptb_apply_local_bond_contraction_sharded_workspace_bytes(int dtype, int64_t Dl, int64_t P, int64_t Drp);
+int ptb_apply_local_bond_contraction_sharded(ptb_comm* comm, int dtype, const void* c, const void* l_shard,
+                                             const void* r_shard, void* out, int64_t Dl, int64_t Dr, int64_t P,
+                                             int64_t Dlp, int64_t Drp, void* workspace, size_t workspace_bytes,
+                                             void* stream);
 
 /* ---------------------------------------------------------------------------
  * Large dense SVD of a two-site split          pytenet/bond_ops.py:41-54, block_sparse_util.py:294

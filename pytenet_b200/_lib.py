@@ -32,8 +32,6 @@ SIGNATURES = {
     "ptb_gemm_segmented": (_int, [_int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64,
                                   _int, _ptr, _ptr, _ptr, _ptr]),
     "ptb_gemm_tile_shape": (_int, [_int, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
-    "ptb_gemm_multicast": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64,
-                                  ctypes.POINTER(_ptr), _int, _i64, _ptr]),
     "ptb_gemm": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                         _i64, _i64, _i64, _i64, _int, _ptr]),
     "ptb_apply_local_hamiltonian_workspace_bytes": (_sz, [_int] + _DIMS8),
@@ -78,6 +76,19 @@ SIGNATURES = {
     "ptb_svd_polar_workspace_bytes": (_int, [_int, _i64, _i64, ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
     "ptb_svd_polar": (_int, [_int, _i64, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _sz, _ptr, _sz, _ptr,
                              ctypes.POINTER(ctypes.c_double), _ptr]),
+    "ptb_comm_unique_id": (_int, [_ptr]),
+    "ptb_comm_init": (_int, [ctypes.POINTER(_ptr), _int, _int, _ptr]),
+    "ptb_comm_destroy": (_int, [_ptr]),
+    "ptb_comm_info": (_int, [_ptr, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
+    "ptb_allreduce_sum": (_int, [_ptr, _int, _ptr, _i64, _ptr]),
+    "ptb_sharded_precontract": (_int, [_int, _int, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr]),
+    "ptb_apply_local_hamiltonian_sharded_workspace_bytes": (_sz, [_int] + [_i64] * 7),
+    "ptb_apply_local_hamiltonian_sharded": (_int, [_ptr, _int, _ptr, _ptr, _ptr, _ptr] + [_i64] * 7 + [_ptr, _sz, _ptr]),
+    "ptb_env_step_left_sharded_workspace_bytes": (_sz, [_int] + [_i64] * 4),
+    "ptb_env_step_left_sharded": (_int, [_int, _ptr, _ptr, _ptr, _ptr] + [_i64] * 7 + [_ptr, _sz, _ptr]),
+    "ptb_apply_local_bond_contraction_sharded_workspace_bytes": (_sz, [_int] + [_i64] * 3),
+    "ptb_apply_local_bond_contraction_sharded": (_int, [_ptr, _int, _ptr, _ptr, _ptr, _ptr] + [_i64] * 5
+                                                 + [_ptr, _sz, _ptr]),
     "ptb_probe_fp64_pipe": (_int, [_int, _int, _int, _ptr, ctypes.POINTER(ctypes.c_double), _ptr]),
 }
 

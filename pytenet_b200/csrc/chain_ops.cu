@@ -55,7 +55,7 @@ int gemm(int ta, int tb, int cj, int64_t M, int64_t N, int64_t K, const void* A,
     // engine selection (an argument, never process state): 0 = auto (warp-specialised TMA kernel when it
     // applies), 1 = first-generation cp.async kernel only, 2 = warp-specialised kernel required
     if (engine != 1 && K > 0) {
-        const int rc = try_launch_ws<CPLX>(ta, tb, cj, p, st, 0, nullptr, split_k, part_ws, part_ws_bytes);
+        const int rc = try_launch_ws<CPLX>(ta, tb, cj, p, st, split_k, part_ws, part_ws_bytes);
         if (rc != 1) return rc;
         if (engine == 2) return PTB_ERR_ALIGNMENT;
     }
@@ -311,9 +311,9 @@ int ptb_gemm_banded(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
     if (dtype == PTB_COMPLEX128)
-        rc = try_launch_ws<true>(trans_a, trans_b, conj_b, p, st, 0, nullptr, 1, nullptr, 0, ktab);
+        rc = try_launch_ws<true>(trans_a, trans_b, conj_b, p, st, 1, nullptr, 0, ktab);
     else if (dtype == PTB_REAL64)
-        rc = try_launch_ws<false>(trans_a, trans_b, 0, p, st, 0, nullptr, 1, nullptr, 0, ktab);
+        rc = try_launch_ws<false>(trans_a, trans_b, 0, p, st, 1, nullptr, 0, ktab);
     else
         return PTB_ERR_BAD_DTYPE;
     return rc == 1 ? PTB_ERR_ALIGNMENT : rc;
@@ -369,8 +369,8 @@ int ptb_gemm_sector(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, 
         return cplx ? launch_ws_segmented<true>(conj_b, p, st, t->seg_ptr, t->segs, off, t->order)
                     : launch_ws_segmented<false>(0, p, st, t->seg_ptr, t->segs, off, t->order);
     }
-    const int rc = cplx ? try_launch_ws<true>(trans_a, trans_b, conj_b, p, st, 0, nullptr, 1, nullptr, 0, t->ktab, t->order)
-                        : try_launch_ws<false>(trans_a, trans_b, 0, p, st, 0, nullptr, 1, nullptr, 0, t->ktab, t->order);
+    const int rc = cplx ? try_launch_ws<true>(trans_a, trans_b, conj_b, p, st, 1, nullptr, 0, t->ktab, t->order)
+                        : try_launch_ws<false>(trans_a, trans_b, 0, p, st, 1, nullptr, 0, t->ktab, t->order);
     return rc == 1 ? PTB_ERR_ALIGNMENT : rc;
 }
 
@@ -379,36 +379,6 @@ int ptb_gemm_tile_shape(int dtype, int* bm, int* bn, int* bk) {
     if (dtype == PTB_COMPLEX128) { *bm = WsCfg<true>::BM; *bn = WsCfg<true>::BN; *bk = WsCfg<true>::BK; return PTB_OK; }
     if (dtype == PTB_REAL64) { *bm = WsCfg<false>::BM; *bn = WsCfg<false>::BN; *bk = WsCfg<false>::BK; return PTB_OK; }
     return PTB_ERR_BAD_DTYPE;
-}
-
-int ptb_gemm_multicast(int dtype, int trans_a, int trans_b, int conj_b, int64_t m, int64_t n, int64_t k, const void* a,
-                       int64_t lda, const void* b, int64_t ldb, void* const* c_list, int n_dst, int64_t ldc,
-                       void* stream) {
-    if (!a || !b || !c_list || n_dst < 1 || n_dst > 8) return PTB_ERR_BAD_ARG;
-    if (m <= 0 || n <= 0 || k <= 0 || !fits_int({m, n, k})) return PTB_ERR_BAD_ARG;
-    for (int i = 0; i < n_dst; i++)
-        if (!c_list[i]) return PTB_ERR_BAD_ARG;
-    GemmParams p;
-    p.A = static_cast<const double*>(a);
-    p.B = static_cast<const double*>(b);
-    p.C = static_cast<double*>(c_list[0]);
-    p.M = (int)m; p.N = (int)n; p.K = (int)k;
-    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
-    p.sA = p.sB = p.sC = 0;
-    p.batch = 1;
-    p.accumulate = 0;
-    p.tiles_m = p.tiles_n = 0;
-    double* extra[7];
-    for (int i = 1; i < n_dst; i++) extra[i - 1] = static_cast<double*>(c_list[i]);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc;
-    if (dtype == PTB_COMPLEX128)
-        rc = try_launch_ws<true>(trans_a, trans_b, conj_b, p, st, n_dst - 1, extra);
-    else if (dtype == PTB_REAL64)
-        rc = try_launch_ws<false>(trans_a, trans_b, 0, p, st, n_dst - 1, extra);
-    else
-        return PTB_ERR_BAD_DTYPE;
-    return rc == 1 ? PTB_ERR_ALIGNMENT : rc;   // the fused kernel exists only on the TMA engine
 }
 
 size_t ptb_apply_local_hamiltonian_workspace_bytes(int dtype, int64_t Dl, int64_t d_in, int64_t Dr, int64_t chi_l,

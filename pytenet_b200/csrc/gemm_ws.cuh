@@ -64,10 +64,6 @@ struct WsParams {
     int accumulate;
     int tiles_m, tiles_n;
     int batched_a, batched_b;  // 0 when the batch stride is 0 (operand shared by all batches)
-    // fused all-gather: the epilogue also stores every C tile to `n_extra` further base pointers of
-    // identical layout -- peer-mapped buffers of the other GPUs, written over NVLink
-    int n_extra;
-    double* Cx[7];
     // split-K: every output tile is computed by `split_k` work units over disjoint k ranges that write
     // partial tiles to Cpart ([batch][split][M][N], dense); a second kernel sums them in fixed order
     int split_k;
@@ -419,8 +415,7 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
         }
         }   // segments
 
-        // epilogue (overlaps the producer's prefetch of the next tile); with n_extra > 0 the tile is
-        // also written to the peer GPUs' buffers (compute + all-gather in one kernel)
+        // epilogue (overlaps the producer's prefetch of the next tile)
         if (un.dest == 2) {
             // tail unit: the whole BM x BN partial tile goes to its dense buffer (no bounds: the reduction
             // kernel only reads the in-range part)
@@ -445,10 +440,10 @@ gemm_ws_kernel(const WsParams p, const __grid_constant__ CUtensorMap tmA, const 
         const bool partial = un.dest == 1;
         const int64_t ldc_eff = partial ? (int64_t)p.N : p.ldc;
         const bool accum = !partial && p.accumulate == 1;
-        for (int dsti = 0; dsti <= p.n_extra; dsti++) {
+        {
             double* __restrict__ Cg =
                 partial ? p.Cpart + ((int64_t)bz * p.split_k + un.sk) * (int64_t)p.M * p.N * E
-                        : (dsti == 0 ? p.C : p.Cx[dsti - 1]) + (int64_t)bz * p.sC * E;
+                        : p.C + (int64_t)bz * p.sC * E;
 #pragma unroll
             for (int i = 0; i < MT; i++) {
                 const int row = m0 + wm * Cfg::WTM + i * 8 + g;
@@ -633,7 +628,7 @@ static int choose_split_k(long long tiles, int KT, int K, int num_sms) {
 
 template <bool CPLX>
 static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp, cudaStream_t stream,
-                         int n_extra = 0, double* const* extra = nullptr, int split_k = 1, void* part_ws = nullptr,
+                         int split_k = 1, void* part_ws = nullptr,
                          size_t part_ws_bytes = 0, const int32_t* ktab = nullptr, const int32_t* order = nullptr) {
     using Cfg = WsCfg<CPLX>;
     constexpr int E = Cfg::E;
@@ -659,8 +654,6 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     p.tiles_n = (gp.N + Cfg::BN - 1) / Cfg::BN;
     p.batched_a = (gp.sA != 0 && gp.batch > 1) ? 1 : 0;
     p.batched_b = (gp.sB != 0 && gp.batch > 1) ? 1 : 0;
-    p.n_extra = 0;
-    for (int i = 0; i < 7; i++) p.Cx[i] = nullptr;
     p.split_k = 1;
     p.Cpart = nullptr;
     p.tail_split = 1;
@@ -669,7 +662,7 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     p.seg_ptr = nullptr; p.segs = nullptr; p.sel_off = nullptr;
     p.order = order;
     if (ktab != nullptr && (reinterpret_cast<uintptr_t>(ktab) % 8) != 0) return PTB_ERR_ALIGNMENT;
-    if (split_k != 1 && n_extra == 0 && part_ws != nullptr && ktab == nullptr) {
+    if (split_k != 1 && part_ws != nullptr && ktab == nullptr) {
         const int KT = (gp.K + Cfg::BK - 1) / Cfg::BK;
         const int num_sms = device_sm_count();
         int sk = split_k > 1 ? split_k : choose_split_k((long long)p.tiles_m * p.tiles_n * p.batch, KT, gp.K, num_sms);
@@ -695,14 +688,6 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
                 }
             }
         }
-    }
-    if (n_extra > 0) {
-        if (n_extra > 7 || gp.accumulate || !extra) return PTB_ERR_BAD_ARG;
-        for (int i = 0; i < n_extra; i++) {
-            if (!extra[i] || !al16(extra[i])) return PTB_ERR_ALIGNMENT;
-            p.Cx[i] = extra[i];
-        }
-        p.n_extra = n_extra;
     }
     CUtensorMap ta, tb;
     memset(&ta, 0, sizeof(ta));
@@ -745,8 +730,6 @@ static int launch_ws_segmented(int conjB, const GemmParams& gp, cudaStream_t str
     p.tiles_n = (gp.N + Cfg::BN - 1) / Cfg::BN;
     p.batched_a = (gp.sA != 0 && gp.batch > 1) ? 1 : 0;
     p.batched_b = (gp.sB != 0 && gp.batch > 1) ? 1 : 0;
-    p.n_extra = 0;
-    for (int i = 0; i < 7; i++) p.Cx[i] = nullptr;
     p.split_k = 1; p.Cpart = nullptr; p.tail_split = 1; p.tail_begin = 0;
     p.ktab = nullptr;
     p.seg_ptr = seg_ptr;

@@ -55,22 +55,6 @@ class _CudaOps:
         return dev.gemm(a2d, r2d, out=out)
 
     @staticmethod
-    def step1_multicast(a2d, r2d, dst_ptrs):
-        """Fused GEMM + all-gather: the product is stored to every pointer of `dst_ptrs` (this rank's
-        slot in each rank's gathered buffer; peers are reached over NVLink) by the kernel's epilogue."""
-        import ctypes
-        from . import _lib
-        lib = _lib.load()
-        m, k = a2d.shape
-        n = r2d.shape[1]
-        arr = (ctypes.c_void_p * len(dst_ptrs))(*dst_ptrs)
-        cplx = a2d.dtype.is_complex
-        st = lib.ptb_gemm_multicast(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, 0, 0, 0, m, n, k,
-                                    a2d.data_ptr(), k, r2d.data_ptr(), n, arr, len(dst_ptrs), n,
-                                    dev.stream_ptr(a2d.device))
-        _lib.check(st, "ptb_gemm_multicast")
-
-    @staticmethod
     def wapply(wblk, tin, tout, accumulate):
         """tout[i] (+)= wblk @ tin[i]  for all i.  wblk (R_out, R_in) real or complex;
         tin (B, R_in, Drp), tout (B, R_out, Drp) complex128 or float64, dense."""
@@ -133,12 +117,11 @@ class ShardedEffectiveHamiltonian:
     """
 
     def __init__(self, w_blocks, l_shard, r_shard, dims, group=None, ops=None, exchange="auto"):
-        # exchange: "fused"  = step-1 GEMM writes its tiles straight into every rank's gathered buffer
-        #                      (peer memory over NVLink, torch symmetric memory for the mapping);
-        #           "nccl"   = step-1 GEMM followed by an NCCL all-gather;
-        #           "auto"   = fused on CUDA with more than one rank when peer mapping is available
+        # exchange of t1: step-1 GEMM followed by an NCCL all-gather.  (Round 1 also had a GEMM whose epilogue
+        # stored its tiles into every rank's gathered buffer over NVLink; at 8 GPUs it lost to the plain NCCL
+        # all-gather -- 148.2 vs 137.9 ms, the peer stores stalled the DMMA warps -- and both lose to the
+        # all-reduce-only form below (91.4 ms), so it was removed.)
         self.exchange = exchange
-        self._symm = None
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -224,37 +207,9 @@ class ShardedEffectiveHamiltonian:
         n1 = (self.Dl, self.d_in * self.P, self.Drp)
         if self._t1 is None or self._t1.dtype != like.dtype:
             self._t2 = torch.empty((self.Dl, self.kg * self.d_out, self.Drp), dtype=like.dtype, device=like.device)
-            want_fused = (self.exchange in ("auto", "fused") and self.world > 1 and like.is_cuda
-                          and hasattr(self.ops, "step1_multicast"))
-            if want_fused:
-                try:
-                    import torch.distributed._symmetric_memory as symm_mem
-                    grp = self.group if self.group is not None else dist.group.WORLD
-                    # allocated as float64 (complex128 = interleaved pairs) so the peer mapping does
-                    # not depend on complex-dtype support of the symmetric-memory allocator
-                    if like.dtype.is_complex:
-                        raw = symm_mem.empty((self.world,) + n1 + (2,), dtype=torch.float64, device=like.device)
-                        self._gathered = torch.view_as_complex(raw)
-                    else:
-                        raw = symm_mem.empty((self.world,) + n1, dtype=like.dtype, device=like.device)
-                        self._gathered = raw
-                    self._symm = symm_mem.rendezvous(raw, group=grp)
-                    slot = int(np.prod(n1)) * like.element_size()
-                    self._dst_ptrs = [int(self._symm.buffer_ptrs[p]) + self.rank * slot for p in range(self.world)]
-                    # own slot first: it is the kernel's primary output
-                    self._dst_ptrs = [self._dst_ptrs[self.rank]] + [q for i, q in enumerate(self._dst_ptrs)
-                                                                    if i != self.rank]
-                    self._t1 = self._gathered[self.rank]
-                    self.exchange = "fused"
-                except Exception as exc:            # peer mapping unavailable: fall back to the NCCL exchange
-                    if self.exchange == "fused":
-                        raise
-                    self._symm = None
-                    self._exchange_note = f"symmetric memory unavailable ({type(exc).__name__}: {exc})"
-            if self._symm is None:
-                self.exchange = "nccl" if self.world > 1 else "local"
-                self._t1 = torch.empty(n1, dtype=like.dtype, device=like.device)
-                self._gathered = torch.empty((self.world,) + n1, dtype=like.dtype, device=like.device)
+            self.exchange = "nccl" if self.world > 1 else "local"
+            self._t1 = torch.empty(n1, dtype=like.dtype, device=like.device)
+            self._gathered = torch.empty((self.world,) + n1, dtype=like.dtype, device=like.device)
         return self._t1, self._gathered, self._t2
 
     def matvec(self, a):
@@ -265,27 +220,18 @@ class ShardedEffectiveHamiltonian:
             self.l_shard = self.l_shard.to(torch.complex128)
             self.r_shard = self.r_shard.to(torch.complex128)
             self._t1 = self._gathered = self._t2 = None
-            self._symm = None
         a = a.to(self.l_shard.dtype) if a.dtype != self.l_shard.dtype else a
         a = a.contiguous()
         t1, gathered, t2 = self._buffers(a)
         a2d = a.reshape(self.Dl * self.d_in, self.Dr)
         r2d = self.r_shard.reshape(self.Dr, self.P * self.Drp)
-        if self._symm is not None:
-            # step 1 fused with the exchange: tiles of t1_g land in every rank's gathered buffer over
-            # NVLink from the GEMM epilogue; the barrier makes all ranks' contributions visible.
-            # (The all-reduce that ended the previous matvec already ordered this overwrite after every
-            # rank's last read of its gathered buffer.)
-            self.ops.step1_multicast(a2d, r2d, self._dst_ptrs)
-            self._symm.barrier(channel=0)
+        # step 1 on this rank's kappa range:  t1[(i,s),(kappa_loc,j')] = a r_g
+        self.ops.step1(a2d, r2d, t1.reshape(self.Dl * self.d_in, self.P * self.Drp))
+        # exchange: every rank receives all kappa ranges of t1
+        if self.world > 1:
+            dist.all_gather_into_tensor(_flat_real(gathered), _flat_real(t1), group=self.group)
         else:
-            # step 1 on this rank's kappa range:  t1[(i,s),(kappa_loc,j')] = a r_g
-            self.ops.step1(a2d, r2d, t1.reshape(self.Dl * self.d_in, self.P * self.Drp))
-            # exchange: every rank receives all kappa ranges of t1
-            if self.world > 1:
-                dist.all_gather_into_tensor(_flat_real(gathered), _flat_real(t1), group=self.group)
-            else:
-                gathered = t1.reshape((1,) + tuple(t1.shape))
+            gathered = t1.reshape((1,) + tuple(t1.shape))
         # step 2 on this rank's k range, accumulating over the source ranges
         for gp in range(self.world):
             # gathered[gp] is [i, (s, kappa_loc), j'] because t1 rows are (i, s) and columns (kappa_loc, j')

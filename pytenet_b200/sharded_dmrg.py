@@ -22,17 +22,59 @@ bit-identical across ranks without further synchronisation.
 The arithmetic goes through an `ops` object (default: the CUDA engine, pytenet_b200/sharded.py); the
 multi-rank logic of the environment update is covered on CPU/gloo with a test-only ops object.
 """
+import ctypes
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import _device as dev
+from . import _lib
 from .mps import MPS, mps_local_orthonormalize_left_qr, mps_local_orthonormalize_right_qr
 from .mpo import MPO
 from .krylov import eigh_krylov
 from .sharded import _CudaOps, _flat_real
 
-__all__ = ["dmrg_singlesite_sharded", "tdvp_singlesite_sharded", "ShardedSite", "shard_env", "gather_env"]
+__all__ = ["dmrg_singlesite_sharded", "tdvp_singlesite_sharded", "ShardedSite", "shard_env", "gather_env",
+           "ptb_communicator", "destroy_communicators"]
+
+
+_CABI = os.environ.get("PYTENET_B200_CABI_SHARDED", "1") != "0"
+_comms = {}          # process group -> opaque ptb_comm handle (ctypes.c_void_p) of the C ABI
+
+
+def ptb_communicator(group=None):
+    """The C ABI's communicator (include/pytenet_b200.h: ptb_comm_*) for the ranks of `group`, created once:
+    rank 0 draws the NCCL id through `ptb_comm_unique_id`, torch.distributed only carries the 128 bytes to the other
+    ranks, every rank calls `ptb_comm_init` on its current device.  None for a single rank.  With it the sharded
+    matvec is ONE C call (two GEMMs + the all-reduce on the same stream) that a host without torch could issue
+    just as well."""
+    world, rank = _world(group)
+    if world == 1:
+        return None
+    key = id(group) if group is not None else 0
+    if key not in _comms:
+        lib = _lib.load()
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(lib.ptb_comm_unique_id(buf), "ptb_comm_unique_id")
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        handle = ctypes.c_void_p()
+        torch.cuda.synchronize()
+        idbuf = ctypes.create_string_buffer(box[0], 128)
+        _lib.check(lib.ptb_comm_init(ctypes.byref(handle), world, rank, idbuf), "ptb_comm_init")
+        _comms[key] = handle
+    return _comms[key]
+
+
+def destroy_communicators():
+    """Destroy the C ABI communicators created by `ptb_communicator` (call before the process group goes away)."""
+    lib = _lib.load()
+    for handle in _comms.values():
+        lib.ptb_comm_destroy(handle)
+    _comms.clear()
 
 
 def _world(group):
@@ -100,7 +142,22 @@ class ShardedSite:
         if q1 > q0:
             w3[:, :q1 - q0] = w[:, :, :, q0:q1].permute(2, 3, 1, 0)
         lw = torch.empty((Dl, din * P * dout, Dlp), dtype=self.dtype, device=lfull.device)
-        self.ops.precontract(w3.reshape(din * P * dout, cl).contiguous(), lfull, lw)
+        # the CUDA engine is driven through the sharded entries of the C ABI (csrc/sharded.cu), communicator
+        # included; a test-only `ops` object (CPU / gloo) keeps the step-by-step form
+        self.cabi = _CABI and isinstance(self.ops, _CudaOps) and lfull.is_cuda
+        w3 = w3.reshape(din * P * dout, cl).contiguous()
+        if self.cabi:
+            self.lib = _lib.load()
+            self.dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
+            self.comm = ptb_communicator(group)
+            if w3.dtype.is_complex and not cplx:
+                raise TypeError("complex MPO tensor on a real state: pass cplx=True")
+            w3 = w3 if w3.dtype in (dev.F64, dev.C128) else w3.to(dev.F64)
+            _lib.check(self.lib.ptb_sharded_precontract(self.dt, int(w3.dtype.is_complex), w3.data_ptr(),
+                                                        lfull.data_ptr(), lw.data_ptr(), Dl, cl, Dlp, din * P * dout,
+                                                        dev.stream_ptr(lfull.device)), "ptb_sharded_precontract")
+        else:
+            self.ops.precontract(w3, lfull, lw)
         self.lw = lw.reshape(Dl * din * P, dout, Dlp)          # [(i, s, kappa_loc), s', i']
         self._t1 = None
 
@@ -108,6 +165,16 @@ class ShardedSite:
         """out[i',s',j'] (full, identical on every rank) = L.W.A.R applied to a (Dl, d, Dr)."""
         Dl, d, Dr, dout, Dlp, Drp, P = self.dims
         a = a.to(self.dtype).contiguous()
+        if self.cabi:
+            # ONE C call: a.r_g, LW_g^T.t1 (split-K) and the all-reduce, all on the current stream
+            out = torch.empty((Dlp, dout, Drp), dtype=self.dtype, device=a.device)
+            nb = self.lib.ptb_apply_local_hamiltonian_sharded_workspace_bytes(self.dt, Dl, d, Dr, P, dout, Dlp, Drp)
+            ws = dev.workspace(nb, a.device, tag="sharded")
+            _lib.check(self.lib.ptb_apply_local_hamiltonian_sharded(
+                self.comm, self.dt, a.data_ptr(), self.lw.data_ptr(), self.r_shard.data_ptr(), out.data_ptr(),
+                Dl, d, Dr, P, dout, Dlp, Drp, ws.data_ptr(), nb, dev.stream_ptr(a.device)),
+                "ptb_apply_local_hamiltonian_sharded")
+            return out
         if self._t1 is None:
             self._t1 = torch.empty((Dl * d, P * Drp), dtype=self.dtype, device=a.device)
         self.ops.step1(a.reshape(Dl * d, Dr), self.r_shard.reshape(Dr, P * Drp), self._t1)
@@ -127,6 +194,16 @@ class ShardedSite:
         # (a sector-wise QR keeps min(rows, cols) indices per sector)
         assert a.shape[0] == Dl and a.shape[1] == d and b.shape[0] == Dlp and b.shape[1] == dout
         Dr = a.shape[2]
+        if self.cabi:
+            b = dev.dense(b.to(self.dtype))
+            Drb = b.shape[2]
+            nxt = torch.empty((Dr, P, Drb), dtype=self.dtype, device=a.device)
+            nb = self.lib.ptb_env_step_left_sharded_workspace_bytes(self.dt, Dl, d, P, Drb)
+            ws = dev.workspace(nb, a.device, tag="sharded")
+            _lib.check(self.lib.ptb_env_step_left_sharded(
+                self.dt, a.data_ptr(), b.data_ptr(), self.lw.data_ptr(), nxt.data_ptr(), Dl, d, Dr, P, dout, Dlp, Drb,
+                ws.data_ptr(), nb, dev.stream_ptr(a.device)), "ptb_env_step_left_sharded")
+            return nxt
         # conj(b) with rows ordered (s', i') to match the column order of LW
         b2 = dev.dense(b.to(self.dtype).permute(1, 0, 2)).reshape(dout * Dlp, b.shape[2])
         x = torch.empty((Dl * d * P, b.shape[2]), dtype=self.dtype, device=a.device)
@@ -229,6 +306,17 @@ def _sharded_bond_matvec(c, l_shard, r_shard, ops, group):
     dt = torch.complex128 if (c.dtype.is_complex or l_shard.dtype.is_complex or r_shard.dtype.is_complex) \
         else torch.float64
     c = c.to(dt).contiguous()
+    if _CABI and isinstance(ops, _CudaOps) and c.is_cuda:
+        lib = _lib.load()
+        code = _lib.PTB_COMPLEX128 if dt.is_complex else _lib.PTB_REAL64
+        ls, rs = dev.dense(l_shard.to(dt)), dev.dense(r_shard.to(dt))
+        out = torch.empty((Dlp, Drp), dtype=dt, device=c.device)
+        nb = lib.ptb_apply_local_bond_contraction_sharded_workspace_bytes(code, Dl, P, Drp)
+        ws = dev.workspace(nb, c.device, tag="sharded")
+        _lib.check(lib.ptb_apply_local_bond_contraction_sharded(
+            ptb_communicator(group), code, c.data_ptr(), ls.data_ptr(), rs.data_ptr(), out.data_ptr(), Dl, Dr, P, Dlp,
+            Drp, ws.data_ptr(), nb, dev.stream_ptr(c.device)), "ptb_apply_local_bond_contraction_sharded")
+        return out
     t = torch.empty((Dl, P * Drp), dtype=dt, device=c.device)
     ops.step1(c, r_shard.to(dt).reshape(Dr, P * Drp), t)                                  # t[i,(k,j')]
     out = torch.empty((Dlp, Drp), dtype=dt, device=c.device)

@@ -22,6 +22,11 @@ def test_header_declares_the_survey_minimum():
         for sfx in ("_d", "_z"):
             assert f"ptb_{stem}{sfx}" in names
     assert "ptb_krylov_combine" in names
+    # communicator handle + sharded variants ("*_comm_init/_destroy and sharded variants of the first four";
+    # the sharded right update is the left one on mirrored tensors, csrc/sharded.cu)
+    for name in ["ptb_comm_init", "ptb_comm_destroy", "ptb_comm_unique_id", "ptb_apply_local_hamiltonian_sharded",
+                 "ptb_apply_local_bond_contraction_sharded", "ptb_env_step_left_sharded", "ptb_sharded_precontract"]:
+        assert name in names
     assert "ptb_apply_local_hamiltonian_workspace_bytes" in names
 
 
