@@ -11,7 +11,11 @@
 // flag.  Step 3 is split along the rows of `out` (the left bra bond i'), whose row blocks are contiguous in
 // the result, so every block travels back while the next one is computed.  What stays exposed is the
 // first input slice and the last output block.
+#include <condition_variable>
+#include <cstring>
 #include <mutex>
+#include <thread>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/pytenet_b200.h"
@@ -33,8 +37,167 @@ struct HostPipe {
     std::mutex busy;            // one host-buffer call at a time per device (the call is synchronous anyway)
 };
 
+// ---- pageable host memory: staged through a page-locked ring ----------------------------------------------
+// A drop-in NumPy caller passes ordinary (pageable) arrays.  cudaMemcpyAsync from / to pageable memory is staged by
+// the driver through one internal bounce buffer on the calling thread (~10 GB/s, and it serialises with the
+// enqueueing of the compute work).  Here the library owns a small ring of page-locked chunks per device; a few
+// worker threads copy the caller's pages into a chunk while the DMA engine drains the previous one, so a pageable
+// call approaches the page-locked one.  Page-locked inputs (detected with cudaPointerGetAttributes) bypass all this.
+class CopyPool {
+public:
+    explicit CopyPool(int nthreads) : n_(nthreads) {
+        for (int i = 0; i < n_; i++) workers_.emplace_back([this, i] { loop(i); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // dst[r * dpitch .. +width) = src[r * spitch .. +width) for r < rows, split over the workers by rows / bytes
+    void copy2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t rows) {
+        if (width * rows < (size_t(1) << 20)) {
+            for (size_t r = 0; r < rows; r++) memcpy(dst + r * dpitch, src + r * spitch, width);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = dst; src_ = src; dp_ = dpitch; sp_ = spitch; w_ = width; rows_ = rows;
+            pending_ = n_;
+            gen_++;
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    void loop(int id) {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+            if (stop_) return;
+            char* dst = dst_; const char* src = src_;
+            const size_t dp = dp_, sp = sp_, w = w_, rows = rows_;
+            lk.unlock();
+            if (rows == 1) {
+                const size_t per = ((w + n_ - 1) / n_ + 63) & ~size_t(63);
+                const size_t b = std::min(w, per * id), e = std::min(w, per * (id + 1));
+                if (e > b) memcpy(dst + b, src + b, e - b);
+            } else {
+                const size_t r0 = rows * id / n_, r1 = rows * (id + 1) / n_;
+                if (dp == w && sp == w) {
+                    if (r1 > r0) memcpy(dst + r0 * w, src + r0 * w, (r1 - r0) * w);
+                } else {
+                    for (size_t r = r0; r < r1; r++) memcpy(dst + r * dp, src + r * sp, w);
+                }
+            }
+            lk.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+    int pending_ = 0;
+    char* dst_ = nullptr; const char* src_ = nullptr;
+    size_t dp_ = 0, sp_ = 0, w_ = 0, rows_ = 0;
+};
+
+constexpr int STAGE_CHUNKS = 4;
+constexpr size_t STAGE_BYTES = size_t(32) << 20;
+
+struct StageRing {
+    char* buf[STAGE_CHUNKS] = {};
+    cudaEvent_t ev[STAGE_CHUNKS] = {};
+    bool busy[STAGE_CHUNKS] = {};
+    int next = 0;
+    bool ok = false;
+    int init() {
+        if (ok) return PTB_OK;
+        for (int i = 0; i < STAGE_CHUNKS; i++) {
+            PTB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&buf[i]), STAGE_BYTES, cudaHostAllocDefault));
+            PTB_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        ok = true;
+        return PTB_OK;
+    }
+    // next chunk, free for the host to write (waits for the DMA / host copy that used it last)
+    int acquire(char** p) {
+        const int c = next;
+        next = (next + 1) % STAGE_CHUNKS;
+        if (busy[c]) PTB_CUDA_TRY(cudaEventSynchronize(ev[c]));
+        busy[c] = false;
+        *p = buf[c];
+        return c;
+    }
+};
+
+CopyPool* copy_pool() {
+    static CopyPool pool([] {
+        unsigned hc = std::thread::hardware_concurrency();
+        int n = hc >= 16 ? 6 : (hc >= 8 ? 4 : 2);
+        return n;
+    }());
+    return &pool;
+}
+
+inline bool is_pageable(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
 std::mutex g_mu;
 HostPipe g_pipe[64];
+StageRing g_ring_in[64], g_ring_out[64];
+
+// Host -> device copy of a (possibly strided) 2-D region on `st`; pageable sources go through the ring.
+int h2d_2d(StageRing* ring, char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t rows,
+           cudaStream_t st) {
+    if (!ring) {
+        if (rows == 1 || (dpitch == width && spitch == width))
+            return cuda_status(cudaMemcpyAsync(dst, src, width * rows, cudaMemcpyHostToDevice, st));
+        return cuda_status(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, st));
+    }
+    if (rows > 1 && dpitch == width && spitch == width) { width *= rows; rows = 1; }
+    if (rows == 1) {
+        for (size_t off = 0; off < width; off += STAGE_BYTES) {
+            const size_t n = std::min(STAGE_BYTES, width - off);
+            char* chunk;
+            const int c = ring->acquire(&chunk);
+            if (c < 0) return c;
+            copy_pool()->copy2d(chunk, n, src + off, n, n, 1);
+            PTB_CUDA_TRY(cudaMemcpyAsync(dst + off, chunk, n, cudaMemcpyHostToDevice, st));
+            PTB_CUDA_TRY(cudaEventRecord(ring->ev[c], st));
+            ring->busy[c] = true;
+        }
+        return PTB_OK;
+    }
+    const size_t rows_per = std::max<size_t>(1, STAGE_BYTES / width);
+    for (size_t r0 = 0; r0 < rows; r0 += rows_per) {
+        const size_t nr = std::min(rows_per, rows - r0);
+        char* chunk;
+        const int c = ring->acquire(&chunk);
+        if (c < 0) return c;
+        copy_pool()->copy2d(chunk, width, src + r0 * spitch, spitch, width, nr);      // gather into a dense chunk
+        PTB_CUDA_TRY(cudaMemcpy2DAsync(dst + r0 * dpitch, dpitch, chunk, width, width, nr, cudaMemcpyHostToDevice, st));
+        PTB_CUDA_TRY(cudaEventRecord(ring->ev[c], st));
+        ring->busy[c] = true;
+    }
+    return PTB_OK;
+}
 
 int pipe_for_current_device(HostPipe** pp) {
     int dev = 0;
@@ -169,6 +332,16 @@ int ptb_apply_local_hamiltonian_host(int dtype, int w_is_complex, const void* a,
         if (col.empty()) { col.push_back(0); val.assign((size_t)we, 0.0); }
     }
 
+    // pageable operands / result: staged through the device's page-locked rings (see above)
+    int devid = 0;
+    PTB_CUDA_TRY(cudaGetDevice(&devid));
+    StageRing* ring_a = is_pageable(a) ? &g_ring_in[devid] : nullptr;
+    StageRing* ring_r = is_pageable(r) ? &g_ring_in[devid] : nullptr;
+    StageRing* ring_l = is_pageable(l) ? &g_ring_in[devid] : nullptr;
+    StageRing* ring_o = is_pageable(out) ? &g_ring_out[devid] : nullptr;
+    if (ring_a || ring_r || ring_l) PTB_TRY(g_ring_in[devid].init());
+    if (ring_o) PTB_TRY(g_ring_out[devid].init());
+
     // all work of this call is ordered after what the caller already enqueued on `stream`
     PTB_CUDA_TRY(cudaEventRecord(P.entry, st));
     PTB_CUDA_TRY(cudaStreamWaitEvent(P.in, P.entry, 0));
@@ -188,17 +361,17 @@ int ptb_apply_local_hamiltonian_host(int dtype, int w_is_complex, const void* a,
     for (int c = 0; c < ns; c++) {
         const int64_t k0 = kb[c], kc = kb[c + 1] - kb[c];
         // columns [k0, k0+kc) of a viewed as (Dl*d) x Dr, same pitch on both sides
-        PTB_CUDA_TRY(cudaMemcpy2DAsync(a_d + k0 * es, (size_t)Dr * es, a_h + k0 * es, (size_t)Dr * es, (size_t)kc * es,
-                                       (size_t)Dl * d, cudaMemcpyHostToDevice, P.in));
-        PTB_CUDA_TRY(cudaMemcpyAsync(r_d + (size_t)k0 * cr * Drp * es, r_h + (size_t)k0 * cr * Drp * es,
-                                     (size_t)kc * cr * Drp * es, cudaMemcpyHostToDevice, P.in));
+        PTB_TRY(h2d_2d(ring_a, a_d + k0 * es, (size_t)Dr * es, a_h + k0 * es, (size_t)Dr * es, (size_t)kc * es,
+                       (size_t)Dl * d, P.in));
+        PTB_TRY(h2d_2d(ring_r, r_d + (size_t)k0 * cr * Drp * es, 0, r_h + (size_t)k0 * cr * Drp * es, 0,
+                       (size_t)kc * cr * Drp * es, 1, P.in));
         PTB_CUDA_TRY(cudaEventRecord(P.slice[c], P.in));
         PTB_CUDA_TRY(cudaStreamWaitEvent(st, P.slice[c], 0));
         rc = ptb_gemm_splitk(dtype, 0, 0, 0, Dl * d, cr * Drp, kc, a_d + k0 * es, Dr, r_d + (size_t)k0 * cr * Drp * es,
                              cr * Drp, t1, cr * Drp, 1, 0, 0, 0, c > 0 ? 1 : 0, 0, part, L.part_bytes, st);
         if (rc) return rc;
     }
-    PTB_CUDA_TRY(cudaMemcpyAsync(l_d, l, (size_t)Dl * cl * Dlp * es, cudaMemcpyHostToDevice, P.in));
+    PTB_TRY(h2d_2d(ring_l, l_d, 0, static_cast<const char*>(l), 0, (size_t)Dl * cl * Dlp * es, 1, P.in));
     PTB_CUDA_TRY(cudaEventRecord(P.l_ready, P.in));
 
     // ---- step 2                                                                      chain_ops.py:276
@@ -226,8 +399,37 @@ int ptb_apply_local_hamiltonian_host(int dtype, int w_is_complex, const void* a,
         if (rc) return rc;
         PTB_CUDA_TRY(cudaEventRecord(P.block[b], st));
         PTB_CUDA_TRY(cudaStreamWaitEvent(P.out, P.block[b], 0));
-        PTB_CUDA_TRY(cudaMemcpyAsync(out_h + (size_t)m0 * dout * Drp * es, out_d + (size_t)m0 * dout * Drp * es,
-                                     (size_t)mc * dout * Drp * es, cudaMemcpyDeviceToHost, P.out));
+        if (!ring_o)
+            PTB_CUDA_TRY(cudaMemcpyAsync(out_h + (size_t)m0 * dout * Drp * es, out_d + (size_t)m0 * dout * Drp * es,
+                                         (size_t)mc * dout * Drp * es, cudaMemcpyDeviceToHost, P.out));
+    }
+    if (ring_o) {
+        // pageable result: every row block travels device -> page-locked chunk on the copy-out stream (ordered
+        // after its GEMM by the event waits above: the blocks were enqueued in order) and is copied to the
+        // caller's pages by the worker threads while the next chunk is in flight
+        struct Pend { int c; char* dst; size_t n; };
+        std::vector<Pend> pend;
+        auto drain = [&](size_t keep) -> int {
+            while (pend.size() > keep) {
+                const Pend q = pend.front();
+                pend.erase(pend.begin());
+                PTB_CUDA_TRY(cudaEventSynchronize(ring_o->ev[q.c]));
+                copy_pool()->copy2d(q.dst, q.n, ring_o->buf[q.c], q.n, q.n, 1);
+                ring_o->busy[q.c] = false;
+            }
+            return PTB_OK;
+        };
+        const size_t total = (size_t)Dlp * dout * Drp * es;
+        for (size_t off = 0; off < total; off += STAGE_BYTES) {
+            const size_t n = std::min(STAGE_BYTES, total - off);
+            PTB_TRY(drain(STAGE_CHUNKS - 1));
+            const int c = ring_o->next;
+            ring_o->next = (ring_o->next + 1) % STAGE_CHUNKS;
+            PTB_CUDA_TRY(cudaMemcpyAsync(ring_o->buf[c], out_d + off, n, cudaMemcpyDeviceToHost, P.out));
+            PTB_CUDA_TRY(cudaEventRecord(ring_o->ev[c], P.out));
+            pend.push_back({c, out_h + off, n});
+        }
+        PTB_TRY(drain(0));
     }
     // later work on the caller's stream may reuse the workspace: order it after the last copy-out
     PTB_CUDA_TRY(cudaEventRecord(P.done, P.out));
