@@ -539,6 +539,10 @@ def sweeps_block(torch, ptb, device):
     by category (CUDA events around the regions of pytenet_b200/_prof.py; "host+other" is what is left of the
     synchronised wall time) and the reference's CPU path beside it.
 
+    Phases: "lanczos" = Krylov runs of the site problems (matvecs + vector kernels + k x k solve), "lanczos_bond" =
+    those of the zero-site problems, "env" = environment updates, "qr" / "svd" = factorisations, "glue" = merges
+    and gauge absorption.
+
     * `tdvp_singlesite` (pytenet/tdvp.py:26-118): XXZ chain L = 24 whose bulk bonds reach D = 2048 (bond profile
       min(2^i, 2^(L-i), 2048): the public signature has no maximum-bond argument), complex128, k = 25, ONE full
       symmetric time step (left + right sweep).

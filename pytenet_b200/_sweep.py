@@ -239,7 +239,7 @@ def local_hamiltonian_step(l, r, w, a, dt, numiter: int, plan=None):
 def local_bond_step(l, r, c, dt, numiter: int, plan=None):
     """exp(-dt K_eff) c for the zero-site (bond) effective Hamiltonian (tdvp.py:232-238)."""
     shape = tuple(c.shape)
-    with region("lanczos"):
+    with region("lanczos_bond"):
         if plan is not None and plan.cplx == (c.dtype.is_complex or l.dtype.is_complex or r.dtype.is_complex):
             def matvec(x):
                 if x.dtype.is_complex != plan.cplx:

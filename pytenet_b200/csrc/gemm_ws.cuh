@@ -24,6 +24,7 @@
 // the block-scaled formats), so the FP64 tensor pipe is driven by warp-level mma.sync.
 #pragma once
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "gemm_dmma.cuh"
@@ -88,7 +89,22 @@ struct WsParams {
     // the tiles by decreasing work so that the round-robin assignment of units to the persistent CTAs is balanced
     // although the per-tile k ranges differ widely.
     const int* order;
+    // tile rows per L2 super-tile of the grouped tile order (ws_tile_coords): the A panels of `group` tile rows stay in
+    // L2 while the B panels stream past them
+    int group;
 };
+
+// Rows per super-tile: a wave of 148 tiles then covers `group` tile rows x 148/group tile columns; the A panels of a
+// group (group x BM x K elements) must fit in the 126 MB L2 next to the streaming B panels and the C write-back.
+static inline int ws_group_rows(int tiles_m, int K, bool cplx) {
+    static const int forced = [] {
+        const char* e = getenv("PTB_GEMM_GROUP");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced > 0) return forced;
+    (void)tiles_m; (void)K; (void)cplx;
+    return 8;
+}
 
 // ---- mbarrier / TMA primitives ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -206,7 +222,7 @@ __device__ __forceinline__ WsUnit ws_decode_unit(const WsParams& p, long long u)
 
 // tile index -> (batch, tile row, tile column) in the grouped order (GROUP tile rows share B panels in L2)
 __device__ __forceinline__ void ws_tile_coords(const WsParams& p, long long t, int& bz, int& tm, int& tn) {
-    constexpr int GROUP = 8;
+    const int GROUP = p.group;
     const int tiles_per_batch = p.tiles_m * p.tiles_n;
     bz = (int)(t / tiles_per_batch);
     const int tile = (int)(t - (long long)bz * tiles_per_batch);
@@ -661,6 +677,7 @@ static int try_launch_ws(int transA, int transB, int conjB, const GemmParams& gp
     p.ktab = reinterpret_cast<const int2*>(ktab);
     p.seg_ptr = nullptr; p.segs = nullptr; p.sel_off = nullptr;
     p.order = order;
+    p.group = ws_group_rows(p.tiles_m, gp.K, CPLX);
     if (ktab != nullptr && (reinterpret_cast<uintptr_t>(ktab) % 8) != 0) return PTB_ERR_ALIGNMENT;
     if (split_k != 1 && part_ws != nullptr && ktab == nullptr) {
         const int KT = (gp.K + Cfg::BK - 1) / Cfg::BK;
@@ -736,6 +753,7 @@ static int launch_ws_segmented(int conjB, const GemmParams& gp, cudaStream_t str
     p.segs = reinterpret_cast<const int4*>(segs);
     p.sel_off = sel_off;
     p.order = order;
+    p.group = 8;
     CUtensorMap ta, tb;
     memset(&ta, 0, sizeof(ta));
     memset(&tb, 0, sizeof(tb));

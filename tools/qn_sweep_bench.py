@@ -24,6 +24,7 @@ ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--dense", type=int, default=1)
 ap.add_argument("--algo", default="one", choices=["one", "two"])
 ap.add_argument("--tol", type=float, default=1e-8)
+ap.add_argument("--prof", type=int, default=0, help="device-time split by phase (pytenet_b200/_prof.py)")
 args = ap.parse_args()
 L, D = args.L, args.D
 h = ptb.fermi_hubbard_1d_mpo(L, 1.0, 4.0, 0.0)
@@ -42,6 +43,9 @@ for mode in (["auto", "0"] if args.dense else ["auto"]):
     psi = psi0.copy()
     tag = "sector_path" if mode == "auto" else "dense_path"
     for rep in ("first_step", "later_step"):        # later steps reuse the cached sector plans
+        if args.prof:
+            from pytenet_b200 import _prof
+            _prof.enable(True)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         if args.algo == "one":
             ptb.tdvp_singlesite(h, psi, dt, 1, numiter_lanczos=args.k)
@@ -50,6 +54,9 @@ for mode in (["auto", "0"] if args.dense else ["auto"]):
         torch.cuda.synchronize()
         res[f"bond_dims_{tag}_{rep}"] = psi.bond_dims
         res[f"seconds_{tag}_{rep}"] = time.perf_counter() - t0
+        if args.prof:
+            res[f"device_seconds_by_phase_{tag}_{rep}"] = {k: v / 1e3 for k, v in _prof.report().items()}
+            _prof.enable(False)
     finals[mode] = psi
 if args.dense:
     ov = ptb.mps_vdot(finals["auto"], finals["0"])
