@@ -30,7 +30,15 @@ def prepare_environments(hamiltonian, psi):
     nsites = hamiltonian.nsites
     assert nsites == psi.nsites
     nrm = psi.orthonormalize(mode="right")
-    rblocks = compute_right_operator_blocks(psi, hamiltonian)
+    if _use_sectors(max(psi.bond_dims), psi.qsite, *psi.qbonds, *hamiltonian.qbonds):
+        # compute_right_operator_blocks (chain_ops.py:102-113) through the sector work lists: at D = 2048 with
+        # quantum numbers the dense contraction of every block costs 30x the sector path
+        rblocks = [None for _ in range(nsites)]
+        rblocks[nsites - 1] = torch.ones((1, 1, 1), dtype=dev.F64, device=psi.a[-1].device)
+        for i in reversed(range(nsites - 1)):
+            rblocks[i] = env_step_right(psi, hamiltonian, i + 1, rblocks[i + 1])
+    else:
+        rblocks = compute_right_operator_blocks(psi, hamiltonian)
     lblocks = [None for _ in range(nsites)]
     lblocks[0] = torch.ones((1, 1, 1), dtype=rblocks[0].dtype, device=rblocks[0].device)
     for i, rb in enumerate(rblocks):

@@ -97,11 +97,9 @@ struct WsParams {
 // Rows per super-tile: a wave of 148 tiles then covers `group` tile rows x 148/group tile columns; the A panels of a
 // group (group x BM x K elements) must fit in the 126 MB L2 next to the streaming B panels and the C write-back.
 static inline int ws_group_rows(int tiles_m, int K, bool cplx) {
-    static const int forced = [] {
-        const char* e = getenv("PTB_GEMM_GROUP");
-        return e ? atoi(e) : 0;
-    }();
-    if (forced > 0) return forced;
+    // measured at the headline shape (ncu dram__bytes, profiles/r02_gemm_ncu.md): 8 rows 6.8 GB per launch, 16 rows
+    // 10.0 GB, 24 rows 12.9 GB, 32 rows 21.2 GB at equal duration -- beyond 8 rows the A panels no longer survive in
+    // L2 next to the streaming B panels and the C write-back
     (void)tiles_m; (void)K; (void)cplx;
     return 8;
 }

@@ -6,7 +6,9 @@ import numpy as np
 import torch
 import pytenet_b200 as ptb
 warnings.simplefilter("ignore")
-L, D, k = 12, 2048, 10
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+D = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 h = ptb.fermi_hubbard_1d_mpo(L, 1.0, 4.0, 0.0)
 rng = np.random.default_rng(11)
 psi = ptb.MPS.construct_random(L, h.qsite, ptb.encode_quantum_number_pair(L, 0), max_vdim=D, rng=rng)
