@@ -15,7 +15,7 @@ import torch
 from . import _device as dev
 from . import _lib
 from ._prof import region
-from .sectors import HeffSectorPlan, EnvSectorPlan, BondSectorPlan
+from .sectors import HeffSectorPlan, EnvSectorPlan, BondSectorPlan, AbsorbSectorPlan
 from .sector_packed import PackedHeffPlan
 from .block_sparse_util import is_qsparse
 from .chain_ops import (apply_local_hamiltonian, apply_local_bond_contraction,
@@ -123,10 +123,58 @@ def env_step_right(psi, hamiltonian, i, r):
 
 
 def bond_plan(qbl, qbr, qw, c, l, r):
-    """BondSectorPlan for the zero-site problem on a bond (rows of `c`: qbl, columns: qbr), or None."""
+    """Sector plan for the zero-site problem on a bond (rows of `c`: qbl, columns: qbr), or None.  The zero-site
+    contraction out[i',j'] = sum l[i,k,i'] c[i,j] r[j,k,j'] is the site contraction with a one-dimensional physical
+    index of quantum number 0 and the identity on the MPO bond as MPO tensor, so the sector-packed plan of the site
+    problem serves it unchanged (grouped GEMMs over the sector blocks, Lanczos run in the packed space); float64
+    problems and bonds that are not grouped by sector use the banded work lists."""
     if not _use_sectors(max(c.shape), qbl, qbr, qw):
         return None
-    return _cached_plan(BondSectorPlan, dev.any_complex(c, l, r), qbl, qbr, qw)
+    cplx = dev.any_complex(c, l, r)
+    if _PACKED and cplx:
+        plan = _cached_plan(PackedHeffPlan, cplx, qbl, np.zeros(1, dtype=np.int64), qbr, qw, qw)
+        if plan.supported:
+            return plan
+    return _cached_plan(BondSectorPlan, cplx, qbl, qbr, qw)
+
+
+_IDENTITY_W = {}
+
+
+def _identity_w(chi, device):
+    """w[k, 0, 0, kappa] = delta(k, kappa): the MPO tensor that turns the site contraction into the zero-site one."""
+    key = (chi, device.index)
+    w = _IDENTITY_W.get(key)
+    if w is None:
+        w = torch.eye(chi, dtype=dev.F64, device=device).reshape(chi, 1, 1, chi).contiguous()
+        _IDENTITY_W[key] = w
+    return w
+
+
+def absorb_left(c, a, qc_rows, qc_cols, qs, qr):
+    """out[x,s,j] = sum_i c[x,i] a[i,s,j] (tdvp.py:84): banded over the sector blocks when that pays, else dense."""
+    if _use_sectors(max(c.shape + tuple(a.shape[::2])), qc_rows, qc_cols, qs, qr):
+        plan = _cached_plan(_AbsorbLeft, dev.any_complex(c, a), qc_rows, qc_cols, qs, qr)
+        return plan.apply(c, a)
+    return dev.gemm(c, a.reshape(a.shape[0], -1)).reshape((c.shape[0],) + tuple(a.shape[1:]))
+
+
+def absorb_right(a, c, qc_rows, qc_cols, qs, ql):
+    """out[i,s,y] = sum_j a[i,s,j] c[j,y] (tdvp.py:112)."""
+    if _use_sectors(max(c.shape + tuple(a.shape[::2])), qc_rows, qc_cols, qs, ql):
+        plan = _cached_plan(_AbsorbRight, dev.any_complex(c, a), qc_rows, qc_cols, qs, ql)
+        return plan.apply(c, a)
+    return dev.gemm(a.reshape(-1, a.shape[2]), c).reshape(tuple(a.shape[:2]) + (c.shape[1],))
+
+
+class _AbsorbLeft(AbsorbSectorPlan):
+    def __init__(self, qc_rows, qc_cols, qs, q_other, cplx=True):
+        super().__init__(qc_rows, qc_cols, qs, q_other, True, cplx=cplx)
+
+
+class _AbsorbRight(AbsorbSectorPlan):
+    def __init__(self, qc_rows, qc_cols, qs, q_other, cplx=True):
+        super().__init__(qc_rows, qc_cols, qs, q_other, False, cplx=cplx)
 
 
 class HeffOperator:
@@ -248,6 +296,12 @@ def local_bond_step(l, r, c, dt, numiter: int, plan=None):
     """exp(-dt K_eff) c for the zero-site (bond) effective Hamiltonian (tdvp.py:232-238)."""
     shape = tuple(c.shape)
     with region("lanczos_bond"):
+        if isinstance(plan, PackedHeffPlan):
+            pk = _packed(plan, _identity_w(l.shape[1], c.device), l, r, c.reshape(shape[0], 1, shape[1]))
+            if pk is not None:
+                op, xp = pk
+                return op.unpack(expm_krylov(op, xp, -dt, numiter, hermitian=True)).reshape(shape)
+            plan = None
         if plan is not None and plan.cplx == (c.dtype.is_complex or l.dtype.is_complex or r.dtype.is_complex):
             def matvec(x):
                 if x.dtype.is_complex != plan.cplx:

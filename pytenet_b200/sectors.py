@@ -27,7 +27,7 @@ import torch
 from . import _lib
 from . import _device as dev
 
-__all__ = ["HeffSectorPlan", "EnvSectorPlan", "BondSectorPlan", "tile_k_ranges"]
+__all__ = ["HeffSectorPlan", "EnvSectorPlan", "BondSectorPlan", "AbsorbSectorPlan", "tile_k_ranges"]
 
 import os
 import itertools
@@ -666,4 +666,70 @@ class BondSectorPlan:
             first = False
         if first:
             out.zero_()
+        return out
+
+
+class AbsorbSectorPlan:
+    """
+    Gauge absorption of the single-site sweeps (pytenet/tdvp.py:84,112) with the block structure of its operands:
+    `c` is block diagonal in the quantum numbers (`c[x, y] != 0` only if `qc_rows[x] == qc_cols[y]`), the site tensor
+    `a[i,s,j]` obeys `ql[i] + qs[s] == qr[j]`.
+
+      left = True :  out[x, s, j]  = sum_i c[x, i]  a[i, s, j]      (qc_cols are the quantum numbers of a's left bond)
+      left = False:  out[i, s, y]  = sum_j a[i, s, j] c[j, y]       (qc_rows are those of a's right bond)
+
+    One banded GEMM (`ptb_gemm_sector`): every output tile visits only the k-tiles that can be non-zero.
+    """
+
+    def __init__(self, qc_rows, qc_cols, qs, q_other, left, cplx=True):
+        self.cplx = cplx
+        self.left = bool(left)
+        qc_rows = np.asarray(qc_rows, dtype=np.int64); qc_cols = np.asarray(qc_cols, dtype=np.int64)
+        qs = np.asarray(qs, dtype=np.int64); q_other = np.asarray(q_other, dtype=np.int64)
+        bm, bn, bk = _tile_shape(cplx)
+        d = len(qs)
+        if self.left:
+            # rows x of c; columns (s, j) of a viewed as (Dk, d*Dr) with q_other = qr: k = i needs ql[i] == qc_rows[x]
+            # and ql[i] == qr[j] - qs[s]
+            self.dims = (len(qc_rows), d * len(q_other), len(qc_cols))
+            need_rows = qc_rows
+            need_cols = (-qs[:, None] + q_other[None, :]).reshape(-1)
+            qk = qc_cols
+        else:
+            # rows (i, s) of a viewed as (Dl*d, Dk) with q_other = ql: k = j needs qr[j] == ql[i] + qs[s] and
+            # qr[j] == qc_cols[y]
+            self.dims = (len(q_other) * d, len(qc_cols), len(qc_rows))
+            need_rows = (q_other[:, None] + qs[None, :]).reshape(-1)
+            need_cols = qc_cols
+            qk = qc_rows
+        m, n, k = self.dims
+        self.supported = cplx or (m % 2 == 0 and n % 2 == 0 and k % 2 == 0)
+        self.tab_host = np.ascontiguousarray(tile_k_ranges(need_rows, need_cols, KIndex(qk), bm, bn, bk)[None])
+        self.order_host = banded_order(self.tab_host)
+        self._dev = None
+
+    def apply(self, c, a):
+        lib = _lib.load()
+        cplx = dev.any_complex(c, a)
+        m, n, k = self.dims
+        if cplx != self.cplx or not self.supported:
+            if self.left:
+                return dev.gemm(c, a.reshape(a.shape[0], -1)).reshape((c.shape[0],) + tuple(a.shape[1:]))
+            return dev.gemm(a.reshape(-1, a.shape[2]), c).reshape(tuple(a.shape[:2]) + (c.shape[1],))
+        c = dev.as_dtype(c, cplx); a = dev.as_dtype(a, cplx)
+        if self._dev is None or self._dev[0] != c.device:
+            self._dev = (c.device, torch.from_numpy(self.tab_host).to(c.device),
+                         torch.from_numpy(self.order_host).to(c.device))
+        _, tab, order = self._dev
+        dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
+        if self.left:
+            out = torch.empty((c.shape[0],) + tuple(a.shape[1:]), dtype=a.dtype, device=a.device)
+            assert tuple(c.shape) == (m, k) and a.shape[0] == k and a.shape[1] * a.shape[2] == n
+            _banded(lib, dt, 0, 0, 0, m, n, k, c.data_ptr(), k, a.data_ptr(), n, out.data_ptr(), n, 1, 0, 0, 0, False,
+                    tab, dev.stream_ptr(c.device), "absorb(left)", order)
+        else:
+            out = torch.empty(tuple(a.shape[:2]) + (c.shape[1],), dtype=a.dtype, device=a.device)
+            assert tuple(c.shape) == (k, n) and a.shape[2] == k and a.shape[0] * a.shape[1] == m
+            _banded(lib, dt, 0, 0, 0, m, n, k, a.data_ptr(), k, c.data_ptr(), n, out.data_ptr(), n, 1, 0, 0, 0, False,
+                    tab, dev.stream_ptr(c.device), "absorb(right)", order)
         return out

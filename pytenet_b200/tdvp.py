@@ -17,7 +17,7 @@ from .mps import MPS, mps_merge_tensor_pair, mps_split_tensor_svd
 from .mpo import MPO, mpo_merge_tensor_pair
 from .block_sparse_util import qnumber_flatten, block_sparse_qr
 from ._sweep import (prepare_environments, local_hamiltonian_step, local_bond_step, sector_plan, bond_plan,
-                     env_step_left, env_step_right)
+                     env_step_left, env_step_right, absorb_left, absorb_right)
 from .krylov import defer_checks
 from ._prof import region
 
@@ -134,9 +134,7 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
             c = local_bond_step(lblocks[i + 1], rblocks[i], c, -0.5 * dt, k,
                                 bond_plan(psi.qbonds[i + 1], qold, qh[i + 1], c, lblocks[i + 1], rblocks[i]))
             with region("glue"):
-                nxt = psi.a[i + 1]
-                psi.a[i + 1] = dev.gemm(c, nxt.reshape(nxt.shape[0], -1)).reshape(
-                    (c.shape[0],) + tuple(nxt.shape[1:]))
+                psi.a[i + 1] = absorb_left(c, psi.a[i + 1], psi.qbonds[i + 1], qold, psi.qsite, psi.qbonds[i + 2])
 
         # full step on the last site (tdvp.py:87-89)
         i = nsites - 1
@@ -157,9 +155,7 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
             c = local_bond_step(lblocks[i], rblocks[i - 1], c, -0.5 * dt, k,
                                 bond_plan(qold, psi.qbonds[i], qh[i], c, lblocks[i], rblocks[i - 1]))
             with region("glue"):
-                prv = psi.a[i - 1]
-                psi.a[i - 1] = dev.gemm(prv.reshape(-1, prv.shape[2]), c).reshape(
-                    tuple(prv.shape[:2]) + (c.shape[1],))
+                psi.a[i - 1] = absorb_right(psi.a[i - 1], c, qold, psi.qbonds[i], psi.qsite, psi.qbonds[i - 1])
             psi.a[i - 1] = local_hamiltonian_step(
                 lblocks[i - 1], rblocks[i - 1], ham[i - 1], psi.a[i - 1], 0.5 * dt, k, site_plan(i - 1))
 

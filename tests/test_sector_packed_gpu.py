@@ -199,3 +199,44 @@ def test_packed_path_at_config3_shape(cuda_lib):
     s0 = int(starts[len(vals) // 2]); s1 = int(starts[len(vals) // 2 + 1])
     sub = oracle.apply_local_hamiltonian(a.cpu().numpy(), w2, l[:, :, s0:s1].cpu().numpy(), r.cpu().numpy())
     assert rel(got[s0:s1].cpu().numpy(), sub) < TOL
+
+
+def test_packed_zero_site_problem_and_banded_absorption(cuda_lib):
+    """The zero-site (bond) contraction through the sector-packed plan -- the site contraction with a one-dimensional
+    physical index and the identity as MPO tensor (`_sweep.bond_plan`) -- and the gauge absorption through the banded
+    GEMM (`sectors.AbsorbSectorPlan`), both against the oracle / NumPy on block-sparse inputs."""
+    import pytenet_b200 as ptb
+    from pytenet_b200 import _sweep
+    from pytenet_b200.sector_packed import PackedHeffPlan
+    from pytenet_b200.sectors import AbsorbSectorPlan
+    rng = np.random.default_rng(19)
+    Dl, Dr, chi, d = 300, 270, 5, 3
+    qbl = np.sort(rng.integers(-2, 3, size=Dl)); qbr = np.sort(rng.integers(-2, 3, size=Dr))
+    qw = rng.integers(-1, 2, size=chi)
+
+    def tensor(shape, qn):
+        t = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+        ob.enforce_qsparsity(t, qn)
+        return t
+    c = tensor((Dl, Dr), [qbl, -qbr])
+    l = tensor((Dl, chi, Dl), [qbl, qw, -qbl]); r = tensor((Dr, chi, Dr), [qbr, qw, -qbr])
+    plan = PackedHeffPlan(qbl, np.zeros(1, dtype=np.int64), qbr, qw, qw)
+    assert plan.supported
+    op = plan.bind(_sweep._identity_w(chi, torch.device("cuda", 0)), cu(l), cu(r))
+    got = op.apply_dense(cu(c).reshape(Dl, 1, Dr)).reshape(Dl, Dr).cpu().numpy()
+    assert rel(got, oracle.apply_local_bond_contraction(c, l, r)) < TOL
+    # the driver-level entry: exp(-dt K_eff) c through the packed Lanczos run == through the dense operator
+    lh = l + l.conj().transpose(2, 1, 0); rh = r + r.conj().transpose(2, 1, 0)
+    import pytenet_b200._sweep as sw
+    y_packed = sw.local_bond_step(cu(lh), cu(rh), cu(c), 0.01j, 6, PackedHeffPlan(qbl, np.zeros(1, dtype=np.int64), qbr, qw, qw))
+    y_dense = sw.local_bond_step(cu(lh), cu(rh), cu(c), 0.01j, 6, None)
+    assert (torch.linalg.norm(y_packed - y_dense) / torch.linalg.norm(y_dense)).item() < 1e-12
+    # gauge absorption, both sides
+    qs = rng.integers(-1, 2, size=d)
+    qn = np.sort(rng.integers(-2, 3, size=280))            # the other bond of the site tensor
+    a = tensor((Dr, d, 280), [qbr, qs, -qn])                # left bond = columns of c
+    got = AbsorbSectorPlan(qbl, qbr, qs, qn, True).apply(cu(c), cu(a)).cpu().numpy()
+    assert rel(got, np.tensordot(c, a, 1)) < 1e-13
+    b = tensor((280, d, Dl), [qn, qs, -qbl])                # right bond = rows of c
+    got = AbsorbSectorPlan(qbl, qbr, qs, qn, False).apply(cu(c), cu(b)).cpu().numpy()
+    assert rel(got, np.tensordot(b, c, 1)) < 1e-13
