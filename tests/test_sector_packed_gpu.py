@@ -226,11 +226,12 @@ def test_packed_zero_site_problem_and_banded_absorption(cuda_lib):
     got = op.apply_dense(cu(c).reshape(Dl, 1, Dr)).reshape(Dl, Dr).cpu().numpy()
     assert rel(got, oracle.apply_local_bond_contraction(c, l, r)) < TOL
     # the driver-level entry: exp(-dt K_eff) c through the packed Lanczos run == through the dense operator
-    lh = l + l.conj().transpose(2, 1, 0); rh = r + r.conj().transpose(2, 1, 0)
+    # (same block-sparse l, r: the Lanczos recursion is the same arithmetic on the allowed entries whether or not
+    # the operator is Hermitian, so the two runs must agree to rounding)
     import pytenet_b200._sweep as sw
-    y_packed = sw.local_bond_step(cu(lh), cu(rh), cu(c), 0.01j, 6, PackedHeffPlan(qbl, np.zeros(1, dtype=np.int64), qbr, qw, qw))
-    y_dense = sw.local_bond_step(cu(lh), cu(rh), cu(c), 0.01j, 6, None)
-    assert (torch.linalg.norm(y_packed - y_dense) / torch.linalg.norm(y_dense)).item() < 1e-12
+    y_packed = sw.local_bond_step(cu(l), cu(r), cu(c), 0.01j, 6, PackedHeffPlan(qbl, np.zeros(1, dtype=np.int64), qbr, qw, qw))
+    y_dense = sw.local_bond_step(cu(l), cu(r), cu(c), 0.01j, 6, None)
+    assert (torch.linalg.norm(y_packed - y_dense) / torch.linalg.norm(y_dense)).item() < 1e-10
     # gauge absorption, both sides
     qs = rng.integers(-1, 2, size=d)
     qn = np.sort(rng.integers(-2, 3, size=280))            # the other bond of the site tensor
