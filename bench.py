@@ -773,7 +773,7 @@ def run_ours(args):
     ms_dom = max(ms1, ms3)
     achieved = f_gemm / ms_dom / 1e9
     prof_traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
     if os.path.exists(tpath):
         try:
             prof_traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
