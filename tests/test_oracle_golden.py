@@ -167,3 +167,32 @@ def test_mps_ops_match_reference(golden_dir):
     for tag in ("fv0", "fv"):
         m = om.from_vector(3, 5, z["fv/input"], tol=float(z[f"{tag}/tol"]))
         assert m.bond_dims == list(z[f"{tag}/bond_dims"]) and rel(m.to_vector(), z[f"{tag}/vec"]) < 1e-12
+
+
+def test_round2_twosite_fixtures(golden_dir):
+    """Round-2 fixtures (tests/golden/make_golden_r2.py): a truncating quantum-number two-site TDVP run and two-site
+    sweeps with tol_split = 0 from a product state (rank-deficient splits) -- oracle == reference in bond dimensions,
+    sector layouts and state."""
+    z = np.load(os.path.join(golden_dir, "tdvp_fh_qnum_trunc_L8.npz"))
+    w, wq, n = load_op(z)
+    psi = load_chain(z, "psi0", n)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        osw.tdvp_twosite(w, wq, psi, complex(z["tdvp/dt"]), int(z["tdvp/nsteps"]), numiter_lanczos=int(z["tdvp/k"]),
+                         tol_split=float(z["tdvp/tol"]))
+    assert psi.bond_dims == list(z["tdvp/bond_dims"])
+    for i in range(n + 1):
+        assert np.array_equal(psi.qbonds[i], z[f"tdvp/qb{i}"])
+    assert rel(psi.to_vector(), z["tdvp/vec"]) < 1e-10
+    z = np.load(os.path.join(golden_dir, "twosite_rank_deficient_L6.npz"))
+    w, wq, n = load_op(z)
+    psi = load_chain(z, "psi0", n)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        osw.tdvp_twosite(w, wq, psi, complex(z["tdvp/dt"]), int(z["tdvp/nsteps"]), numiter_lanczos=int(z["tdvp/k"]),
+                         tol_split=0)
+        psi2 = load_chain(z, "psi0", n)
+        en = osw.dmrg_twosite(w, wq, psi2, len(z["dmrg/en"]), numiter_lanczos=int(z["dmrg/k"]), tol_split=0)
+    assert psi.bond_dims == list(z["tdvp/bond_dims"]) and psi2.bond_dims == list(z["dmrg/bond_dims"])
+    assert rel(psi.to_vector(), z["tdvp/vec"]) < 1e-10
+    assert np.max(np.abs(en - z["dmrg/en"])) < 1e-11
