@@ -457,6 +457,11 @@ def sharded_sweep_block(torch, dist, device, world, rank, D=128, k=10):
     import pytenet_b200 as ptb
     from pytenet_b200.hamiltonian import load_cached_mpo
     from pytenet_b200.sharded_dmrg import dmrg_singlesite_sharded
+    # untimed warm-up on the 10-orbital sibling (library handles, plan caches, workspaces)
+    h10 = load_cached_mpo(os.path.join(ROOT, "tests", "golden", "molecular_mpo_N10.npz"), device=device)
+    dmrg_singlesite_sharded(h10, ptb.MPS.construct_random(10, h10.qsite, 5, max_vdim=16, dtype="complex",
+                                                          rng=np.random.default_rng(3), device=device), 1,
+                            numiter_lanczos=4)
     h = load_cached_mpo(os.path.join(ROOT, "tests", "golden", "molecular_mpo_N32.npz"), device=device)
     n = h.nsites
     psi = ptb.MPS.construct_random(n, h.qsite, n // 2, max_vdim=D, dtype="complex", rng=np.random.default_rng(11),

@@ -283,7 +283,9 @@ def block_sparse_eigh(a, q0):
     return u, ev_dev.cpu().numpy(), q
 
 
-_POLAR_MIN = int(os.environ.get("PYTENET_B200_POLAR_SVD_MIN", "768"))     # min(m, n) from which gesvdp is used
+# min(m, n) from which gesvdp is used: measured 3x faster than gesvd from 256 up (complex128: 256 8 vs 25 ms,
+# 512 18 vs 62 ms, 1024 44 vs 163 ms, 2048 152 vs 579 ms)
+_POLAR_MIN = int(os.environ.get("PYTENET_B200_POLAR_SVD_MIN", "256"))
 
 
 def dense_svd(a):

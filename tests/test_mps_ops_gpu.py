@@ -180,7 +180,8 @@ def test_batched_sector_svd(cuda_lib, cplx):
     assert len(ptb.retained_bond_indices(gs, 0.0)) == len(ws)
 
 
-@pytest.mark.parametrize("shape,cplx", [((1024, 1024), True), ((900, 1300), False), ((1500, 800), True)])
+@pytest.mark.parametrize("shape,cplx", [((1024, 1024), True), ((900, 1300), False), ((1500, 800), True),
+                                        ((256, 300), True), ((400, 260), False)])
 def test_dense_svd_polar_driver(cuda_lib, shape, cplx):
     """block_sparse_util.dense_svd on large blocks (cuSOLVER's polar-decomposition driver through ptb_svd_polar):
     singular values equal LAPACK's to 1e-13 of the largest -- also for a spectrum graded over ten decades --, the
