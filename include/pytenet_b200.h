@@ -357,6 +357,26 @@ int ptb_svd_polar(int dtype, int64_t rows, int64_t cols, void* a, int64_t lda, d
                   int64_t ldv, void* device_ws, size_t device_bytes, void* host_ws, size_t host_bytes, int* info,
                   double* err_sigma, void* stream);
 
+/* Batched form: the independent sector blocks of ONE split (pytenet/block_sparse_util.py:276-300 loops over the
+ * sectors and calls LAPACK per block) factorised concurrently -- every job as ptb_svd_polar, run on up to
+ * `max_workers` (<= 8; <= 0: 8) internal worker streams with their own cuSOLVER handles; the work is ordered after
+ * everything enqueued on `stream` so far, and `stream` waits for all jobs before the call returns.  Per job:
+ * `device_ws` of at least the size ptb_svd_polar_workspace_bytes reports, `info` a device int; `err_sigma` and
+ * `status` (PTB_OK or an error code) are written on return.  Returns the last non-OK job status, else PTB_OK. */
+typedef struct ptb_svd_job {
+    int64_t rows, cols;
+    void* a; int64_t lda;              /* column-major rows x cols, destroyed */
+    double* s;                         /* min(rows, cols) */
+    void* u; int64_t ldu;              /* column-major rows x min */
+    void* v; int64_t ldv;              /* column-major cols x min */
+    void* device_ws; size_t device_bytes;
+    int* info;                         /* device */
+    double err_sigma;                  /* out */
+    int status;                        /* out */
+    int reserved;
+} ptb_svd_job;
+int ptb_svd_polar_batch(int dtype, int njobs, ptb_svd_job* jobs, int max_workers, void* stream);
+
 /* ---------------------------------------------------------------------------
  * A whole Lanczos run on the local effective Hamiltonian in ONE call
  *   pytenet/krylov.py:12-57 driven by the closures tdvp.py:223-229 (site), tdvp.py:232-238 (bond),
@@ -403,7 +423,12 @@ int ptb_bond_lanczos(int dtype, const void* c, const void* l, const void* r, int
  * ptb_block_gather: dst chunk (rows x cols at dst + dst_off, leading dimension dst_ld) = sum over its terms of
  * coef * src[src_off + r*src_rs + c*src_cs]; `work` lists {chunk, first row, number of rows, 0} per CTA.  Serves the
  * W step (coefficients = MPO entries), the packing of a / l / r and the unpacking of the result (one term, coef 1,
- * strides express transposition).  coef_im is ignored for float64 data.
+ * strides express transposition).  coef_im is ignored for float64 data.  A chunk with flags bit 0 set reads the
+ * complex conjugate of its source elements (bra tensors of the environment updates, pytenet/chain_ops.py:55,93).
+ * The environment updates run on the same two kernels (pytenet_b200/sector_packed.py: PackedEnvPlan):
+ *   step_right:  T1^T_beta = RB_beta^T AT_beta,  T2^T = W . T1^T (block gather),
+ *                r_next as LP-layout blocks  (K' x n_alpha') = T2^T_alpha'^T (K' x N') conj(BT_alpha') (N' x n_alpha')
+ *   step_left:   the same on the mirrored tensors (strides of the gather tables, no copies).
  * ------------------------------------------------------------------------- */
 typedef struct ptb_group_tile {
     int64_t a_off, b_off, c_off;
@@ -417,7 +442,7 @@ int ptb_gemm_grouped(int dtype, const void* a, const void* b, void* c, const ptb
 
 typedef struct ptb_gather_chunk {
     int64_t dst_off;
-    int32_t dst_ld, rows, cols, term_begin, term_end, reserved;
+    int32_t dst_ld, rows, cols, term_begin, term_end, flags;      /* flags bit 0: conjugate the source */
 } ptb_gather_chunk;                     /* 32 bytes */
 typedef struct ptb_gather_term {
     int64_t src_off;

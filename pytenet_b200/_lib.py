@@ -99,6 +99,14 @@ class SectorTables(ctypes.Structure):
     _fields_ = [("ktab", _ptr), ("seg_ptr", _ptr), ("segs", _ptr), ("sel_off", _ptr), ("order", _ptr)]
 
 
+class SvdJob(ctypes.Structure):
+    """ptb_svd_job of include/pytenet_b200.h."""
+    _fields_ = [("rows", _i64), ("cols", _i64), ("a", _ptr), ("lda", _i64), ("s", _ptr), ("u", _ptr), ("ldu", _i64),
+                ("v", _ptr), ("ldv", _i64), ("device_ws", _ptr), ("device_bytes", _sz), ("info", _ptr),
+                ("err_sigma", ctypes.c_double), ("status", _int), ("reserved", _int)]
+
+
+SIGNATURES["ptb_svd_polar_batch"] = (_int, [_int, _int, ctypes.POINTER(SvdJob), _int, _ptr])
 SIGNATURES["ptb_gemm_sector"] = (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                                         _i64, _i64, _i64, _i64, _int, ctypes.POINTER(SectorTables), _ptr])
 

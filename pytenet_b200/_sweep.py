@@ -16,7 +16,7 @@ from . import _device as dev
 from . import _lib
 from ._prof import region
 from .sectors import HeffSectorPlan, EnvSectorPlan, BondSectorPlan, AbsorbSectorPlan
-from .sector_packed import PackedHeffPlan
+from .sector_packed import PackedHeffPlan, PackedEnvPlan
 from .block_sparse_util import is_qsparse
 from .chain_ops import (apply_local_hamiltonian, apply_local_bond_contraction,
                         compute_right_operator_blocks, contraction_operator_step_left,
@@ -82,7 +82,7 @@ def sector_plan(ql, qs, qr, qwl, qwr, like, *others):
     if not (np.any(ql) or np.any(qr) or np.any(qs) or np.any(qwl) or np.any(qwr)):
         return None
     cplx = True if like is None else dev.any_complex(like, *[t for t in others if isinstance(t, torch.Tensor)])
-    if _PACKED and cplx:
+    if _PACKED:
         # sector-packed grouped GEMM (sector_packed.py) whenever the bonds are grouped by sector -- every bond a
         # sweep has orthonormalised is; else the banded work lists over the dense layout (sectors.py)
         plan = _cached_plan(PackedHeffPlan, cplx, ql, qs, qr, qwl, qwr)
@@ -99,6 +99,25 @@ def _use_sectors(nbond, *qnums):
     return any(np.any(q) for q in qnums)
 
 
+class _PackedEnvLeft(PackedEnvPlan):
+    def __init__(self, ql, qs, qr, qwl, qwr, cplx=True):
+        super().__init__(ql, qs, qr, qwl, qwr, cplx=cplx, side="left")
+
+
+class _PackedEnvRight(PackedEnvPlan):
+    def __init__(self, ql, qs, qr, qwl, qwr, cplx=True):
+        super().__init__(ql, qs, qr, qwl, qwr, cplx=cplx, side="right")
+
+
+def _packed_env(cls, a, w, env, qn):
+    """Sector-packed environment update (sector_packed.PackedEnvPlan), or None when the bonds are not grouped by
+    sector or the operands are not plain device tensors of the expected shapes."""
+    if not _PACKED or w.dtype not in (dev.F64, dev.C128) or not (a.is_cuda and w.is_cuda and env.is_cuda):
+        return None
+    plan = _cached_plan(cls, dev.any_complex(a, env, w), *qn)
+    return plan.apply(a, w, env) if plan.supported else None
+
+
 def env_step_left(psi, hamiltonian, i, l):
     """lblocks[i+1] from lblocks[i] and site i (tdvp.py:79,179; dmrg.py:72,153), through the sector work lists
     when the quantum numbers are non-trivial and the bonds large, else the dense contraction."""
@@ -106,6 +125,9 @@ def env_step_left(psi, hamiltonian, i, l):
     qn = (psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], hamiltonian.qbonds[i], hamiltonian.qbonds[i + 1])
     with region("env"):
         if _use_sectors(max(a.shape[0], a.shape[2]), *qn) and isinstance(l, torch.Tensor) and l.shape[0] == a.shape[0]:
+            out = _packed_env(_PackedEnvLeft, a, w, l, qn)
+            if out is not None:
+                return out
             plan = _cached_plan(EnvSectorPlan, dev.any_complex(a, l, w), *qn)
             return plan.step_left(a, w, l)
         return contraction_operator_step_left(a, a, w, l)
@@ -117,6 +139,9 @@ def env_step_right(psi, hamiltonian, i, r):
     qn = (psi.qbonds[i], psi.qsite, psi.qbonds[i + 1], hamiltonian.qbonds[i], hamiltonian.qbonds[i + 1])
     with region("env"):
         if _use_sectors(max(a.shape[0], a.shape[2]), *qn) and isinstance(r, torch.Tensor) and r.shape[0] == a.shape[2]:
+            out = _packed_env(_PackedEnvRight, a, w, r, qn)
+            if out is not None:
+                return out
             plan = _cached_plan(EnvSectorPlan, dev.any_complex(a, r, w), *qn)
             return plan.step_right(a, w, r)
         return contraction_operator_step_right(a, a, w, r)
@@ -131,7 +156,7 @@ def bond_plan(qbl, qbr, qw, c, l, r):
     if not _use_sectors(max(c.shape), qbl, qbr, qw):
         return None
     cplx = dev.any_complex(c, l, r)
-    if _PACKED and cplx:
+    if _PACKED:
         plan = _cached_plan(PackedHeffPlan, cplx, qbl, np.zeros(1, dtype=np.int64), qbr, qw, qw)
         if plan.supported:
             return plan
@@ -262,6 +287,8 @@ def _packed(plan, w, l, r, a):
     Dl, d, Dr, cl, cr = plan.dims
     if (tuple(a.shape) != (Dl, d, Dr) or tuple(w.shape) != (cl, d, d, cr) or tuple(l.shape) != (Dl, cl, Dl)
             or tuple(r.shape) != (Dr, cr, Dr) or w.dtype not in (dev.F64, dev.C128)):
+        return None
+    if dev.any_complex(w, l, r, a) != plan.cplx:
         return None
     op = plan.bind(w, l, r)
     return op, op.pack(a)

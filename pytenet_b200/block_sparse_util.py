@@ -283,9 +283,10 @@ def block_sparse_eigh(a, q0):
     return u, ev_dev.cpu().numpy(), q
 
 
-# min(m, n) from which gesvdp is used: measured 3x faster than gesvd from 256 up (complex128: 256 8 vs 25 ms,
-# 512 18 vs 62 ms, 1024 44 vs 163 ms, 2048 152 vs 579 ms)
-_POLAR_MIN = int(os.environ.get("PYTENET_B200_POLAR_SVD_MIN", "256"))
+# min(m, n) from which gesvdp is used: measured 2-3x faster than gesvd from 64 up (complex128, ms: 64 3.1 vs 5.9,
+# 128 6.5 vs 12.6, 256 8 vs 25, 512 18 vs 62, 1024 44 vs 163, 2048 152 vs 579; profiles/r02_svd_bench.json,
+# profiles/r02_svd_mid_bench.json)
+_POLAR_MIN = int(os.environ.get("PYTENET_B200_POLAR_SVD_MIN", "64"))
 
 
 def dense_svd(a):
@@ -330,6 +331,77 @@ def dense_svd(a):
     return vbuf.mH, sdev, ubuf
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    st = _SIDE_STREAMS.get(device.index)
+    if st is None:
+        st = _SIDE_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
+def dense_svd_batch(mats):
+    """
+    Thin SVDs of several independent dense device matrices (the sector blocks of one split that are too large for
+    the batched Jacobi kernel) -> list of `(u, s, vh)`.  Blocks the polar driver takes (`min(m, n) >= _POLAR_MIN`)
+    are factorised CONCURRENTLY by `ptb_svd_polar_batch` (worker streams with their own cuSOLVER handles: a
+    mid-size factorisation is a latency-bound chain of small kernels and host synchronisations, 4-8 ms each, so
+    the four to eight large blocks of a split overlap almost perfectly); the others, and any block for which the
+    driver reports a loss of accuracy, go through `dense_svd` one by one.
+    """
+    out = [None] * len(mats)
+    jobs_idx = [i for i, a in enumerate(mats)
+                if min(a.shape) >= _POLAR_MIN and a.dtype in (dev.F64, dev.C128) and a.is_cuda]
+    if len(jobs_idx) >= 2 and len({mats[i].dtype for i in jobs_idx}) == 1:
+        lib = _lib.load()
+        a0 = mats[jobs_idx[0]]
+        cplx = a0.dtype.is_complex
+        dt = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
+        device = a0.device
+        jobs = (_lib.SvdJob * len(jobs_idx))()
+        keep = []
+        need = []
+        for i in jobs_idx:
+            a = mats[i]
+            m, n = a.shape
+            tall = m > n
+            work = dev.dense(a.mH) if tall else a.clone()
+            rows, cols = work.shape[1], work.shape[0]
+            nd, nh = ctypes.c_size_t(0), ctypes.c_size_t(0)
+            _lib.check(lib.ptb_svd_polar_workspace_bytes(dt, rows, cols, ctypes.byref(nd), ctypes.byref(nh)),
+                       "ptb_svd_polar_workspace_bytes")
+            need.append((max(nd.value, 16) + 255) // 256 * 256)
+            keep.append((tall, work, rows, cols))
+        ws = dev.workspace(sum(need), device, tag="svd_batch")
+        infos = torch.zeros(len(jobs_idx), dtype=torch.int32, device=device)
+        bufs = []
+        pos = 0
+        for j, (i, (tall, work, rows, cols)) in enumerate(zip(jobs_idx, keep)):
+            k = min(rows, cols)
+            ubuf = torch.empty((k, rows), dtype=work.dtype, device=device)
+            vbuf = torch.empty((k, cols), dtype=work.dtype, device=device)
+            sdev = torch.empty(k, dtype=dev.F64, device=device)
+            bufs.append((ubuf, vbuf, sdev))
+            jb = jobs[j]
+            jb.rows, jb.cols, jb.a, jb.lda = rows, cols, work.data_ptr(), rows
+            jb.s, jb.u, jb.ldu, jb.v, jb.ldv = sdev.data_ptr(), ubuf.data_ptr(), rows, vbuf.data_ptr(), cols
+            jb.device_ws, jb.device_bytes = ws.data_ptr() + pos, need[j]
+            jb.info = infos.data_ptr() + 4 * j
+            pos += need[j]
+        st = lib.ptb_svd_polar_batch(dt, len(jobs_idx), jobs, 0, dev.stream_ptr(device))
+        info_h = infos.cpu().numpy()
+        for j, i in enumerate(jobs_idx):
+            ok = st == 0 or jobs[j].status == 0
+            if ok and jobs[j].status == 0 and info_h[j] == 0 and jobs[j].err_sigma <= 1e-11:
+                ubuf, vbuf, sdev = bufs[j]
+                out[i] = (ubuf.mH, sdev, vbuf) if keep[j][0] else (vbuf.mH, sdev, ubuf)
+    for i, a in enumerate(mats):
+        if out[i] is None:
+            out[i] = dense_svd(a)
+    return out
+
+
 def block_sparse_svd(a, q0, q1):
     """
     Sector-wise thin SVD of a block-sparse matrix -> `(u, s, v, q)` with `s` a host
@@ -356,21 +428,32 @@ def block_sparse_svd(a, q0, q1):
     u = torch.zeros((a.shape[0], nb), dtype=a.dtype, device=a.device)
     v = torch.zeros((nb, a.shape[1]), dtype=a.dtype, device=a.device)
     s_dev = torch.zeros(nb, dtype=dev.F64, device=a.device)
+    side = None
     if small:
         # all sectors whose block and right vectors fit in shared memory: ONE launch of the batched one-sided
-        # Jacobi kernel (csrc/block_svd.cu), singular values descending per sector as LAPACK returns them
+        # Jacobi kernel (csrc/block_svd.cu), singular values descending per sector as LAPACK returns them.  When
+        # larger sectors follow, the kernel runs on a side stream so that it overlaps their factorisations (both
+        # are latency bound and use a fraction of the SMs).
+        stream = dev.stream_ptr(a.device)
+        if large and not _CAPTURING:
+            side = _side_stream(a.device)
+            side.wait_stream(torch.cuda.current_stream(a.device))
+            stream = side.cuda_stream
         st = _lib.load().ptb_block_svd(_lib.PTB_COMPLEX128 if a.dtype.is_complex else _lib.PTB_REAL64, a.data_ptr(),
                                        a.shape[1], len(small), tab.data_ptr(), max_work, tab.data_ptr() + row_off,
                                        tab.data_ptr() + col_off, u.data_ptr(), nb, s_dev.data_ptr(), v.data_ptr(),
-                                       a.shape[1], dev.stream_ptr(a.device))
+                                       a.shape[1], stream)
         _lib.check(st, "ptb_block_svd")
     if large:
         dix = plan.all_indices()
         nsec = len(plan.sectors)
-        for i in large:
+        blocks = dense_svd_batch([a.index_select(0, dix[i]).index_select(1, dix[nsec + i]) for i in large])
+        if side is not None:
+            torch.cuda.current_stream(a.device).wait_stream(side)       # u, v, s_dev are shared with the kernel
+            side = None
+        for i, (us, ss, vs) in zip(large, blocks):
             rt, ct = dix[i], dix[nsec + i]
             p0, sz = plan.starts[i], plan.sizes[i]
-            us, ss, vs = dense_svd(a.index_select(0, rt).index_select(1, ct))
             u[rt, p0:p0 + sz] = us
             v[p0:p0 + sz, ct] = vs
             s_dev[p0:p0 + sz] = ss

@@ -14,8 +14,9 @@ using namespace ptb;
 
 namespace {
 
-constexpr int SVD_THREADS = 256;
-constexpr int SVD_WARPS = SVD_THREADS / 32;
+// threads per CTA: one warp per column pair of a round; blocks with more than 16 columns get the full 32 warps
+// (a round of k/2 pairs is then at most two pair-steps deep up to k = 128; the kernel is latency bound)
+constexpr int SVD_MAX_THREADS = 1024;
 constexpr int SVD_MAX_SWEEPS = 60;
 constexpr int SVD_MAX_K = 1024;
 
@@ -51,7 +52,7 @@ __device__ __forceinline__ void rotate_columns(double* mat, int rows, int p, int
 
 // meta per sector: {m, n, row_off, col_off, pos, 0, 0, 0}
 template <bool CPLX>
-__global__ void __launch_bounds__(SVD_THREADS) sector_svd_kernel(const double* __restrict__ A, int64_t lda,
+__global__ void __launch_bounds__(SVD_MAX_THREADS) sector_svd_kernel(const double* __restrict__ A, int64_t lda,
                                                                  const int* __restrict__ meta,
                                                                  const int* __restrict__ rowidx,
                                                                  const int* __restrict__ colidx, double* __restrict__ U,
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(SVD_THREADS) sector_svd_kernel(const double* _
     double* sig = v + (size_t)k * k * E;         // k
     int* rank = reinterpret_cast<int*>(sig + k); // k
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int SVD_THREADS = blockDim.x, SVD_WARPS = blockDim.x >> 5;
 
     for (int idx = tid; idx < m * n; idx += SVD_THREADS) {
         const int i = idx / n, j = idx - i * n;
@@ -197,6 +199,10 @@ int ptb_block_svd(int dtype, const void* a, int64_t lda, int nsec, const int32_t
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // shared memory: G (rows x k) + V (k x k) = max_work_elems elements, then k singular values and k ranks
     const size_t smem_need = (size_t)max_work_elems * es + (size_t)SVD_MAX_K * 12 + 64;
+    // max_work_elems >= 2 k^2 for the largest block: k <= sqrt(max_work_elems / 2)
+    int pairs = 1;
+    while ((size_t)(2 * pairs) * (2 * pairs) * 2 < (size_t)max_work_elems && pairs < 32) pairs++;
+    const int SVD_THREADS = pairs <= 8 ? 256 : (pairs <= 16 ? 512 : SVD_MAX_THREADS);
     if (cplx) {
         static DeviceFlags configured;
         PTB_TRY(ensure_dynamic_smem(configured, sector_svd_kernel<true>, 220 * 1024));

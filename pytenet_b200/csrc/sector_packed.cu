@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) block_gather_kernel(const doub
     const ptb_gather_chunk ch = chunks[wk.x];
     const int row0 = wk.y, nrows = wk.z;
     const int total = nrows * ch.cols;
+    const double sgn = (ch.flags & 1) ? -1.0 : 1.0;        // conjugated source (bra tensors)
     for (int idx = threadIdx.x; idx < total; idx += GATHER_THREADS) {
         const int r = row0 + idx / ch.cols;
         const int c = idx % ch.cols;
@@ -34,7 +35,8 @@ __global__ void __launch_bounds__(GATHER_THREADS) block_gather_kernel(const doub
             const ptb_gather_term tm = terms[t];
             const int64_t s = tm.src_off + (int64_t)r * tm.src_rs + (int64_t)c * tm.src_cs;
             if (CPLX) {
-                const double2 v = *reinterpret_cast<const double2*>(src + 2 * s);
+                double2 v = *reinterpret_cast<const double2*>(src + 2 * s);
+                v.y *= sgn;
                 re += tm.coef_re * v.x - tm.coef_im * v.y;
                 im += tm.coef_re * v.y + tm.coef_im * v.x;
             } else {

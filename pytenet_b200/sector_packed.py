@@ -31,6 +31,7 @@ Lanczos run stays in X (`pack` once, `unpack` once): the Lanczos vector kernels 
 allowed entries (4 % of the dense vector at config 3).  Inner products and norms are sums over the same
 non-zero entries, so alphas / betas equal the dense run's up to summation order.
 
+complex128 and float64 (real states: every leading dimension padded to an even number of elements).
 Sector layouts are untouched (qbonds / retained indices stay bit-exact).  Bonds that are not grouped by sector
 (e.g. `MPS.construct_random` output before the first orthonormalisation) are not supported here -- `supported`
 is False and the callers use the banded path of sectors.py.
@@ -43,7 +44,7 @@ import torch
 from . import _lib
 from . import _device as dev
 
-__all__ = ["PackedHeffPlan", "PackedHeffOperator"]
+__all__ = ["PackedHeffPlan", "PackedHeffOperator", "PackedEnvPlan"]
 
 _KSPLIT = 256          # step-3 groups are split along their stacked contraction index into pieces of about this size
 _GATHER_ELEMS = 4096   # elements per CTA of the block-gather kernel
@@ -63,47 +64,68 @@ def _runs(q):
     return vals, starts.astype(np.int64), sizes.astype(np.int64)
 
 
-class _Gather:
-    """Host tables of one block-gather launch (ptb_block_gather): chunks, terms, work items."""
+_CHUNK_DT = np.dtype([("dst_off", "<i8"), ("dst_ld", "<i4"), ("rows", "<i4"), ("cols", "<i4"), ("t0", "<i4"),
+                      ("t1", "<i4"), ("flags", "<i4")])
+_TERM_DT = np.dtype([("src_off", "<i8"), ("rs", "<i4"), ("cs", "<i4"), ("re", "<f8"), ("im", "<f8")])
+_TILE_DT = np.dtype([("a", "<i8"), ("b", "<i8"), ("c", "<i8"), ("lda", "<i4"), ("ldb", "<i4"), ("ldc", "<i4"),
+                     ("m", "<i4"), ("n", "<i4"), ("k", "<i4"), ("acc", "<i4"), ("res", "<i4", (3,))])
+assert _CHUNK_DT.itemsize == 32 and _TERM_DT.itemsize == 32 and _TILE_DT.itemsize == 64
 
-    def __init__(self):
-        self.chunks = []      # (dst_off, dst_ld, rows, cols, term_begin, term_end)
-        self.terms = []       # (src_off, src_rs, src_cs, coef_re, coef_im)
 
-    def chunk(self, dst_off, dst_ld, rows, cols, terms):
-        if rows <= 0 or cols <= 0:
-            return
-        t0 = len(self.terms)
-        self.terms.extend(terms)
-        self.chunks.append((dst_off, dst_ld, rows, cols, t0, len(self.terms)))
+def _gather_tables(dst_off, dst_ld, rows, cols, term_count, src_off, src_rs, src_cs, coef_re=None, coef_im=None,
+                   conj=False):
+    """Host tables of one block-gather launch (ptb_block_gather) from per-chunk arrays and per-term arrays; chunk c
+    owns the next `term_count[c]` terms.  Empty chunks are dropped.  `conj`: the chunks read the complex conjugate
+    of the source.  Returns (chunks, terms, work items)."""
+    dst_off, dst_ld, rows, cols, term_count = (np.asarray(v, dtype=np.int64).reshape(-1)
+                                               for v in (dst_off, dst_ld, rows, cols, term_count))
+    t1 = np.cumsum(term_count)
+    t0 = t1 - term_count
+    keep = (rows > 0) & (cols > 0)
+    ch = np.zeros(int(np.count_nonzero(keep)), dtype=_CHUNK_DT)
+    ch["dst_off"], ch["dst_ld"], ch["rows"], ch["cols"] = dst_off[keep], dst_ld[keep], rows[keep], cols[keep]
+    ch["t0"], ch["t1"] = t0[keep], t1[keep]
+    ch["flags"] = 1 if conj else 0
+    nt = len(np.asarray(src_off).reshape(-1))
+    tm = np.zeros(max(nt, 1), dtype=_TERM_DT)
+    if nt:
+        tm["src_off"][:nt], tm["rs"][:nt], tm["cs"][:nt] = src_off, src_rs, src_cs
+        tm["re"][:nt] = 1.0 if coef_re is None else coef_re
+        tm["im"][:nt] = 0.0 if coef_im is None else coef_im
+    # work items: row ranges of about _GATHER_ELEMS elements
+    rows_k, cols_k = rows[keep], cols[keep]
+    per = np.maximum(1, _GATHER_ELEMS // np.maximum(cols_k, 1))
+    nwork = -(-rows_k // per)
+    ci = np.repeat(np.arange(len(rows_k)), nwork)
+    first = np.cumsum(nwork) - nwork
+    r0 = (np.arange(int(nwork.sum())) - first[ci]) * per[ci]
+    wk = np.zeros((len(ci), 4), dtype=np.int32)
+    wk[:, 0], wk[:, 1], wk[:, 2] = ci, r0, np.minimum(per[ci], rows_k[ci] - r0)
+    return ch, tm, wk
 
-    def finish(self):
-        ch = np.zeros(len(self.chunks), dtype=[("dst_off", "<i8"), ("dst_ld", "<i4"), ("rows", "<i4"), ("cols", "<i4"),
-                                               ("t0", "<i4"), ("t1", "<i4"), ("res", "<i4")])
-        for i, c in enumerate(self.chunks):
-            ch[i] = c + (0,)
-        tm = np.zeros(max(len(self.terms), 1), dtype=[("src_off", "<i8"), ("rs", "<i4"), ("cs", "<i4"),
-                                                       ("re", "<f8"), ("im", "<f8")])
-        for i, t in enumerate(self.terms):
-            tm[i] = t
-        work = []
-        for i, c in enumerate(self.chunks):
-            rows, cols = c[2], c[3]
-            per = max(1, _GATHER_ELEMS // cols)
-            for r0 in range(0, rows, per):
-                work.append((i, r0, min(per, rows - r0), 0))
-        wk = np.asarray(work, dtype=np.int32).reshape(-1, 4)
-        assert ch.dtype.itemsize == 32 and tm.dtype.itemsize == 32
-        return ch, tm, wk
+
+def _pack_segments(arrays):
+    """One byte buffer holding the given arrays at 64-byte aligned offsets: (buffer, offsets)."""
+    offs, pos = [], 0
+    for a in arrays:
+        offs.append(pos)
+        pos += (a.nbytes + 63) // 64 * 64
+    buf = np.zeros(max(pos, 64), dtype=np.uint8)
+    for a, o in zip(arrays, offs):
+        if a.nbytes:
+            buf[o:o + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+    return buf, offs
 
 
 class _DeviceGather:
-    def __init__(self, tables, device):
+    def __init__(self, tables, device, views=None):
         ch, tm, wk = tables
         self.nwork = len(wk)
-        self.ch = torch.from_numpy(ch.view(np.uint8).reshape(-1)).to(device) if len(ch) else None
-        self.tm = torch.from_numpy(tm.view(np.uint8).reshape(-1)).to(device)
-        self.wk = torch.from_numpy(np.ascontiguousarray(wk)).to(device) if len(wk) else None
+        if views is None:
+            buf, offs = _pack_segments([ch, tm, wk])
+            dbuf = torch.from_numpy(buf).to(device)
+            views = [dbuf[o:] for o in offs]
+        self.ch, self.tm, self.wk = views
 
     def run(self, lib, dt, src, dst, stream):
         if self.nwork == 0:
@@ -116,21 +138,67 @@ class _DeviceGather:
 def _tile_table(tiles):
     """(n, 64-byte) device-ready table from (a_off, b_off, c_off, lda, ldb, ldc, m, n, k) tuples, sorted by
     decreasing k (longest tiles first over the persistent CTAs)."""
-    tiles = sorted(tiles, key=lambda t: -t[8])
-    tab = np.zeros(len(tiles), dtype=[("a", "<i8"), ("b", "<i8"), ("c", "<i8"), ("lda", "<i4"), ("ldb", "<i4"),
-                                      ("ldc", "<i4"), ("m", "<i4"), ("n", "<i4"), ("k", "<i4"), ("acc", "<i4"),
-                                      ("res", "<i4", (3,))])
-    for i, t in enumerate(tiles):
-        tab[i] = t + (0, (0, 0, 0))
-    assert tab.dtype.itemsize == 64
+    cols = np.asarray(tiles, dtype=np.int64).reshape(-1, 9)
+    return _tile_table_cols(*[cols[:, i] for i in range(9)])
+
+
+def _tile_table_cols(a, b, c, lda, ldb, ldc, m, n, k):
+    order = np.argsort(-np.asarray(k, dtype=np.int64), kind="stable")
+    tab = np.zeros(len(order), dtype=_TILE_DT)
+    for name, v in zip(("a", "b", "c", "lda", "ldb", "ldc", "m", "n", "k"), (a, b, c, lda, ldb, ldc, m, n, k)):
+        tab[name] = np.asarray(v, dtype=np.int64)[order]
     return tab
+
+
+def _seg_offsets(group, size, ngroups):
+    """Running (exclusive) sum of `size` inside each group, in the given order of the entries, and the group totals."""
+    group = np.asarray(group, dtype=np.int64); size = np.asarray(size, dtype=np.int64)
+    tot = np.bincount(group, weights=size, minlength=ngroups).astype(np.int64) if len(group) else np.zeros(ngroups, np.int64)
+    if len(group) == 0:
+        return np.zeros(0, dtype=np.int64), tot
+    order = np.argsort(group, kind="stable")
+    g, sz = group[order], size[order]
+    cs = np.cumsum(sz) - sz
+    first = np.concatenate([[True], g[1:] != g[:-1]])
+    base = cs[first][np.cumsum(first) - 1]
+    off = np.empty_like(cs)
+    off[order] = cs - base
+    return off, tot
+
+
+def _k_pieces(klen, live):
+    """Split the contraction range [0, klen[g]) of every live group g into pieces of about _KSPLIT (multiples of 16):
+    (group of each piece, k0, k1, pieces per group, index of each group's first piece)."""
+    npc = np.where(live, np.maximum(1, -(-klen // _KSPLIT)), 0)
+    stepk = -(-klen // np.maximum(npc, 1))
+    stepk = -(-stepk // 16) * 16
+    npc = np.where(live, -(-klen // np.maximum(stepk, 1)), 0)
+    pc_g = np.repeat(np.arange(len(klen)), npc)
+    pc_first = np.cumsum(npc) - npc
+    pc_p = np.arange(int(npc.sum())) - pc_first[pc_g]
+    pc_k0 = pc_p * stepk[pc_g]
+    pc_k1 = np.minimum(pc_k0 + stepk[pc_g], klen[pc_g])
+    return pc_g, pc_k0, pc_k1, npc, pc_first
+
+
+def _tiles_of(groups_m, groups_n, BM, BN):
+    """Tile enumeration of a list of (m x n) matrices: per tile (matrix index, row start, column start)."""
+    ntm, ntn = -(-groups_m // BM), -(-groups_n // BN)
+    cnt = ntm * ntn
+    gi = np.repeat(np.arange(len(cnt)), cnt)
+    local = np.arange(int(cnt.sum())) - (np.cumsum(cnt) - cnt)[gi]
+    ntn_g = np.maximum(ntn[gi], 1)
+    return gi, (local // ntn_g) * BM, (local % ntn_g) * BN
 
 
 class PackedHeffPlan:
     """
     Everything about the sector-packed matvec that depends on the quantum numbers only: sector lists, packed
     layouts, GEMM tile tables and the gather tables that pack `a`, `l`, `r` and unpack the result.
-    Arguments as `sectors.HeffSectorPlan` (bra bonds = ket bonds, as in the sweeps).
+    Arguments as `sectors.HeffSectorPlan` (bra bonds = ket bonds, as in the sweeps).  Built with array operations
+    over the (sector, physical index, MPO index) combinations: a two-site TDVP step with truncation changes the
+    sector layout of every bond at every split, so plans are rebuilt per local problem there and their construction
+    is on the critical path of the sweep.
     """
 
     def __init__(self, ql, qs, qr, qwl, qwr, cplx=True):
@@ -141,8 +209,7 @@ class PackedHeffPlan:
         Dl, d, Dr, cl, cr = len(self.ql), len(self.qs), len(self.qr), len(self.qwl), len(self.qwr)
         self.dims = (Dl, d, Dr, cl, cr)
         L, R = _runs(self.ql), _runs(self.qr)
-        # complex128 only: every row of a packed operand is then 16-byte granular for the bulk copies
-        self.supported = self.cplx and L is not None and R is not None
+        self.supported = L is not None and R is not None
         self._dev = {}
         self._wcache = {}
         if not self.supported:
@@ -156,127 +223,121 @@ class PackedHeffPlan:
         qL, oL, nL = L
         qR, oR, nR = R
         self.L, self.R = L, R
-        idxL = {int(v): i for i, v in enumerate(qL)}
-        idxR = {int(v): i for i, v in enumerate(qR)}
         nLs, nRs = len(qL), len(qR)
+        sortL, sortR = np.argsort(qL), np.argsort(qR)
 
-        # ---- packed vector space X: group b (right sector), columns = stacked (alpha, s) blocks ----
-        self.x_chunk = {}                       # (alpha, s) -> (b, m_off)
-        M = np.zeros(nRs, dtype=np.int64)
-        for s in range(d):
-            for al in range(nLs):
-                b = idxR.get(int(qL[al] + self.qs[s]))
-                if b is not None:
-                    self.x_chunk[(al, s)] = (b, int(M[b]))
-                    M[b] += nL[al]
+        def lookup(vals, perm, q):
+            """Index of the sector with quantum number q (array), -1 where there is none."""
+            sv = vals[perm]
+            pos = np.minimum(np.searchsorted(sv, q), len(sv) - 1)
+            return np.where(sv[pos] == q, perm[pos], -1)
+        in_L = lambda q: lookup(qL, sortL, q)          # noqa: E731
+        in_R = lambda q: lookup(qR, sortR, q)          # noqa: E731
+        # float64: the bulk copies of the grouped GEMM move 16-byte granules, so every leading dimension is rounded
+        # up to an even number of elements (complex128 needs no padding).  Padding entries of the packed VECTORS are
+        # kept at zero (they take part in the Lanczos inner products); padding of the intermediates is never read.
+        ev = (lambda v: v) if self.cplx else (lambda v: v + (v & 1))
+        excl = lambda v: np.cumsum(v) - v              # noqa: E731
+
+        # ---- packed vector space X: group b (right sector), columns = stacked (alpha, s) blocks, s-major ----
+        xs, xal = np.repeat(np.arange(d), nLs), np.tile(np.arange(nLs), d)
+        xb = in_R(qL[xal] + self.qs[xs])
+        ok = xb >= 0
+        xs, xal, xb = xs[ok], xal[ok], xb[ok]
+        xm, M = _seg_offsets(xb, nL[xal], nRs)
+        self.XB = np.full((nLs, d), -1, dtype=np.int64); self.XM = np.zeros((nLs, d), dtype=np.int64)
+        self.XB[xal, xs], self.XM[xal, xs] = xb, xm
+        self.xc = (xs, xal, xb, xm)
         self.M = M
-        self.offX = np.concatenate([[0], np.cumsum(nR * M)])[:-1]
-        self.nX = int(np.sum(nR * M))
+        Mp = self.Mp = ev(M)
+        self.offX = excl(nR * Mp)
+        self.nX = int(np.sum(nR * Mp))
 
         # ---- step 1 operand RB: group b, columns = stacked (K, gamma(b, K)) ----
-        self.rb_chunk = {}                      # (b, K) -> (gamma, n_off)
-        N1 = np.zeros(nRs, dtype=np.int64)
-        for b in range(nRs):
-            for K in range(cr):
-                g = idxR.get(int(qR[b] + self.qwr[K]))
-                if g is not None:
-                    self.rb_chunk[(b, K)] = (g, int(N1[b]))
-                    N1[b] += nR[g]
+        rb_b, rb_K = np.repeat(np.arange(nRs), cr), np.tile(np.arange(cr), nRs)
+        rb_g = in_R(qR[rb_b] + self.qwr[rb_K])
+        ok = rb_g >= 0
+        rb_b, rb_K, rb_g = rb_b[ok], rb_K[ok], rb_g[ok]
+        rb_n, N1 = _seg_offsets(rb_b, nR[rb_g], nRs)
+        self.RBG = np.full((nRs, cr), -1, dtype=np.int64); self.RBN = np.zeros((nRs, cr), dtype=np.int64)
+        self.RBG[rb_b, rb_K], self.RBN[rb_b, rb_K] = rb_g, rb_n
+        self.rbc = (rb_b, rb_K, rb_g, rb_n)
         self.N1 = N1
-        self.offRB = np.concatenate([[0], np.cumsum(nR * N1)])[:-1]
-        self.nRB = int(np.sum(nR * N1))
-        self.offT1 = np.concatenate([[0], np.cumsum(M * N1)])[:-1]
-        self.nT1 = int(np.sum(M * N1))
+        N1p = self.N1p = ev(N1)
+        self.offRB = excl(nR * N1p)
+        self.nRB = int(np.sum(nR * N1p))
+        self.offT1 = excl(Mp * N1p)
+        self.nT1 = int(np.sum(Mp * N1p))
 
-        # ---- step 3: group a' (left sector): rows of T2 / LP = stacked (alpha, k), columns of T2 = stacked (s', gamma') ----
-        self.t2_row = {}                        # (a', alpha, k) -> kk_off
-        self.t2_col = {}                        # (a', s') -> (gamma', n_off)
-        K3 = np.zeros(nLs, dtype=np.int64)
-        N3 = np.zeros(nLs, dtype=np.int64)
-        for ap in range(nLs):
-            for k in range(cl):
-                al = idxL.get(int(qL[ap] - self.qwl[k]))
-                if al is not None:
-                    self.t2_row[(ap, al, k)] = int(K3[ap])
-                    K3[ap] += nL[al]
-            for sp in range(d):
-                g = idxR.get(int(qL[ap] + self.qs[sp]))
-                if g is not None:
-                    self.t2_col[(ap, sp)] = (g, int(N3[ap]))
-                    N3[ap] += nR[g]
+        # ---- step 3: group a' (left sector): rows of T2 / LP = stacked (k, alpha), columns of T2 = stacked (s', gamma') ----
+        tr_ap, tr_k = np.repeat(np.arange(nLs), cl), np.tile(np.arange(cl), nLs)
+        tr_al = in_L(qL[tr_ap] - self.qwl[tr_k])
+        ok = tr_al >= 0
+        tr_ap, tr_k, tr_al = tr_ap[ok], tr_k[ok], tr_al[ok]
+        tr_kk, K3 = _seg_offsets(tr_ap, nL[tr_al], nLs)
+        self.tr = (tr_ap, tr_k, tr_al, tr_kk)
+        tc_ap, tc_sp = np.repeat(np.arange(nLs), d), np.tile(np.arange(d), nLs)
+        tc_g = in_R(qL[tc_ap] + self.qs[tc_sp])
+        ok = tc_g >= 0
+        tc_ap, tc_sp, tc_g = tc_ap[ok], tc_sp[ok], tc_g[ok]
+        tc_n, N3 = _seg_offsets(tc_ap, nR[tc_g], nLs)
+        self.TCG = np.full((nLs, d), -1, dtype=np.int64); self.TCN = np.zeros((nLs, d), dtype=np.int64)
+        self.TCG[tc_ap, tc_sp], self.TCN[tc_ap, tc_sp] = tc_g, tc_n
+        self.tc = (tc_ap, tc_sp, tc_g, tc_n)
         self.K3, self.N3 = K3, N3
-        self.offT2 = np.concatenate([[0], np.cumsum(K3 * N3)])[:-1]
-        self.nT2 = int(np.sum(K3 * N3))
-        self.offLP = np.concatenate([[0], np.cumsum(K3 * nL)])[:-1]
-        self.nLP = int(np.sum(K3 * nL))
-        # K-split of the step-3 groups: piece p of group a' covers stacked rows [kb[p], kb[p+1]) and writes its own
+        N3p, nLp = ev(N3), ev(nL)
+        self.N3p, self.nLp = N3p, nLp
+        self.offT2 = excl(K3 * N3p)
+        self.nT2 = int(np.sum(K3 * N3p))
+        self.offLP = excl(K3 * nLp)
+        self.nLP = int(np.sum(K3 * nLp))
+        self.K3p = ev(K3)                          # transposed intermediates of the environment update
+        self.offT2T = excl(N3 * self.K3p)
+        self.nT2T = int(np.sum(N3 * self.K3p))
+        # K-split of the step-3 groups: piece p of group a' covers stacked rows [k0, k1) and writes its own
         # partial product O_(a',p); the repack gather sums the pieces (fixed order, deterministic)
-        self.k_pieces = []
-        o_sizes = []
-        for ap in range(nLs):
-            kk = int(K3[ap])
-            if kk == 0 or N3[ap] == 0:
-                self.k_pieces.append([])
-                continue
-            npc = max(1, -(-kk // _KSPLIT))
-            step = -(-kk // npc)
-            step = -(-step // 16) * 16
-            bounds = list(range(0, kk, step)) + [kk]
-            self.k_pieces.append([(bounds[p], bounds[p + 1]) for p in range(len(bounds) - 1)])
-            o_sizes.extend([int(N3[ap] * nL[ap])] * (len(bounds) - 1))
-        self.offO = []
-        pos = 0
-        for ap in range(nLs):
-            offs = []
-            for _ in self.k_pieces[ap]:
-                offs.append(pos)
-                pos += int(N3[ap] * nL[ap])
-            self.offO.append(offs)
-        self.nO = pos
+        pc_ap, pc_k0, pc_k1, npc, pc_first = _k_pieces(K3, (K3 > 0) & (N3 > 0))
+        pc_size = N3p[pc_ap] * nLp[pc_ap]
+        pc_off = excl(pc_size)
+        self.nO = int(pc_size.sum())
+        self.pieces = (pc_ap, pc_k0, pc_k1, pc_off, npc, pc_first)
 
         # ---- GEMM tile tables ----
-        t1, t3 = [], []
-        for b in range(nRs):
-            if M[b] == 0 or N1[b] == 0:
-                continue
-            for tm in range(0, int(M[b]), BM):
-                for tn in range(0, int(N1[b]), BN):
-                    t1.append((int(self.offX[b] + tm), int(self.offRB[b] + tn), int(self.offT1[b] + tm * N1[b] + tn),
-                               int(M[b]), int(N1[b]), int(N1[b]), min(BM, int(M[b]) - tm), min(BN, int(N1[b]) - tn),
-                               int(nR[b])))
-        for ap in range(nLs):
-            for p, (k0, k1) in enumerate(self.k_pieces[ap]):
-                for tm in range(0, int(N3[ap]), BM):
-                    for tn in range(0, int(nL[ap]), BN):
-                        t3.append((int(self.offT2[ap] + k0 * N3[ap] + tm), int(self.offLP[ap] + k0 * nL[ap] + tn),
-                                   int(self.offO[ap][p] + tm * nL[ap] + tn), int(N3[ap]), int(nL[ap]), int(nL[ap]),
-                                   min(BM, int(N3[ap]) - tm), min(BN, int(nL[ap]) - tn), k1 - k0))
-        self.tiles1_host = _tile_table(t1)
-        self.tiles3_host = _tile_table(t3)
+        live1 = np.flatnonzero((M > 0) & (N1 > 0))
+        gi, tm, tn = _tiles_of(Mp[live1], N1p[live1], BM, BN)
+        b = live1[gi]
+        self.tiles1_host = _tile_table_cols(self.offX[b] + tm, self.offRB[b] + tn, self.offT1[b] + tm * N1p[b] + tn,
+                                            Mp[b], N1p[b], N1p[b], np.minimum(BM, Mp[b] - tm),
+                                            np.minimum(BN, N1p[b] - tn), nR[b])
+        gi, tm, tn = _tiles_of(N3p[pc_ap], nLp[pc_ap], BM, BN)
+        ap, k0 = pc_ap[gi], pc_k0[gi]
+        self.tiles3_host = _tile_table_cols(self.offT2[ap] + k0 * N3p[ap] + tm, self.offLP[ap] + k0 * nLp[ap] + tn,
+                                            pc_off[gi] + tm * nLp[ap] + tn, N3p[ap], nLp[ap], nLp[ap],
+                                            np.minimum(BM, N3p[ap] - tm), np.minimum(BN, nLp[ap] - tn),
+                                            pc_k1[gi] - k0)
 
         # ---- gather tables that depend on the quantum numbers only ----
-        one = (1.0, 0.0)
-        g_pack_a, g_unpack, g_pack_r, g_pack_l, g_repack = _Gather(), _Gather(), _Gather(), _Gather(), _Gather()
-        for (al, s), (b, m_off) in self.x_chunk.items():
-            dense_off = int((oL[al] * d + s) * Dr + oR[b])
-            x_off = int(self.offX[b] + m_off)
-            # X[b][j, m_off + i] = a[oL+i, s, oR+j]
-            g_pack_a.chunk(x_off, int(M[b]), int(nR[b]), int(nL[al]), [(dense_off, 1, d * Dr) + one])
-            # out[oL+i, s, oR+j] = X[b][j, m_off + i]
-            g_unpack.chunk(dense_off, d * Dr, int(nL[al]), int(nR[b]), [(x_off, 1, int(M[b])) + one])
-        for (b, K), (g, n_off) in self.rb_chunk.items():
-            g_pack_r.chunk(int(self.offRB[b] + n_off), int(N1[b]), int(nR[b]), int(nR[g]),
-                           [(int((oR[b] * cr + K) * Dr + oR[g]), cr * Dr, 1) + one])
-        for (ap, al, k), kk in self.t2_row.items():
-            g_pack_l.chunk(int(self.offLP[ap] + kk * nL[ap]), int(nL[ap]), int(nL[al]), int(nL[ap]),
-                           [(int((oL[al] * cl + k) * Dl + oL[ap]), cl * Dl, 1) + one])
-        for (ap, sp), (g, n_off) in self.t2_col.items():
-            # X chunk (a', s') of group g:  X[g][j', m_off + i'] = sum_p O_(a',p)[n_off + j', i']
-            _, m_off = self.x_chunk[(ap, sp)]
-            terms = [(int(off + n_off * nL[ap]), int(nL[ap]), 1) + one for off in self.offO[ap]]
-            g_repack.chunk(int(self.offX[g] + m_off), int(M[g]), int(nR[g]), int(nL[ap]), terms)
-        self.g_host = {"pack_a": g_pack_a.finish(), "unpack": g_unpack.finish(), "pack_r": g_pack_r.finish(),
-                       "pack_l": g_pack_l.finish(), "repack": g_repack.finish()}
+        one = np.ones(len(xb), dtype=np.int64)
+        dense_off = (oL[xal] * d + xs) * Dr + oR[xb]
+        x_off = self.offX[xb] + xm
+        # X[b][j, m_off + i] = a[oL+i, s, oR+j]
+        pack_a = _gather_tables(x_off, Mp[xb], nR[xb], nL[xal], one, dense_off, one, one * (d * Dr))
+        # out[oL+i, s, oR+j] = X[b][j, m_off + i]
+        unpack = _gather_tables(dense_off, one * (d * Dr), nL[xal], nR[xb], one, x_off, one, Mp[xb])
+        one = np.ones(len(rb_b), dtype=np.int64)
+        pack_r = _gather_tables(self.offRB[rb_b] + rb_n, N1p[rb_b], nR[rb_b], nR[rb_g], one,
+                                (oR[rb_b] * cr + rb_K) * Dr + oR[rb_g], one * (cr * Dr), one)
+        one = np.ones(len(tr_ap), dtype=np.int64)
+        pack_l = _gather_tables(self.offLP[tr_ap] + tr_kk * nLp[tr_ap], nLp[tr_ap], nL[tr_al], nL[tr_ap], one,
+                                (oL[tr_al] * cl + tr_k) * Dl + oL[tr_ap], one * (cl * Dl), one)
+        # X chunk (a', s') of group g:  X[g][j', m_off + i'] = sum_p O_(a',p)[n_off + j', i']
+        cnt = npc[tc_ap]
+        ci = np.repeat(np.arange(len(tc_ap)), cnt)
+        pidx = pc_first[tc_ap[ci]] + (np.arange(int(cnt.sum())) - excl(cnt)[ci])
+        t_ap = tc_ap[ci]
+        repack = _gather_tables(self.offX[tc_g] + self.XM[tc_ap, tc_sp], Mp[tc_g], nR[tc_g], nL[tc_ap], cnt,
+                                pc_off[pidx] + tc_n[ci] * nLp[t_ap], nLp[t_ap], np.ones(len(ci), dtype=np.int64))
+        self.g_host = {"pack_a": pack_a, "unpack": unpack, "pack_r": pack_r, "pack_l": pack_l, "repack": repack}
 
     # -------------------------------------------------------------------------------------------------
     def flop_counts(self):
@@ -304,45 +365,63 @@ class PackedHeffPlan:
         self._wcache[key] = (tables, w)
         return tables
 
-    def w_tables_host(self, wh):
-        """Host tables (chunks, terms, work) of the W step for the MPO tensor values `wh` (NumPy)."""
+    def w_tables_host(self, wh, transposed=False):
+        """Host tables (chunks, terms, work) of the W step for the MPO tensor values `wh` (NumPy): one chunk per
+        (a', k, s') block of T2, one term per non-zero MPO entry w[k, s', s, K] that connects it to a block of T1.
+        `transposed`: source and destination are the transposed intermediates T1^T (N1 x M per group) and T2^T
+        (N3 x K3 per group) of the environment update (`PackedEnvPlan`)."""
         Dl, d, Dr, cl, cr = self.dims
         assert wh.shape == (cl, d, d, cr)
         _, _, nL = self.L
         _, _, nR = self.R
-        nz = {}
-        for k, sp, s, K in zip(*np.nonzero(wh)):
-            nz.setdefault((int(k), int(sp)), []).append((int(s), int(K), complex(wh[k, sp, s, K])))
-        gw = _Gather()
-        for (ap, al, k), kk in self.t2_row.items():
-            for sp in range(d):
-                col = self.t2_col.get((ap, sp))
-                if col is None:
-                    continue
-                g, n_off = col
-                terms = []
-                for s, K, val in nz.get((k, sp), []):
-                    src = self.x_chunk.get((al, s))
-                    if src is None:
-                        continue
-                    b, m_off = src
-                    rb = self.rb_chunk.get((b, K))
-                    if rb is None or rb[0] != g:
-                        continue            # an MPO entry that violates charge conservation would meet structural zeros
-                    terms.append((int(self.offT1[b] + m_off * self.N1[b] + rb[1]), int(self.N1[b]), 1,
-                                  val.real, val.imag))
-                gw.chunk(int(self.offT2[ap] + kk * self.N3[ap] + n_off), int(self.N3[ap]), int(nL[al]), int(nR[g]),
-                         terms)
-        return gw.finish()
+        tr_ap, tr_k, tr_al, tr_kk = self.tr
+        nrow = len(tr_ap)
+        # chunks: (row entry (a', k, alpha), s') with a column block in group a'
+        c_row, c_sp = np.repeat(np.arange(nrow), d), np.tile(np.arange(d), nrow)
+        c_g = self.TCG[tr_ap[c_row], c_sp]
+        ok = c_g >= 0
+        c_row, c_sp, c_g = c_row[ok], c_sp[ok], c_g[ok]
+        chunk_id = np.full((nrow, d), -1, dtype=np.int64)
+        chunk_id[c_row, c_sp] = np.arange(len(c_row))
+        # terms: non-zero entries (k, s', s, K) x row entries with the same k
+        nk, nsp, ns, nK = np.nonzero(wh)
+        vals = wh[nk, nsp, ns, nK]
+        rows_of_k = [np.flatnonzero(tr_k == k) for k in range(cl)]
+        cnt = np.array([len(rows_of_k[k]) for k in nk], dtype=np.int64)
+        e = np.repeat(np.arange(len(nk)), cnt)                       # entry index of every candidate term
+        rw = np.concatenate([rows_of_k[k] for k in nk]) if len(nk) else np.zeros(0, dtype=np.int64)
+        cid = chunk_id[rw, nsp[e]]
+        b = self.XB[tr_al[rw], ns[e]]
+        ok = (cid >= 0) & (b >= 0)
+        # an MPO entry that violates charge conservation would meet structural zeros: it has no term
+        ok &= self.RBG[np.maximum(b, 0), nK[e]] == np.where(cid >= 0, c_g[np.maximum(cid, 0)], -2)
+        e, rw, cid, b = e[ok], rw[ok], cid[ok], b[ok]
+        order = np.argsort(cid, kind="stable")
+        e, rw, cid, b = e[order], rw[order], cid[order], b[order]
+        v = vals[e]
+        ap = tr_ap[c_row]
+        nterms = np.bincount(cid, minlength=len(c_row))
+        one = np.ones(len(b), dtype=np.int64)
+        if transposed:
+            # T2T[a'][(s', j'), (k, alpha, i)] = sum w T1T[b][(K, j'), (alpha, s, i)]
+            src = self.offT1[b] + self.RBN[b, nK[e]] * self.Mp[b] + self.XM[tr_al[rw], ns[e]]
+            return _gather_tables(self.offT2T[ap] + self.TCN[ap, c_sp] * self.K3p[ap] + tr_kk[c_row], self.K3p[ap],
+                                  nR[c_g], nL[tr_al[c_row]], nterms, src, self.Mp[b], one, np.real(v), np.imag(v))
+        src = self.offT1[b] + self.XM[tr_al[rw], ns[e]] * self.N1p[b] + self.RBN[b, nK[e]]
+        return _gather_tables(self.offT2[ap] + tr_kk[c_row] * self.N3p[ap] + self.TCN[ap, c_sp], self.N3p[ap],
+                              nL[tr_al[c_row]], nR[c_g], nterms, src, self.N1p[b], one, np.real(v), np.imag(v))
 
     def device_tables(self, device):
         key = device.index
         hit = self._dev.get(key)
         if hit is None:
-            up = lambda t: torch.from_numpy(t.view(np.uint8).reshape(-1)).to(device)      # noqa: E731
-            hit = {"tiles1": up(self.tiles1_host), "tiles3": up(self.tiles3_host)}
-            for name, tabs in self.g_host.items():
-                hit[name] = _DeviceGather(tabs, device)
+            names = list(self.g_host)
+            arrays = [self.tiles1_host, self.tiles3_host] + [t for n in names for t in self.g_host[n]]
+            buf, offs = _pack_segments(arrays)
+            dbuf = torch.from_numpy(buf).to(device)            # ONE upload for all tables of the plan
+            hit = {"tiles1": dbuf[offs[0]:], "tiles3": dbuf[offs[1]:]}
+            for i, name in enumerate(names):
+                hit[name] = _DeviceGather(self.g_host[name], device, [dbuf[o:] for o in offs[2 + 3 * i: 5 + 3 * i]])
             self._dev[key] = hit
         return hit
 
@@ -388,7 +467,8 @@ class PackedHeffOperator:
     def pack(self, a):
         plan = self.plan
         a = dev.as_dtype(a, plan.cplx)
-        x = torch.empty(max(plan.nX, 1), dtype=a.dtype, device=a.device)
+        alloc = torch.empty if plan.cplx else torch.zeros          # float64: padding entries must be zero
+        x = alloc(max(plan.nX, 1), dtype=a.dtype, device=a.device)
         self.tabs["pack_a"].run(self.lib, self.dt, a, x, dev.stream_ptr(a.device))
         return x[:plan.nX]
 
@@ -404,7 +484,7 @@ class PackedHeffOperator:
         assert x.shape[0] == plan.nX
         x = dev.as_dtype(x, plan.cplx)
         stream = dev.stream_ptr(x.device)
-        y = torch.empty(max(plan.nX, 1), dtype=x.dtype, device=x.device)
+        y = (torch.empty if plan.cplx else torch.zeros)(max(plan.nX, 1), dtype=x.dtype, device=x.device)
         n1, n3 = len(plan.tiles1_host), len(plan.tiles3_host)
         if n1:
             _lib.check(lib.ptb_gemm_grouped(dt, x.data_ptr(), self.rb.data_ptr(), self.t1.data_ptr(),
@@ -419,3 +499,156 @@ class PackedHeffOperator:
     def apply_dense(self, a):
         """Dense in, dense out (tests / one-off calls): pack, one matvec, unpack."""
         return self.unpack(self(self.pack(a)))
+
+
+class PackedEnvPlan:
+    """
+    `contraction_operator_step_right / _left` (pytenet/chain_ops.py:16-57, 60-99; bra = ket, as in the sweeps) on
+    the sector-packed layouts -- the same two kernels as the matvec, no structural zero stored or multiplied:
+
+        step_right(a, w, r)[i,k,i'] = sum a[i,s,j] r[j,K,j'] w[k,s',s,K] conj(a[i',s',j'])
+
+      1  X = pack(a), RB = pack(r)                            (block gathers, as for the matvec)
+      2  T1^T_b (N1 x M) = RB_b^T X_b                         grouped GEMM, contraction over the right sector b
+      3  T2^T_a'[(s',j'), (k,alpha,i)] = sum w T1^T[..]       block gather, coefficients = MPO entries
+      4  BT_a'[(s',j'), i'] = conj(a[i',s',j'])               block gather from X with the conjugate flag
+      5  O_a' (K3 x n_a') = T2^T_a'^T BT_a'                   grouped GEMM, contraction over (s',j') split into pieces
+      6  r_next[i,k,i'] = sum of the pieces                   block gather into the dense (zero-initialised) block
+
+    `side="left"` is the same computation on the mirrored tensors a~[j,s,i] = a[i,s,j], w~[K,s',s,k] = w[k,s',s,K],
+    r~ = l with quantum numbers (-qr, qs, -ql, -qwr, -qwl): mirroring only changes the strides in the pack table of
+    `a` and the (host) index order of the MPO entries, nothing is transposed in memory.
+    """
+
+    def __init__(self, ql, qs, qr, qwl, qwr, cplx=True, side="right"):
+        assert side in ("left", "right")
+        self.side = side
+        self.cplx = bool(cplx)
+        ql, qs, qr, qwl, qwr = (np.asarray(q, dtype=np.int64) for q in (ql, qs, qr, qwl, qwr))
+        self.dims = (len(ql), len(qs), len(qr), len(qwl), len(qwr))
+        if side == "left":
+            ql, qr, qwl, qwr = -qr, -ql, -qwr, -qwl
+        base = self.base = PackedHeffPlan(ql, qs, qr, qwl, qwr, cplx=cplx)
+        self.supported = base.supported
+        self._dev = {}
+        self._wcache = {}
+        if not self.supported:
+            return
+        Dl, d, Dr, cl, cr = base.dims              # of the (possibly mirrored) problem
+        BM, BN, _ = base.tile
+        _, oL, nL = base.L
+        _, oR, nR = base.R
+        excl = lambda v: np.cumsum(v) - v          # noqa: E731
+        Mp, N1p, N3, K3, K3p, nLp = base.Mp, base.N1p, base.N3, base.K3, base.K3p, base.nLp
+        # pack of `a`: X[b][j, m_off + i] = a~[oL+i, s, oR+j]; strides (sx, ss, sy) of a~ in the memory of `a`
+        sx, ss, sy = (d * Dr, Dr, 1) if side == "right" else (1, Dl, d * Dl)
+        xs, xal, xb, xm = base.xc
+        one = np.ones(len(xb), dtype=np.int64)
+        pack_a = _gather_tables(base.offX[xb] + xm, Mp[xb], nR[xb], nL[xal], one,
+                                oL[xal] * sx + xs * ss + oR[xb] * sy, one * sy, one * sx)
+        # T1^T_b = RB_b^T X_b
+        live1 = np.flatnonzero((base.M > 0) & (base.N1 > 0))
+        gi, tm, tn = _tiles_of(N1p[live1], Mp[live1], BM, BN)
+        b = live1[gi]
+        self.tiles1 = _tile_table_cols(base.offRB[b] + tm, base.offX[b] + tn, base.offT1[b] + tm * Mp[b] + tn,
+                                       N1p[b], Mp[b], Mp[b], np.minimum(BM, N1p[b] - tm), np.minimum(BN, Mp[b] - tn),
+                                       nR[b])
+        # BT_a'[(n_off(s') + j'), i'] = conj(X[g][j', m_off(a', s') + i'])
+        tc_ap, tc_sp, tc_g, tc_n = base.tc
+        self.offBT = excl(N3 * nLp)
+        self.nBT = int(np.sum(N3 * nLp))
+        one = np.ones(len(tc_ap), dtype=np.int64)
+        pack_bt = _gather_tables(self.offBT[tc_ap] + tc_n * nLp[tc_ap], nLp[tc_ap], nR[tc_g], nL[tc_ap], one,
+                                 base.offX[tc_g] + base.XM[tc_ap, tc_sp], Mp[tc_g], one, conj=True)
+        # O_(a',p) (K3 x n_a') = T2^T_a'[rows k0:k1]^T BT_a'[rows k0:k1]
+        pc_ap, pc_k0, pc_k1, npc, pc_first = _k_pieces(N3, (K3 > 0) & (N3 > 0))
+        pc_size = K3p[pc_ap] * nLp[pc_ap]
+        pc_off = excl(pc_size)
+        self.nO = int(pc_size.sum())
+        gi, tm, tn = _tiles_of(K3p[pc_ap], nLp[pc_ap], BM, BN)
+        ap, k0 = pc_ap[gi], pc_k0[gi]
+        self.tiles3 = _tile_table_cols(base.offT2T[ap] + k0 * K3p[ap] + tm, self.offBT[ap] + k0 * nLp[ap] + tn,
+                                       pc_off[gi] + tm * nLp[ap] + tn, K3p[ap], nLp[ap], nLp[ap],
+                                       np.minimum(BM, K3p[ap] - tm), np.minimum(BN, nLp[ap] - tn), pc_k1[gi] - k0)
+        # out[oL[alpha]+i, k, oL[a']+i'] = sum_p O_(a',p)[kk + i, i']
+        tr_ap, tr_k, tr_al, tr_kk = base.tr
+        cnt = npc[tr_ap]
+        ci = np.repeat(np.arange(len(tr_ap)), cnt)
+        pidx = pc_first[tr_ap[ci]] + (np.arange(int(cnt.sum())) - excl(cnt)[ci])
+        t_ap = tr_ap[ci]
+        one = np.ones(len(tr_ap), dtype=np.int64)
+        unpack = _gather_tables((oL[tr_al] * cl + tr_k) * Dl + oL[tr_ap], one * (cl * Dl), nL[tr_al], nL[tr_ap], cnt,
+                                pc_off[pidx] + tr_kk[ci] * nLp[t_ap], nLp[t_ap], np.ones(len(ci), dtype=np.int64))
+        self.g_host = {"pack_a": pack_a, "pack_r": base.g_host["pack_r"], "pack_bt": pack_bt, "unpack": unpack}
+
+    def w_tables_host(self, wh):
+        """Tables of the W step (T1^T -> T2^T) for the MPO tensor values `wh` (as passed to the contraction)."""
+        if self.side == "left":
+            wh = np.ascontiguousarray(np.transpose(wh, (3, 1, 2, 0)))
+        return self.base.w_tables_host(wh, transposed=True)
+
+    def _w_tables(self, w):
+        key = (w.data_ptr(), w._version, tuple(w.shape), w.dtype)
+        hit = self._wcache.get(key)
+        if hit is not None:
+            return hit[0]
+        tables = _DeviceGather(self.w_tables_host(w.detach().cpu().numpy()), w.device)
+        if len(self._wcache) > 8:
+            self._wcache.clear()
+        self._wcache[key] = (tables, w)
+        return tables
+
+    def device_tables(self, device):
+        key = device.index
+        hit = self._dev.get(key)
+        if hit is None:
+            names = list(self.g_host)
+            arrays = [self.tiles1, self.tiles3] + [t for n in names for t in self.g_host[n]]
+            buf, offs = _pack_segments(arrays)
+            dbuf = torch.from_numpy(buf).to(device)
+            hit = {"tiles1": dbuf[offs[0]:], "tiles3": dbuf[offs[1]:]}
+            for i, name in enumerate(names):
+                hit[name] = _DeviceGather(self.g_host[name], device, [dbuf[o:] for o in offs[2 + 3 * i: 5 + 3 * i]])
+            self._dev[key] = hit
+        return hit
+
+    def apply(self, a, w, env):
+        """The next environment block: `step_right(a, a, w, env)` resp. `step_left(a, a, w, env)` (dense in / out)."""
+        base = self.base
+        Dl, d, Dr, cl, cr = base.dims
+        da, dd, db, dcl, dcr = self.dims
+        assert tuple(a.shape) == (da, dd, db) and tuple(w.shape) == (dcl, dd, dd, dcr)
+        assert tuple(env.shape) == (Dr, cr, Dr)
+        assert dev.any_complex(a, w, env) == self.cplx
+        lib = _lib.load()
+        dt = _lib.PTB_COMPLEX128 if self.cplx else _lib.PTB_REAL64
+        dtype = dev.C128 if self.cplx else dev.F64
+        device = a.device
+        tabs = self.device_tables(device)
+        wtab = self._w_tables(dev.dense(w))
+        stream = dev.stream_ptr(device)
+        a = dev.as_dtype(a, self.cplx); env = dev.as_dtype(env, self.cplx)
+        es = 16 if self.cplx else 8
+        sizes = [base.nX, base.nRB, base.nT1, base.nT2T, self.nBT, self.nO]
+        offs, pos = [], 0
+        for n in sizes:
+            offs.append(pos)
+            pos += (max(n, 1) * es + 63) // 64 * 64
+        ws = dev.workspace(pos, device, tag="packed_env")
+        x, rb, t1, t2, bt, o = (ws[o_:o_ + max(n, 1) * es].view(dtype) for o_, n in zip(offs, sizes))
+        if not self.cplx:
+            x.zero_()                                            # padding columns take part in step 2
+        tabs["pack_a"].run(lib, dt, a, x, stream)
+        tabs["pack_r"].run(lib, dt, env, rb, stream)
+        n1, n3 = len(self.tiles1), len(self.tiles3)
+        if n1:
+            _lib.check(lib.ptb_gemm_grouped(dt, rb.data_ptr(), x.data_ptr(), t1.data_ptr(), tabs["tiles1"].data_ptr(),
+                                            n1, stream), "ptb_gemm_grouped(env 1)")
+        wtab.run(lib, dt, t1, t2, stream)
+        tabs["pack_bt"].run(lib, dt, x, bt, stream)
+        if n3:
+            _lib.check(lib.ptb_gemm_grouped(dt, t2.data_ptr(), bt.data_ptr(), o.data_ptr(), tabs["tiles3"].data_ptr(),
+                                            n3, stream), "ptb_gemm_grouped(env 3)")
+        out = torch.zeros((Dl, cl, Dl), dtype=dtype, device=device)
+        tabs["unpack"].run(lib, dt, o, out, stream)
+        return out

@@ -181,7 +181,8 @@ def test_batched_sector_svd(cuda_lib, cplx):
 
 
 @pytest.mark.parametrize("shape,cplx", [((1024, 1024), True), ((900, 1300), False), ((1500, 800), True),
-                                        ((256, 300), True), ((400, 260), False)])
+                                        ((256, 300), True), ((400, 260), False), ((64, 64), True), ((100, 70), True),
+                                        ((128, 200), False), ((97, 97), False)])
 def test_dense_svd_polar_driver(cuda_lib, shape, cplx):
     """block_sparse_util.dense_svd on large blocks (cuSOLVER's polar-decomposition driver through ptb_svd_polar):
     singular values equal LAPACK's to 1e-13 of the largest -- also for a spectrum graded over ten decades --, the
@@ -209,3 +210,59 @@ def test_dense_svd_polar_driver(cuda_lib, shape, cplx):
         assert np.all(np.diff(s) <= 1e-15 * ws[0])
         assert rel((u * s) @ vh, a) < 1e-13
         assert rel(u.conj().T @ u, np.eye(k)) < 1e-12 and rel(vh @ vh.conj().T, np.eye(k)) < 1e-12
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+def test_dense_svd_batch_concurrent_blocks(cuda_lib, cplx):
+    """block_sparse_util.dense_svd_batch (ptb_svd_polar_batch: the independent sector blocks of one split on
+    concurrent worker streams): every block equals LAPACK's singular values to 1e-13 of its largest, isometric
+    factors, reconstruction -- mid-size, wide, tall, graded, and blocks below the polar threshold in the same batch."""
+    from pytenet_b200.block_sparse_util import dense_svd_batch
+    rng = np.random.default_rng(77 + int(cplx))
+    shapes = [(70, 90), (130, 130), (200, 150), (64, 64), (30, 41), (96, 300), (257, 129), (180, 180), (75, 64),
+              (64, 201), (222, 222)]
+    mats = []
+    for m, n in shapes:
+        a = rng.normal(size=(m, n)) + (1j * rng.normal(size=(m, n)) if cplx else 0)
+        if (m + n) % 3 == 0:                                 # graded spectrum over eight decades
+            k = min(m, n)
+            u, _, vh = np.linalg.svd(a, full_matrices=False)
+            a = (u * np.logspace(0, -8, k)) @ vh
+        mats.append(np.ascontiguousarray(a))
+    for rep in range(2):                                     # second call reuses the worker slots
+        outs = dense_svd_batch([torch.from_numpy(a).cuda() for a in mats])
+        assert len(outs) == len(mats)
+        for a, (u, s, vh) in zip(mats, outs):
+            m, n = a.shape
+            k = min(m, n)
+            u, s, vh = u.resolve_conj().cpu().numpy(), s.cpu().numpy(), vh.resolve_conj().cpu().numpy()
+            ws = np.linalg.svd(a, compute_uv=False)
+            assert u.shape == (m, k) and vh.shape == (k, n)
+            assert np.max(np.abs(s - ws)) < 1e-13 * ws[0]
+            assert rel((u * s) @ vh, a) < 1e-13
+            assert rel(u.conj().T @ u, np.eye(k)) < 1e-12 and rel(vh @ vh.conj().T, np.eye(k)) < 1e-12
+
+
+def test_block_sparse_svd_with_many_mid_size_sectors_matches_oracle(cuda_lib):
+    """A two-site split at config-3-like sector sizes (sector blocks of 100-250 rows: too large for the batched
+    Jacobi kernel, factorised concurrently by the polar driver): singular values, sector order and retained
+    indices equal the oracle's block_sparse_svd / retained_bond_indices."""
+    import pytenet_b200 as ptb
+    import oracle.blocksparse as ob
+    rng = np.random.default_rng(5)
+    sizes0 = [110, 240, 17, 180, 150, 64]
+    sizes1 = [130, 200, 25, 190, 90, 70]
+    q0 = np.concatenate([np.full(n, q) for q, n in zip([-2, -1, 0, 1, 2, 3], sizes0)])
+    q1 = np.concatenate([np.full(n, q) for q, n in zip([-2, -1, 0, 1, 2, 3], sizes1)])
+    p0, p1 = rng.permutation(len(q0)), rng.permutation(len(q1))
+    q0, q1 = q0[p0], q1[p1]
+    a = rng.normal(size=(len(q0), len(q1))) + 1j * rng.normal(size=(len(q0), len(q1)))
+    ob.enforce_qsparsity(a, [q0, -q1])
+    u, s, v, q = ptb.block_sparse_svd(torch.from_numpy(a).cuda(), q0, q1)
+    uo, so, vo, qo = ob.block_sparse_svd(a, q0, q1)
+    assert np.array_equal(q, qo)
+    assert np.max(np.abs(s - so)) < 1e-13 * so.max()
+    u, v = u.resolve_conj().cpu().numpy(), v.resolve_conj().cpu().numpy()
+    assert rel((u * s) @ v, a) < 1e-13
+    for tol in (0.0, 1e-8, 1e-2):
+        assert np.array_equal(ptb.retained_bond_indices(s, tol), ob.retained_bond_indices(so, tol))

@@ -58,13 +58,47 @@ def test_grouped_gemm_kernel_against_numpy(cuda_lib):
     assert np.array_equal(got[untouched], C0[untouched])
 
 
-def _block_sparse_problem(rng, Dl, d, Dr, cl, cr, lo=-2, hi=2):
+def test_grouped_gemm_kernel_float64_against_numpy(cuda_lib):
+    """float64 tiles (128 x 128): the bulk copies move 16-byte granules, so offsets, leading dimensions and the m / n
+    extents are even (what `PackedHeffPlan(cplx=False)` emits); contraction lengths arbitrary."""
+    from pytenet_b200.sector_packed import _tile_table
+    rng = np.random.default_rng(13)
+    nA, nB, nC = 400000, 300000, 400000
+    A, B, C0 = rng.normal(size=nA), rng.normal(size=nB), rng.normal(size=nC)
+    tiles, want = [], C0.copy()
+    c_pos = 0
+    for (m, n, k) in [(128, 128, 16), (128, 128, 300), (2, 2, 1), (6, 4, 2), (38, 64, 50), (128, 10, 7), (34, 18, 129),
+                      (128, 64, 4), (64, 128, 33), (100, 50, 1), (2, 128, 18), (128, 2, 5), (78, 32, 255)] * 3:
+        lda = m + 2 * int(rng.integers(0, 5)); ldb = n + 2 * int(rng.integers(0, 5)); ldc = n + int(rng.integers(0, 5))
+        a_off = 2 * int(rng.integers(0, (nA - k * lda - m) // 2)); b_off = 2 * int(rng.integers(0, (nB - k * ldb - n) // 2))
+        c_off = c_pos
+        c_pos += m * ldc + 7
+        assert c_pos < nC
+        tiles.append((a_off, b_off, c_off, lda, ldb, ldc, m, n, k))
+        a = A[a_off + np.arange(k)[:, None] * lda + np.arange(m)[None, :]]
+        b = B[b_off + np.arange(k)[:, None] * ldb + np.arange(n)[None, :]]
+        want[c_off + np.arange(m)[:, None] * ldc + np.arange(n)[None, :]] = a.T @ b
+    tab = _tile_table(tiles)
+    dA, dB, dC = cu(A), cu(B), cu(C0)
+    dT = torch.from_numpy(tab.view(np.uint8).reshape(-1)).cuda()
+    st = cuda_lib.ptb_gemm_grouped(0, dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), dT.data_ptr(), len(tab),
+                                   torch.cuda.current_stream().cuda_stream)
+    assert st == 0
+    got = dC.cpu().numpy()
+    assert rel(got, want) < 1e-13
+    untouched = np.ones(nC, dtype=bool)
+    for (a_off, b_off, c_off, lda, ldb, ldc, m, n, k) in tiles:
+        untouched[(c_off + np.arange(m)[:, None] * ldc + np.arange(n)[None, :]).reshape(-1)] = False
+    assert np.array_equal(got[untouched], C0[untouched])
+
+
+def _block_sparse_problem(rng, Dl, d, Dr, cl, cr, lo=-2, hi=2, cplx=True):
     ql = np.sort(rng.integers(lo, hi + 1, size=Dl)); qr = np.sort(rng.integers(lo - 1, hi + 1, size=Dr))
     qs = rng.integers(-1, 2, size=d)
     qwl, qwr = rng.integers(-1, 2, size=cl), rng.integers(-1, 2, size=cr)
 
     def tensor(shape, qn):
-        t = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+        t = rng.normal(size=shape) + (1j * rng.normal(size=shape) if cplx else 0)
         ob.enforce_qsparsity(t, qn)
         return t
     a = tensor((Dl, d, Dr), [ql, qs, -qr])
@@ -74,20 +108,22 @@ def _block_sparse_problem(rng, Dl, d, Dr, cl, cr, lo=-2, hi=2):
     return (ql, qs, qr, qwl, qwr), a, w, l, r
 
 
+@pytest.mark.parametrize("cplx", [True, False])
 @pytest.mark.parametrize("seed,dims", [(1, (300, 2, 260, 5, 5)), (2, (150, 4, 330, 6, 6)), (3, (420, 3, 129, 4, 5)),
-                                       (4, (64, 16, 64, 6, 6))])
-def test_packed_matvec_matches_oracle(cuda_lib, seed, dims):
+                                       (4, (64, 16, 64, 6, 6)), (5, (201, 3, 177, 3, 4))])
+def test_packed_matvec_matches_oracle(cuda_lib, seed, dims, cplx):
     """PackedHeffOperator: pack -> grouped GEMM -> W gather -> grouped GEMM -> repack -> unpack equals the oracle's
     dense contraction; forbidden entries of the result are exactly zero; pack / unpack are inverse on allowed
     entries; the packed matvec is linear and reusable across vectors."""
     import pytenet_b200 as ptb
     from pytenet_b200.sector_packed import PackedHeffPlan
     rng = np.random.default_rng(seed)
-    qn, a, w, l, r = _block_sparse_problem(rng, *dims)
-    plan = PackedHeffPlan(*qn, cplx=True)
+    qn, a, w, l, r = _block_sparse_problem(rng, *dims, cplx=cplx)
+    plan = PackedHeffPlan(*qn, cplx=cplx)
     assert plan.supported
     op = plan.bind(cu(w), cu(l), cu(r))
     x = op.pack(cu(a))
+    assert x.dtype == (torch.complex128 if cplx else torch.float64)
     assert rel(op.unpack(x).cpu().numpy(), a) == 0.0
     got = op.unpack(op(x)).cpu().numpy()
     ref = oracle.apply_local_hamiltonian(a, w, l, r)
@@ -95,7 +131,7 @@ def test_packed_matvec_matches_oracle(cuda_lib, seed, dims):
     mask = ob.qnumber_outer_sum([qn[0], qn[1], -qn[2]]) != 0
     assert np.all(got[mask] == 0)
     # second vector on the same operator, linearity in the packed space
-    a2 = a[::-1].copy() * (0.3 - 0.7j); ob.enforce_qsparsity(a2, [qn[0], qn[1], -qn[2]])
+    a2 = a[::-1].copy() * ((0.3 - 0.7j) if cplx else 0.3); ob.enforce_qsparsity(a2, [qn[0], qn[1], -qn[2]])
     x2 = op.pack(cu(a2))
     y12 = op(x + 2 * x2)
     assert (torch.linalg.norm(y12 - (op(x) + 2 * op(x2))) / torch.linalg.norm(y12)).item() < 1e-13
@@ -104,6 +140,35 @@ def test_packed_matvec_matches_oracle(cuda_lib, seed, dims):
     assert abs(torch.vdot(x, x2).item() - np.vdot(a, a2)) < 1e-10 * np.linalg.norm(a) * np.linalg.norm(a2)
     dense = ptb.apply_local_hamiltonian(cu(a), cu(w), cu(l), cu(r)).cpu().numpy()
     assert rel(got, dense) < 1e-13
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+@pytest.mark.parametrize("side", ["right", "left"])
+@pytest.mark.parametrize("seed,dims", [(1, (300, 2, 260, 5, 5)), (2, (150, 4, 330, 6, 6)), (3, (421, 3, 129, 4, 5)),
+                                       (4, (1, 4, 4, 1, 6)), (5, (700, 4, 700, 6, 6))])
+def test_packed_environment_update_matches_oracle(cuda_lib, seed, dims, side, cplx):
+    """PackedEnvPlan.apply == the oracle's contraction_operator_step_right / _left on block-sparse inputs (1e-12),
+    forbidden entries of the new block exactly zero, and equal to the dense device contraction."""
+    import pytenet_b200 as ptb
+    from pytenet_b200.sector_packed import PackedEnvPlan
+    rng = np.random.default_rng(seed)
+    qn, a, w, l, r = _block_sparse_problem(rng, *dims, cplx=cplx)
+    plan = PackedEnvPlan(*qn, cplx=cplx, side=side)
+    assert plan.supported
+    if side == "right":
+        got = plan.apply(cu(a), cu(w), cu(r)).cpu().numpy()
+        ref = oracle.contraction_operator_step_right(a, a, w, r)
+        dense = ptb.contraction_operator_step_right(cu(a), cu(a), cu(w), cu(r)).cpu().numpy()
+        mask = ob.qnumber_outer_sum([qn[0], qn[3], -qn[0]]) != 0
+    else:
+        got = plan.apply(cu(a), cu(w), cu(l)).cpu().numpy()
+        ref = oracle.contraction_operator_step_left(a, a, w, l)
+        dense = ptb.contraction_operator_step_left(cu(a), cu(a), cu(w), cu(l)).cpu().numpy()
+        mask = ob.qnumber_outer_sum([qn[2], qn[4], -qn[2]]) != 0
+    assert got.shape == ref.shape
+    assert rel(got, ref) < TOL
+    assert rel(got, dense) < 1e-13
+    assert np.all(got[mask] == 0)
 
 
 def test_config3_reduced_D_reference_generator_profile_vs_oracle(cuda_lib):
