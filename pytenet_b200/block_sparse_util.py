@@ -50,6 +50,22 @@ def qnumber_flatten(qnums):
     return qnumber_outer_sum(qnums).reshape(-1)
 
 
+_QVEC_CACHE = {}
+
+
+def _qvec(q, device):
+    """Quantum numbers of one axis as an int64 device vector, cached by content: sweeps test the same bonds again
+    every step, and a host->device copy from pageable memory is a synchronisation point."""
+    q = np.ascontiguousarray(q, dtype=np.int64)
+    key = (q.tobytes(), device.index)
+    t = _QVEC_CACHE.get(key)
+    if t is None:
+        if len(_QVEC_CACHE) >= 4096:
+            _QVEC_CACHE.clear()
+        t = _QVEC_CACHE[key] = torch.as_tensor(q, device=device)
+    return t
+
+
 def _forbidden_mask(qnums, device):
     """Boolean device tensor: True where the quantum numbers do not sum to zero.
     Built by broadcasting the per-axis vectors on the device (no dense host mask)."""
@@ -58,12 +74,17 @@ def _forbidden_mask(qnums, device):
     for ax, q in enumerate(qnums):
         shape = [1] * nd
         shape[ax] = len(q)
-        t = torch.as_tensor(np.asarray(q, dtype=np.int64), device=device).reshape(shape)
+        t = _qvec(q, device).reshape(shape)
         total = t if total is None else total + t
     return total != 0
 
 
 _CAPTURING = False      # set while a sweep step is captured into a CUDA graph (tdvp._StepGraph)
+
+
+def _violations(a, qnums):
+    """0-dim bool device tensor: some forbidden entry of `a` is non-zero (one fused pass, no boolean gather)."""
+    return torch.any((a != 0) & _forbidden_mask(qnums, a.device))
 
 
 def is_qsparse(a, qnums):
@@ -73,10 +94,21 @@ def is_qsparse(a, qnums):
             return True                      # all quantum numbers zero: nothing is forbidden
         if _CAPTURING:
             return True                      # a device->host read cannot be captured; the eager steps checked it
-        mask = _forbidden_mask(qnums, a.device)
-        return not bool(torch.any((a != 0) & mask).item())         # one fused pass, no boolean gather
+        return not bool(_violations(a, qnums).item())
     mask = qnumber_outer_sum(qnums) != 0
     return not np.any(np.asarray(a)[mask])
+
+
+def _assert_qsparse(a, qnums, message="sparsity pattern must match quantum numbers"):
+    """The reference's `assert is_qsparse(...)` (:114, :254).  Inside the sweep drivers (krylov.deferred_checks) the
+    test runs on the device and its result is examined when the driver returns, so a factorisation is no
+    synchronisation point; elsewhere it is checked immediately."""
+    from . import krylov
+    if (isinstance(a, torch.Tensor) and a.is_cuda and krylov.deferring() and not _CAPTURING
+            and any(np.any(np.asarray(q)) for q in qnums)):
+        krylov.defer_flag(_violations(a, qnums), message)
+        return
+    assert is_qsparse(a, qnums), message
 
 
 def enforce_qsparsity(a, qnums):
@@ -211,6 +243,17 @@ def _qr_plan(q0, q1, shape, es, device):
     return plan
 
 
+_QR_STREAMS = {}
+_QR_MAX_STREAMS = 6
+
+
+def _qr_streams(device, n):
+    pool = _QR_STREAMS.setdefault(device.index, [])
+    while len(pool) < min(n, _QR_MAX_STREAMS):
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:min(n, _QR_MAX_STREAMS)]
+
+
 def block_sparse_qr(a, q0, q1):
     """
     Sector-wise reduced QR of a block-sparse matrix (`a[i, j] != 0` only if
@@ -220,7 +263,7 @@ def block_sparse_qr(a, q0, q1):
     assert a.ndim == 2
     q0 = np.ascontiguousarray(q0); q1 = np.ascontiguousarray(q1)
     assert len(q0) == a.shape[0] and len(q1) == a.shape[1]
-    assert is_qsparse(a, [q0, -q1])
+    _assert_qsparse(a, [q0, -q1])
     plan = _qr_plan(q0, q1, tuple(a.shape), a.element_size(), a.device)
     if len(plan.sectors) == 0:
         assert float(torch.linalg.norm(a)) == 0
@@ -235,6 +278,8 @@ def block_sparse_qr(a, q0, q1):
     nb = plan.nb
     q = torch.zeros((a.shape[0], nb), dtype=a.dtype, device=a.device)
     r = torch.zeros((nb, a.shape[1]), dtype=a.dtype, device=a.device)
+    main = torch.cuda.current_stream(a.device)
+    ready = main.record_event() if (len(plan.large) > 1 and not _CAPTURING) else None     # inputs and outputs exist
     if plan.small:
         # all sectors that fit in shared memory: ONE launch of the batched Householder kernel (csrc/block_qr.cu),
         # which gathers each block, factorises it with LAPACK's conventions and scatters Q and R into place
@@ -245,13 +290,23 @@ def block_sparse_qr(a, q0, q1):
                                       r.data_ptr(), a.shape[1], dev.stream_ptr(a.device))
         _lib.check(st, "ptb_block_qr")
     if plan.large:
+        # sectors beyond the shared-memory kernel: cuSOLVER per block.  A panel factorisation of a few hundred
+        # columns occupies a handful of SMs for ~0.5 ms, so the independent blocks are spread round-robin over side
+        # streams (gather, geqrf, orgqr and the scatter into disjoint parts of q / r all stay on the block's stream)
         nl = len(plan.large)
+        streams = _qr_streams(a.device, nl) if ready is not None else []
+        for st in streams:
+            st.wait_event(ready)            # the batched kernel of the small sectors overlaps too
         for j, i in enumerate(plan.large):
             rt, ct = plan.large_idx[j], plan.large_idx[nl + j]
-            qs, rs = torch.linalg.qr(a.index_select(0, rt).index_select(1, ct), mode="reduced")
             p0, sz = plan.starts[i], plan.sizes[i]
-            q[rt, p0:p0 + sz] = qs
-            r[p0:p0 + sz, ct] = rs
+            with torch.cuda.stream(streams[j % len(streams)] if streams else main):
+                qs, rs = torch.linalg.qr(a.index_select(0, rt).index_select(1, ct), mode="reduced")
+                q[rt, p0:p0 + sz] = qs
+                r[p0:p0 + sz, ct] = rs
+                del qs, rs
+        for st in streams:
+            main.wait_stream(st)
     return q, r, plan.qinterm.copy()
 
 
@@ -410,7 +465,7 @@ def block_sparse_svd(a, q0, q1):
     assert a.ndim == 2
     q0 = np.ascontiguousarray(q0); q1 = np.ascontiguousarray(q1)
     assert len(q0) == a.shape[0] and len(q1) == a.shape[1]
-    assert is_qsparse(a, [q0, -q1])
+    _assert_qsparse(a, [q0, -q1])
     plan = _qr_plan(q0, q1, tuple(a.shape), a.element_size(), a.device)       # same sector structure as the QR
     if len(plan.sectors) == 0:
         assert float(torch.linalg.norm(a)) == 0

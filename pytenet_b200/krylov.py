@@ -122,20 +122,50 @@ _DEFER_SLOTS = 2048
 _DEFER_WIDTH = 128
 
 
+_FLAG_SLOTS = 4096
+
+
 class _Deferred:
     depth = 0
     ring = None
     meta = []
+    flag_ring = None       # page-locked bools: device-side assertion results (True = violated)
+    flag_meta = []         # message per used slot
 
 
 def _flush_deferred():
-    if not _Deferred.meta:
+    if not _Deferred.meta and not _Deferred.flag_meta:
         return
     torch.cuda.synchronize()
+    if _Deferred.flag_meta:
+        flags = _Deferred.flag_ring.numpy()
+        msgs, _Deferred.flag_meta = _Deferred.flag_meta, []
+        for slot, msg in enumerate(msgs):
+            assert not flags[slot], msg
+    if not _Deferred.meta:
+        return
     host = _Deferred.ring.numpy()
     meta, _Deferred.meta = _Deferred.meta, []
     for slot, (n, numiter) in enumerate(meta):
         _check_scalars(host[slot], n, numiter)
+
+
+def deferring():
+    """True inside a `deferred_checks()` block (the sweep drivers)."""
+    return _Deferred.depth > 0
+
+
+def defer_flag(violated, message):
+    """Record a device-side assertion -- `violated` is a 0-dim bool device tensor that must be False -- without
+    synchronising: the flag is copied asynchronously into a page-locked ring and asserted when the enclosing
+    `deferred_checks()` block ends (the reference's assertions, e.g. block_sparse_util.py:114, issued later)."""
+    if _Deferred.flag_ring is None:
+        _Deferred.flag_ring = torch.zeros(_FLAG_SLOTS, dtype=torch.bool, pin_memory=True)
+    if len(_Deferred.flag_meta) == _FLAG_SLOTS:
+        _flush_deferred()
+    slot = len(_Deferred.flag_meta)
+    _Deferred.flag_ring[slot:slot + 1].copy_(violated.reshape(1), non_blocking=True)
+    _Deferred.flag_meta.append(message)
 
 
 class deferred_checks:

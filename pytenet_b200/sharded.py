@@ -369,6 +369,11 @@ class PrecontractedShardedHamiltonian:
     def matvec(self, a):
         """Apply the sharded effective Hamiltonian to `a` (Dl, d, Dr); every rank gets the full result."""
         assert tuple(a.shape) == (self.Dl, self.d_in, self.Dr)
+        if a.dtype.is_complex and not self.lw.dtype.is_complex:
+            # a complex state on a real operator: promote the operator once (never demote the state)
+            self.lw = self.lw.to(torch.complex128)
+            self.r_shard = self.r_shard.to(torch.complex128)
+            self._t1 = None
         a = a.to(self.lw.dtype) if a.dtype != self.lw.dtype else a
         a = a.contiguous()
         rows = self.Dl * self.d_in

@@ -7,7 +7,9 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 import pytenet_b200 as ptb
 warnings.simplefilter("ignore")
-L, D, k = 12, 2048, 10
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+D = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 h = ptb.fermi_hubbard_1d_mpo(L, 1.0, 4.0, 0.0)
 rng = np.random.default_rng(11)
 psi = ptb.MPS.construct_random(L, h.qsite, ptb.encode_quantum_number_pair(L, 0), max_vdim=D, rng=rng)
@@ -20,5 +22,5 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
 tot = sum(e.device_time_total for e in rows)
 print(f"total device time {tot / 1e3:.1f} ms in {sum(e.count for e in rows)} launches")
-for e in rows[:28]:
+for e in rows[:40]:
     print(f"{e.device_time_total / 1e3:9.2f} ms {100 * e.device_time_total / tot:5.1f}% {e.count:6d}x  {e.key[:100]}")

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 import pytenet_b200 as ptb
-from pytenet_b200 import _sweep
+from pytenet_b200 import _sweep, _prof
 
 warnings.simplefilter("ignore")
 ap = argparse.ArgumentParser()
@@ -44,7 +44,6 @@ for mode in (["auto", "0"] if args.dense else ["auto"]):
     tag = "sector_path" if mode == "auto" else "dense_path"
     for rep in ("first_step", "later_step"):        # later steps reuse the cached sector plans
         if args.prof:
-            from pytenet_b200 import _prof
             _prof.enable(True)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         if args.algo == "one":
@@ -58,6 +57,21 @@ for mode in (["auto", "0"] if args.dense else ["auto"]):
             res[f"device_seconds_by_phase_{tag}_{rep}"] = {k: v / 1e3 for k, v in _prof.report().items()}
             _prof.enable(False)
     finals[mode] = psi
+    if mode == "auto":
+        # the driver's prologue (right-orthonormalisation + all right environment blocks, tdvp.py:44-63) is part of
+        # every call: three more steps in ONE call give the cost of a time step without it
+        _prof.enable(False) if args.prof else None
+        psi3 = psi.copy()
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        if args.algo == "one":
+            ptb.tdvp_singlesite(h, psi3, dt, 3, numiter_lanczos=args.k)
+        else:
+            ptb.tdvp_twosite(h, psi3, dt, 3, numiter_lanczos=args.k, tol_split=args.tol)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter() - t0
+        res["seconds_three_steps_one_call"] = t3
+        res["seconds_per_step_without_prologue"] = (t3 - res[f"seconds_{tag}_later_step"]) / 2
+        del psi3
 if args.dense:
     ov = ptb.mps_vdot(finals["auto"], finals["0"])
     res["overlap_sector_vs_dense"] = [float(np.real(ov)), float(np.imag(ov))]
