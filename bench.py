@@ -158,10 +158,29 @@ def block_sparse_block(torch, ptb, device, time_ms, peak_tflops, D=2048):
         "intermediate_bytes": {"t1": pplan.nT1 * es, "t2": pplan.nT2 * es, "dense_layout_t1": 16.0 * D * d1 * d1 * 6 * D},
         "speedup_vs_dense": ms_d / ms_p, "speedup_vs_banded_round1": ms_b / ms_p,
     }
+    # ---- environment update (contraction_operator_step_right) at the same sector profile, one-site tensor ----
+    from pytenet_b200.sectors import EnvSectorPlan
+    from pytenet_b200.sector_packed import PackedEnvPlan
+    fill = float((a != 0).double().mean().item())
+    del a, x, y, op
+    w1 = torch.from_numpy(np.ascontiguousarray(wbulk)).to(device)
+    a1 = crand(D, d1, D); ptb.enforce_qsparsity(a1, [q, qsite, -q])
+    env_dense = ptb.contraction_operator_step_right(a1, a1, w1, r)
+    ms_ed = time_ms(lambda: ptb.contraction_operator_step_right(a1, a1, w1, r), reps=2)
+    eplan = PackedEnvPlan(q, qsite, q, qb, qb, cplx=True, side="right")
+    env_p = eplan.apply(a1, w1, r)
+    err_e = (torch.linalg.norm(env_p - env_dense) / torch.linalg.norm(env_dense)).item()
+    ms_ep = time_ms(lambda: eplan.apply(a1, w1, r), reps=10)
+    bplan = EnvSectorPlan(q, qsite, q, qb, qb, cplx=True)
+    ms_eb = time_ms(lambda: bplan.step_right(a1, w1, r), reps=5)
+    env = {"op": f"contraction_operator_step_right, a ({D},{d1},{D}), w (6,{d1},{d1},6), same sectors",
+           "ms_dense": ms_ed, "ms_banded_round1": ms_eb, "ms_sector_packed": ms_ep,
+           "rel_diff_vs_dense": err_e, "speedup_vs_dense": ms_ed / ms_ep, "speedup_vs_banded_round1": ms_eb / ms_ep}
+    del env_dense, env_p, a1
     return {"workload": f"two-site Fermi-Hubbard heff matvec a ({D},16,{D}), h2 (6,16,16,6), {int((sizes > 0).sum())} "
                         f"(N,Sz) sectors (Gaussian size profile, max {int(sizes.max())})",
-            "tensor_fill": float((a != 0).double().mean().item()), "ms_dense": ms_d, "gflops_alg_dense_path": fa / ms_d / 1e6,
-            "sector_packed": packed,
+            "tensor_fill": fill, "ms_dense": ms_d, "gflops_alg_dense_path": fa / ms_d / 1e6,
+            "sector_packed": packed, "environment_update": env,
             "banded_round1": {"ms_per_matvec": ms_b, "rel_diff_vs_dense": err_b, "flops_visited": fc["visited"],
                               "flops_exact_sector_blocks": fc["exact"], "visited_over_exact": fc["visited"] / fc["exact"],
                               "tflops_exact": fc["exact"] / ms_b / 1e9, "speedup_vs_dense": ms_d / ms_b},
@@ -635,6 +654,94 @@ def sweeps_block(torch, ptb, device):
     out["dmrg_twosite"]["speedup_vs_cpu_extrapolated"] = cpu_k2 * units2 / secs
     del h, psi
     torch.cuda.empty_cache()
+
+    # ---- single-site TDVP with quantum numbers at D = 2048 (BASELINE config-3 physics, block-sparse path) ----
+    # Fermi-Hubbard chain in the (N = L, Sz = 0) sector, random state from the reference generator's sector
+    # profile (MPS.construct_random), brought to canonical form once so that every bond is grouped by sector.
+    # The first call builds and caches the sector plans (host tables); the second is the steady state of a run.
+    L3 = 32
+    h = ptb.fermi_hubbard_1d_mpo(L3, 1.0, 4.0, 0.0)
+    psi = ptb.MPS.construct_random(L3, h.qsite, ptb.encode_quantum_number_pair(L3, 0), max_vdim=D_HEAD,
+                                   rng=np.random.default_rng(11))
+    psi.orthonormalize(mode="left")
+    fn3 = lambda h_, p_: ptb.tdvp_singlesite(h_, p_, 0.02j, 1, numiter_lanczos=k)      # noqa: E731
+    first, _ = run("tdvp1_qn_first", fn3, h, psi)
+    secs, ph = run("tdvp1_qn", fn3, h, psi)
+    big = int(np.argmax(psi.bond_dims))
+    _, cnt = np.unique(psi.qbonds[big], return_counts=True)
+    out["tdvp_singlesite_quantum_numbers"] = {
+        "driver": "pytenet_b200.tdvp_singlesite(H, psi, dt=0.02j, numsteps=1, numiter_lanczos=25)",
+        "workload": f"Fermi-Hubbard L={L3} (t=1, U=4), sector (N={L3}, Sz=0), complex128, MPS.construct_random("
+                    f"max_vdim={D_HEAD}): {sum(1 for b in psi.bond_dims if b >= D_HEAD - 64)} bonds at ~{D_HEAD}, "
+                    f"{len(cnt)} sectors on the largest bond (median {float(np.median(cnt)):.0f}, max {int(cnt.max())} rows)",
+        "seconds_per_step": secs, "seconds_first_step_incl_plan_construction": first,
+        "device_seconds_by_phase": ph,
+        "path": "sector-packed grouped GEMM for site / bond problems and environment updates, batched sector QR",
+    }
+    del h, psi
+    torch.cuda.empty_cache()
+    return out
+
+
+def latency_block(torch, ptb, device):
+    """The launch-latency end of the path, through the public drivers (N = 1 only):
+    * BASELINE config 1 -- README XXZ chain L = 10, D <= 28, `tdvp_singlesite`, 100 steps, k = 5 (fixture state of
+      tests/golden/tdvp_xxz_L10.npz, generated from the reference) -- with the oracle's CPU run of the same steps
+      beside it and the agreement of the two final states;
+    * BASELINE config 5 at one sample stream -- METTS for the Ising chain L = 64 (experiments/metts_ising.py:17-46):
+      samples per second and the realised bond dimensions."""
+    import warnings
+    from oracle import sweeps as osw
+    z = np.load(os.path.join(ROOT, "tests", "golden", "tdvp_xxz_L10.npz"))
+    n = int(z["h/nsites"])
+    hq = [z[f"h/qb{i}"] for i in range(n + 1)]
+    hw = [z[f"h/w{i}"] for i in range(n)]
+    pq = [z[f"psi0/qb{i}"] for i in range(n + 1)]
+    pa = [z[f"psi0/a{i}"] for i in range(n)]
+    dt = complex(z["dt"]); k = int(z["k"]); steps = 100
+    h = ptb.MPO.from_tensors(z["h/qsite"], hq, hw)
+    mk = lambda: ptb.MPS.from_tensors(z["psi0/qsite"], pq, pa)          # noqa: E731
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ptb.tdvp_singlesite(h, mk(), dt, 6, numiter_lanczos=k)          # untimed: module loading, first graph capture
+        best = None
+        for _ in range(2):
+            psi = mk()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            ptb.tdvp_singlesite(h, psi, dt, steps, numiter_lanczos=k)
+            torch.cuda.synchronize(); secs = time.perf_counter() - t0
+            best = secs if best is None else min(best, secs)
+        vec_gpu = psi.to_vector()
+        ch = osw.Chain([a.copy() for a in pa], z["psi0/qsite"], [q.copy() for q in pq])
+        t0 = time.perf_counter()
+        osw.tdvp_singlesite(hw, hq, ch, dt, steps, numiter_lanczos=k)
+        cpu_s = time.perf_counter() - t0
+        vec_cpu = ch.to_vector()
+        out["readme_tdvp_singlesite"] = {
+            "workload": f"README XXZ L={n}, bonds {psi.bond_dims}, tdvp_singlesite, {steps} steps, k={k}",
+            "seconds": best, "ms_per_step": 1e3 * best / steps,
+            "path": "one CUDA graph launch per time step; one kernel per small local problem (csrc/lanczos_small.cu)",
+            "cpu": {"kind": "port", "seconds": cpu_s, "cores": cpu_threads()},
+            "speedup_vs_cpu": cpu_s / best,
+            "rel_diff_final_state_vs_cpu": float(np.linalg.norm(vec_gpu - vec_cpu) / np.linalg.norm(vec_cpu)),
+        }
+        # METTS, one stream
+        hm = ptb.ising_1d_mpo(64, 1.0, 0.8, -0.375)
+        rng = np.random.default_rng(1000)
+        kw = dict(numsteps=10, numiter_lanczos=8, tol_split=1e-10)
+        ptb.metts_energy_samples(hm, 1.0, 1, rng, **kw)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        stats = {}
+        nsamp = 6
+        vals = ptb.metts_energy_samples(hm, 1.0, nsamp, rng, stats=stats, **kw)
+        torch.cuda.synchronize(); secs = time.perf_counter() - t0
+        out["metts_ising_L64"] = {
+            "workload": "Ising L=64 METTS, beta=1, two-site TDVP in imaginary time (10 steps, k=8, tol_split=1e-10)",
+            "samples": nsamp, "seconds": secs, "samples_per_s": nsamp / secs,
+            "energy_per_site_mean": float(np.mean(vals.real) / 64),
+            "realised_max_bond_dim": int(max(stats["max_bond"])) if stats.get("max_bond") else None,
+        }
     return out
 
 
@@ -828,6 +935,9 @@ def run_ours(args):
         del a, l, r, out
         torch.cuda.empty_cache()
         sweeps = sweeps_block(torch, ptb, device)
+    latency = None
+    if world == 1 and os.environ.get("PTB_BENCH_SKIP_LATENCY") != "1":
+        latency = latency_block(torch, ptb, device)
 
     line = {
         "metric": METRIC, "value": world * F / (ms / 1e3) / 1e9, "unit": "GFLOP/s", "n_gpus": world,
@@ -850,6 +960,7 @@ def run_ours(args):
         "sharded": sharded,
         "sharded_sweep": sharded_sweep,
         "sweeps": sweeps,
+        "latency_regime": latency,
         "other_shapes": other,
         "other_ops": other_ops,
         "block_sparse": block_sparse,

@@ -403,6 +403,26 @@ int ptb_bond_lanczos(int dtype, const void* c, const void* l, const void* r, int
                      void* stream);
 
 /* ---------------------------------------------------------------------------
+ * One kernel per local problem (launch-latency regime: README config, METTS, chain edges)
+ *   pytenet/tdvp.py:223-238, dmrg.py:181-189 (closures) + krylov.py:12-57 (Lanczos) + krylov.py:110-139 (expm_krylov)
+ * A single CTA runs the start normalisation, all `numiter` Lanczos iterations on H_eff = (l, w, r) -- the three
+ * contraction steps of chain_ops.py:273-278 as FP64 FMA loops over L2-resident operands --, and, with
+ * `apply_expm`, the numiter x numiter tridiagonal problem and out = exp(dt H_eff) x as the combination of the
+ * Lanczos vectors (dt = dt_re + i dt_im; the drivers pass -dt).  `w == NULL` is the zero-site problem
+ * (apply_local_bond_contraction, chain_ops.py:282-317: d == 1, chi_l == chi_r).  V (numiter x n elements) receives the
+ * Lanczos vectors, scal = [|x|, alpha[0:numiter], beta[0:numiter-1]] as ptb_heff_lanczos; all numiter steps are
+ * executed, the breakdown rule of krylov.py:44-50 is applied to the betas inside the k x k solve (and by the caller
+ * to `scal`).  ptb_local_step_small_fits: 1 when one matvec is small enough for a single CTA (<= 160 000 complex
+ * multiply-adds) and numiter <= 64; otherwise ptb_local_step_small returns PTB_ERR_TOO_LARGE.
+ * ------------------------------------------------------------------------- */
+int ptb_local_step_small_fits(int64_t Dl, int64_t d, int64_t Dr, int64_t chi_l, int64_t chi_r, int numiter);
+size_t ptb_local_step_small_workspace_bytes(int dtype, int64_t Dl, int64_t d, int64_t Dr, int64_t chi_l, int64_t chi_r);
+int ptb_local_step_small(int dtype, const void* x, const void* w, int w_is_complex, const void* l, const void* r,
+                         int64_t Dl, int64_t d, int64_t Dr, int64_t chi_l, int64_t chi_r, int numiter, void* V,
+                         double* scal, int apply_expm, double dt_re, double dt_im, int out_is_complex, void* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Sector-packed block-sparse path (BASELINE config 3: quantum-number sectors as a device-side grouped GEMM)
  *   sector structure: pytenet/block_sparse_util.py:47-53 (sparsity rule), :151-169 (sector order);
  *   contraction: pytenet/chain_ops.py:237-279.

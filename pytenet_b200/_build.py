@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpytenet_b200.so")
-SOURCES = ["block_qr.cu", "block_svd.cu", "chain_ops.cu", "dense_svd.cu", "heff_small.cu", "host_entry.cu", "krylov.cu", "lanczos_heff.cu", "sector_packed.cu", "sharded.cu", "wapply.cu", "probe.cu"]
+SOURCES = ["block_qr.cu", "block_svd.cu", "chain_ops.cu", "dense_svd.cu", "heff_small.cu", "host_entry.cu", "krylov.cu", "lanczos_heff.cu", "lanczos_small.cu", "sector_packed.cu", "sharded.cu", "wapply.cu", "probe.cu"]
 
 
 def _dependencies():

@@ -64,6 +64,10 @@ SIGNATURES = {
                          + [_int, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "ptb_bond_lanczos_workspace_bytes": (_sz, [_int] + [_i64] * 3),
     "ptb_bond_lanczos": (_int, [_int, _ptr, _ptr, _ptr] + [_i64] * 3 + [_int, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "ptb_local_step_small_fits": (_int, [_i64] * 5 + [_int]),
+    "ptb_local_step_small_workspace_bytes": (_sz, [_int] + [_i64] * 5),
+    "ptb_local_step_small": (_int, [_int, _ptr, _ptr, _int, _ptr, _ptr] + [_i64] * 5 + [_int, _ptr, _ptr, _int,
+                                    ctypes.c_double, ctypes.c_double, _int, _ptr, _ptr, _sz, _ptr]),
     "ptb_krylov_expm_workspace_bytes": (_sz, []),
     "ptb_krylov_expm_apply": (_int, [_int, _i64, _int, _ptr, _i64, _ptr, ctypes.c_double, ctypes.c_double, _int, _ptr,
                                      _ptr, _ptr]),

@@ -202,6 +202,55 @@ class _AbsorbRight(AbsorbSectorPlan):
         super().__init__(qc_rows, qc_cols, qs, q_other, False, cplx=cplx)
 
 
+def _small_local_step(x, w, l, r, dims, numiter, dt, V=None, scal=None):
+    """The whole local problem in ONE kernel launch (csrc/lanczos_small.cu: ptb_local_step_small) when it is small
+    enough for a single CTA -- the launch-latency regime (README config, METTS, chain edges).  `dt is None`: the
+    Lanczos run only (fills `V`, `scal`; returns True).  Otherwise returns (exp(-dt H) x ... as `out`, scal).
+    Returns None when the problem does not qualify."""
+    Dl, d, Dr, cl, cr = dims
+    lib = _lib.load()
+    if numiter > 64 or not lib.ptb_local_step_small_fits(Dl, d, Dr, cl, cr, numiter):
+        return None
+    if not all(isinstance(t, torch.Tensor) and t.is_cuda for t in (x, l, r)):
+        return None
+    cplx = x.dtype.is_complex
+    if x.dtype not in (dev.F64, dev.C128):
+        return None
+    if (l.dtype.is_complex or r.dtype.is_complex) and not cplx:
+        return None                      # mixed dtypes: the step-by-step path applies NumPy's promotion rules
+    w_cplx = False
+    if w is not None:
+        if not (isinstance(w, torch.Tensor) and w.is_cuda) or w.dtype not in (dev.F64, dev.C128):
+            return None
+        w_cplx = w.dtype.is_complex
+        if w_cplx and not cplx:
+            return None
+        w = dev.dense(w)
+    device = x.device
+    l = dev.as_dtype(l, cplx); r = dev.as_dtype(r, cplx)
+    n = Dl * d * Dr
+    dt_code = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
+    if V is None:
+        V = torch.empty((numiter, n), dtype=x.dtype, device=device)
+        scal = torch.empty(2 * numiter, dtype=dev.F64, device=device)      # the kernel writes every entry
+    nbytes = lib.ptb_local_step_small_workspace_bytes(dt_code, Dl, d, Dr, cl, cr)
+    ws = dev.workspace(nbytes, device, tag="small_step")
+    out = None
+    apply_expm, dre, dim_, out_cplx = 0, 0.0, 0.0, 0
+    if dt is not None:
+        dtc = complex(dt)
+        out_cplx = int(cplx or isinstance(dt, (complex, np.complexfloating)))
+        out = torch.empty(n, dtype=dev.C128 if out_cplx else dev.F64, device=device)
+        apply_expm, dre, dim_ = 1, dtc.real, dtc.imag
+    st = lib.ptb_local_step_small(dt_code, x.data_ptr(), w.data_ptr() if w is not None else None, int(w_cplx),
+                                  l.data_ptr(), r.data_ptr(), Dl, d, Dr, cl, cr, numiter, V.data_ptr(),
+                                  scal.data_ptr(), apply_expm, dre, dim_, out_cplx,
+                                  out.data_ptr() if out is not None else None, ws.data_ptr(), nbytes,
+                                  dev.stream_ptr(device))
+    _lib.check(st, "ptb_local_step_small")
+    return True if dt is None else (out, scal)
+
+
 class HeffOperator:
     """The closure of tdvp.py:223-229 / dmrg.py:181-189 as an object: calling it applies the local effective
     Hamiltonian to a flat vector; `ptb_lanczos_run` hands a whole Lanczos run to the fused C entry
@@ -213,11 +262,30 @@ class HeffOperator:
     def __call__(self, x):
         return apply_local_hamiltonian(x.reshape(self.shape), self.w, self.l, self.r).reshape(-1)
 
+    def _dims(self, x):
+        w, l, r = self.w, self.l, self.r
+        Dl, d, Dr = self.shape
+        if not all(isinstance(t, torch.Tensor) for t in (w, l, r)) or w.ndim != 4:
+            return None
+        cl, dout, din, cr = w.shape
+        if (dout != d or din != d or tuple(l.shape) != (Dl, cl, Dl) or tuple(r.shape) != (Dr, cr, Dr)
+                or x.numel() != Dl * d * Dr):
+            return None
+        return Dl, d, Dr, cl, cr
+
+    def ptb_expm_run(self, x, dt, numiter):
+        """exp(dt H_eff) x in one kernel launch when the problem is small (krylov._expm_device prefers it)."""
+        dims = self._dims(x)
+        return None if dims is None else _small_local_step(x, self.w, self.l, self.r, dims, numiter, dt)
+
     def ptb_lanczos_run(self, x, numiter, V, scal):
         w, l, r = self.w, self.l, self.r
         Dl, d, Dr = self.shape
         if not all(isinstance(t, torch.Tensor) and t.is_cuda for t in (w, l, r)) or w.ndim != 4:
             return False
+        dims = self._dims(x)
+        if dims is not None and _small_local_step(x, w, l, r, dims, numiter, None, V, scal):
+            return True
         cplx = x.dtype.is_complex
         if (l.dtype.is_complex or r.dtype.is_complex or w.dtype.is_complex) and not cplx:
             return False                 # mixed dtypes: the step-by-step path applies NumPy's promotion rules
@@ -254,11 +322,28 @@ class BondOperator:
     def __call__(self, x):
         return apply_local_bond_contraction(x.reshape(self.shape), self.l, self.r).reshape(-1)
 
+    def _dims(self, x):
+        l, r = self.l, self.r
+        Dl, Dr = self.shape
+        if not all(isinstance(t, torch.Tensor) for t in (l, r)):
+            return None
+        chi = l.shape[1]
+        if tuple(l.shape) != (Dl, chi, Dl) or tuple(r.shape) != (Dr, chi, Dr) or x.numel() != Dl * Dr:
+            return None
+        return Dl, 1, Dr, chi, chi
+
+    def ptb_expm_run(self, x, dt, numiter):
+        dims = self._dims(x)
+        return None if dims is None else _small_local_step(x, None, self.l, self.r, dims, numiter, dt)
+
     def ptb_lanczos_run(self, x, numiter, V, scal):
         l, r = self.l, self.r
         Dl, Dr = self.shape
         if not all(isinstance(t, torch.Tensor) and t.is_cuda for t in (l, r)):
             return False
+        dims = self._dims(x)
+        if dims is not None and _small_local_step(x, None, l, r, dims, numiter, None, V, scal):
+            return True
         cplx = x.dtype.is_complex
         if (l.dtype.is_complex or r.dtype.is_complex) and not cplx:
             return False

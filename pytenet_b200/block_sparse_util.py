@@ -82,6 +82,13 @@ def _forbidden_mask(qnums, device):
 _CAPTURING = False      # set while a sweep step is captured into a CUDA graph (tdvp._StepGraph)
 
 
+def _all_zero(qnums):
+    for q in qnums:
+        if (q.any() if isinstance(q, np.ndarray) else np.any(q)):
+            return False
+    return True
+
+
 def _violations(a, qnums):
     """0-dim bool device tensor: some forbidden entry of `a` is non-zero (one fused pass, no boolean gather)."""
     return torch.any((a != 0) & _forbidden_mask(qnums, a.device))
@@ -90,7 +97,7 @@ def _violations(a, qnums):
 def is_qsparse(a, qnums):
     """True iff `a` vanishes wherever the quantum numbers do not sum to zero (:47-53)."""
     if isinstance(a, torch.Tensor) and a.is_cuda:
-        if all(not np.any(np.asarray(q)) for q in qnums):
+        if _all_zero(qnums):
             return True                      # all quantum numbers zero: nothing is forbidden
         if _CAPTURING:
             return True                      # a device->host read cannot be captured; the eager steps checked it
@@ -103,11 +110,13 @@ def _assert_qsparse(a, qnums, message="sparsity pattern must match quantum numbe
     """The reference's `assert is_qsparse(...)` (:114, :254).  Inside the sweep drivers (krylov.deferred_checks) the
     test runs on the device and its result is examined when the driver returns, so a factorisation is no
     synchronisation point; elsewhere it is checked immediately."""
-    from . import krylov
-    if (isinstance(a, torch.Tensor) and a.is_cuda and krylov.deferring() and not _CAPTURING
-            and any(np.any(np.asarray(q)) for q in qnums)):
-        krylov.defer_flag(_violations(a, qnums), message)
-        return
+    if isinstance(a, torch.Tensor) and a.is_cuda:
+        if _all_zero(qnums):
+            return                           # all quantum numbers zero: nothing is forbidden
+        from . import krylov
+        if krylov.deferring() and not _CAPTURING:
+            krylov.defer_flag(_violations(a, qnums), message)
+            return
     assert is_qsparse(a, qnums), message
 
 
@@ -344,6 +353,10 @@ def block_sparse_eigh(a, q0):
 _POLAR_MIN = int(os.environ.get("PYTENET_B200_POLAR_SVD_MIN", "64"))
 
 
+_POLAR_SKIP = {}
+_POLAR_BACKOFF = 8
+
+
 def dense_svd(a):
     """
     Thin SVD `a = u diag(s) vh` of one dense device matrix; `s` stays on the device.  Large float64 / complex128
@@ -354,6 +367,14 @@ def dense_svd(a):
     m, n = a.shape
     k = min(m, n)
     if k < _POLAR_MIN or a.dtype not in (dev.F64, dev.C128) or not a.is_cuda:
+        return torch.linalg.svd(a, full_matrices=False, driver=_SVD_DRIVER)
+    # The polar driver perturbs a numerically singular matrix (spectrum graded beyond ~1e-15 of the largest value,
+    # as the two-site tensors of converged physical states are) and then reports err_sigma up to 1e-4: such
+    # results are discarded below.  A shape whose last attempt was discarded goes straight to gesvd for the next
+    # _POLAR_BACKOFF calls instead of paying for both factorisations again.
+    skey = (m, n, a.dtype)
+    if _POLAR_SKIP.get(skey, 0) > 0:
+        _POLAR_SKIP[skey] -= 1
         return torch.linalg.svd(a, full_matrices=False, driver=_SVD_DRIVER)
     lib = _lib.load()
     cplx = a.dtype.is_complex
@@ -378,6 +399,7 @@ def dense_svd(a):
                            ctypes.byref(err), dev.stream_ptr(a.device))
     _lib.check(st, "ptb_svd_polar")
     if int(info.item()) != 0 or not (err.value <= 1e-11):
+        _POLAR_SKIP[skey] = _POLAR_BACKOFF
         return torch.linalg.svd(a, full_matrices=False, driver=_SVD_DRIVER)
     # work = U_cm diag(s) V_cm^H with ubuf = U_cm^T and vbuf = V_cm^T as row-major arrays, and work (column-major) is
     # a^T (wide `a`) or conj(a) (tall `a`):   wide: a = conj(V_cm) s U_cm^T;   tall: a = conj(U_cm) s V_cm^T
@@ -457,10 +479,12 @@ def dense_svd_batch(mats):
     return out
 
 
-def block_sparse_svd(a, q0, q1):
+def block_sparse_svd(a, q0, q1, with_device_sigma=False):
     """
     Sector-wise thin SVD of a block-sparse matrix -> `(u, s, v, q)` with `s` a host
     float64 array ordered sector-ascending, sigma-descending inside a sector (:244-319).
+    `with_device_sigma`: additionally return the same singular values as a device vector (the callers scale the
+    factors with it without a host->device copy).
     """
     assert a.ndim == 2
     q0 = np.ascontiguousarray(q0); q1 = np.ascontiguousarray(q1)
@@ -473,16 +497,22 @@ def block_sparse_svd(a, q0, q1):
         v = torch.zeros((1, a.shape[1]), dtype=a.dtype, device=a.device)
         if a.shape[0] > 0:
             u[0, 0] = 1
+        if with_device_sigma:
+            return u, np.zeros(1), v, q0[:1], torch.zeros(1, dtype=dev.F64, device=a.device)
         return u, np.zeros(1), v, q0[:1]
     nb = plan.nb
     small, large, tab, row_off, col_off, max_work = plan.svd_tables(a.element_size())
     if plan.one_dense and large:
         us, ss, vs = dense_svd(a)
+        if with_device_sigma:
+            return us, ss.cpu().numpy(), vs, plan.qinterm.copy(), ss
         return us, ss.cpu().numpy(), vs, plan.qinterm.copy()
     a = dev.dense(a)
-    u = torch.zeros((a.shape[0], nb), dtype=a.dtype, device=a.device)
-    v = torch.zeros((nb, a.shape[1]), dtype=a.dtype, device=a.device)
-    s_dev = torch.zeros(nb, dtype=dev.F64, device=a.device)
+    # one sector covering the whole matrix, taken by the batched kernel: every entry of u, v, s is written
+    alloc = torch.empty if (plan.one_dense and small and not large) else torch.zeros
+    u = alloc((a.shape[0], nb), dtype=a.dtype, device=a.device)
+    v = alloc((nb, a.shape[1]), dtype=a.dtype, device=a.device)
+    s_dev = alloc(nb, dtype=dev.F64, device=a.device)
     side = None
     if small:
         # all sectors whose block and right vectors fit in shared memory: ONE launch of the batched one-sided
@@ -533,5 +563,8 @@ def block_sparse_svd(a, q0, q1):
                                               driver=_SVD_DRIVER)
                 u[rt, p0:p0 + sz] = us
                 v[p0:p0 + sz, ct] = vs
+                s_dev[p0:p0 + sz] = ss
                 s_host[p0:p0 + sz] = ss.cpu().numpy()
+    if with_device_sigma:
+        return u, s_host, v, plan.qinterm.copy(), s_dev
     return u, s_host, v, plan.qinterm.copy()

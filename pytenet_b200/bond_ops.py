@@ -26,14 +26,23 @@ def retained_bond_indices(s, tol):
     return np.where(cum > tol)[0]
 
 
-def split_block_sparse_matrix_svd(a, q0, q1, tol):
-    """Sector-wise SVD followed by truncation -> `(u, s, v, q)` (:41-54); `u`, `v` stay on the device."""
-    u, s, v, q = block_sparse_svd(a, q0, q1)
+def split_block_sparse_matrix_svd(a, q0, q1, tol, with_device_sigma=False):
+    """Sector-wise SVD followed by truncation -> `(u, s, v, q)` (:41-54); `u`, `v` stay on the device.
+    `with_device_sigma`: a fifth return value holds the kept singular values as a device vector."""
+    u, s, v, q, s_dev = block_sparse_svd(a, q0, q1, with_device_sigma=True)
     keep = retained_bond_indices(s, tol)
     if len(keep) != len(s):
-        kt = torch.as_tensor(keep, device=u.device)
-        u = u.index_select(1, kt)
-        v = v.index_select(0, kt)
+        nk = len(keep)
+        if nk > 0 and keep[-1] == nk - 1:
+            # the kept indices are a prefix (one sector, values descending): slices, no index upload
+            u, v, s_dev = u[:, :nk], v[:nk], s_dev[:nk]
+        else:
+            kt = torch.as_tensor(keep, device=u.device)
+            u = u.index_select(1, kt)
+            v = v.index_select(0, kt)
+            s_dev = s_dev.index_select(0, kt)
         s = s[keep]
         q = q[keep]
+    if with_device_sigma:
+        return u, s, v, q, s_dev
     return u, s, v, q

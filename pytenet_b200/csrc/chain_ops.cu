@@ -35,6 +35,44 @@ inline bool fits_int(std::initializer_list<int64_t> v) {
     return true;
 }
 
+// ---- tiny products (launch-latency regime: merges, gauge absorption, environment updates at D <~ 32) ----
+// The tensor-pipe engines are persistent kernels with ~200 KB of shared memory, tensor maps and an mbarrier
+// pipeline: ~10 us per launch whatever the size.  Below TINY_GEMM_MACS multiply-adds one thread per output element
+// with plain FP64 FMAs over L1/L2-resident operands finishes in 2-3 us.
+constexpr long long TINY_GEMM_MACS = 1LL << 18;
+
+template <bool CPLX>
+__global__ void __launch_bounds__(128) gemm_tiny_kernel(const GemmParams p, int ta, int tb, int cj) {
+    constexpr int E = CPLX ? 2 : 1;
+    const long long per = (long long)p.M * p.N;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per * p.batch) return;
+    const int bz = (int)(idx / per);
+    const int rem = (int)(idx - (long long)bz * per);
+    const int m = rem / p.N, n = rem - m * p.N;
+    const double* A = p.A + (size_t)bz * p.sA * E;
+    const double* B = p.B + (size_t)bz * p.sB * E;
+    const size_t a0 = ta ? (size_t)m : (size_t)m * p.lda, as = ta ? (size_t)p.lda : 1;
+    const size_t b0 = tb ? (size_t)n * p.ldb : (size_t)n, bs = tb ? 1 : (size_t)p.ldb;
+    double re = 0.0, im = 0.0;
+    for (int k = 0; k < p.K; k++) {
+        if (CPLX) {
+            const double ar = A[(a0 + k * as) * 2], ai = A[(a0 + k * as) * 2 + 1];
+            const double br = B[(b0 + k * bs) * 2];
+            double bi = B[(b0 + k * bs) * 2 + 1];
+            if (cj) bi = -bi;
+            re = fma(ar, br, re); re = fma(-ai, bi, re);
+            im = fma(ar, bi, im); im = fma(ai, br, im);
+        } else {
+            re = fma(A[a0 + k * as], B[b0 + k * bs], re);
+        }
+    }
+    double* c = p.C + ((size_t)bz * p.sC + (size_t)m * p.ldc + n) * E;
+    if (p.accumulate) { re += c[0]; if (CPLX) im += c[1]; }
+    c[0] = re;
+    if (CPLX) c[1] = im;
+}
+
 // split_k: 1 = never split; 0 = choose automatically when `part_ws` is given; >1 = forced
 template <bool CPLX>
 int gemm(int ta, int tb, int cj, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
@@ -52,6 +90,12 @@ int gemm(int ta, int tb, int cj, int64_t M, int64_t N, int64_t K, const void* A,
     p.accumulate = acc ? 1 : 0;
     p.tiles_m = p.tiles_n = 0;
     if (M == 0 || N == 0 || batch == 0) return PTB_OK;
+    if (engine == 0 && split_k <= 1 && (long long)M * N * batch <= (1LL << 22) &&
+        (long long)M * N * batch * (K > 0 ? K : 1) <= TINY_GEMM_MACS) {
+        const long long total = (long long)M * N * batch;
+        gemm_tiny_kernel<CPLX><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p, ta, tb, cj);
+        return cuda_status(cudaGetLastError());
+    }
     // engine selection (an argument, never process state): 0 = auto (warp-specialised TMA kernel when it
     // applies), 1 = first-generation cp.async kernel only, 2 = warp-specialised kernel required
     if (engine != 1 && K > 0) {

@@ -367,6 +367,20 @@ def _expm_device(afunc, x, dt, numiter):
     """expm_krylov with the k x k problem solved on the device (ptb_krylov_expm_apply): no device->host
     transfer on the way; the scalar checks follow immediately, or at the end of a `deferred_checks()` block."""
     lib = _lib.load()
+    fused = getattr(afunc, "ptb_expm_run", None)
+    if fused is not None and numiter >= 1:
+        # small local problems: Lanczos run, k x k problem and combination in ONE kernel (csrc/lanczos_small.cu)
+        xf = x.reshape(-1)
+        xf = dev.as_dtype(xf, xf.dtype.is_complex)
+        res = fused(xf, dt, numiter)
+        if res is not None:
+            out, scal = res
+            n = xf.shape[0]
+            if _Deferred.depth > 0:
+                _defer(scal, _threshold_length(afunc, n), numiter)
+            else:
+                _check_scalars(scal.cpu().numpy(), _threshold_length(afunc, n), numiter)
+            return out
     n, V, scal = _lanczos_device(afunc, x, numiter)
     vc = V.dtype.is_complex
     dtc = complex(dt)

@@ -344,9 +344,9 @@ def mps_local_orthonormalize_left_svd(a, a_next, qsite, qbonds, tol: float):
     """Left-orthonormalise `a` by a truncated SVD and absorb `sigma v` into the next tensor (mps.py:494-508)."""
     s = a.shape
     assert len(s) == 3
-    u, sigma, v, qbond = split_block_sparse_matrix_svd(
-        a.reshape(s[0] * s[1], s[2]), qnumber_flatten((qbonds[0], qsite)), qbonds[1], tol)
-    sv = dev.dense(v) * torch.as_tensor(sigma, device=a.device)[:, None]
+    u, sigma, v, qbond, sig = split_block_sparse_matrix_svd(
+        a.reshape(s[0] * s[1], s[2]), qnumber_flatten((qbonds[0], qsite)), qbonds[1], tol, with_device_sigma=True)
+    sv = dev.dense(v) * sig[:, None]
     return dev.dense(u.reshape(s[0], s[1], u.shape[1])), _left_multiply(sv, a_next), qbond
 
 
@@ -354,9 +354,10 @@ def mps_local_orthonormalize_right_svd(a, a_prev, qsite, qbonds, tol: float):
     """Right-orthonormalise `a` by a truncated SVD and absorb `u sigma` into the previous tensor (mps.py:511-525)."""
     s = a.shape
     assert len(s) == 3
-    u, sigma, v, qbond = split_block_sparse_matrix_svd(
-        a.reshape(s[0], s[1] * s[2]), qbonds[0], qnumber_flatten([-np.asarray(qsite), qbonds[1]]), tol)
-    us = dev.dense(u) * torch.as_tensor(sigma, device=a.device)
+    u, sigma, v, qbond, sig = split_block_sparse_matrix_svd(
+        a.reshape(s[0], s[1] * s[2]), qbonds[0], qnumber_flatten([-np.asarray(qsite), qbonds[1]]), tol,
+        with_device_sigma=True)
+    us = dev.dense(u) * sig
     prev = dev.gemm(a_prev.reshape(-1, a_prev.shape[-1]), us).reshape(tuple(a_prev.shape[:-1]) + (us.shape[1],))
     return dev.dense(v.reshape(v.shape[0], s[1], s[2])), prev, qbond
 
@@ -383,9 +384,9 @@ def mps_split_tensor_svd(a, qsite0, qsite1, qbonds_outer, svd_distr: str, tol=0)
     b0, b2 = a.shape[0], a.shape[2]
     q0 = qnumber_flatten([qbonds_outer[0], qsite0])
     q1 = qnumber_flatten([-qsite1, qbonds_outer[1]])
-    u, sigma, v, qbond = split_block_sparse_matrix_svd(a.reshape(b0 * d0, d1 * b2), q0, q1, tol)
+    u, sigma, v, qbond, sig = split_block_sparse_matrix_svd(a.reshape(b0 * d0, d1 * b2), q0, q1, tol,
+                                                            with_device_sigma=True)
     nb = len(sigma)
-    sig = torch.as_tensor(sigma, device=a.device)
     if svd_distr == "left":
         u = u * sig
     elif svd_distr == "right":

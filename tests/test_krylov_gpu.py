@@ -201,7 +201,13 @@ def test_fused_lanczos_run_equals_stepwise(cuda_lib, cplx, dims):
     bop = _sweep.BondOperator(cu(l), cu(r2), (Dl, Dr))
     n1, al1, be1, V1 = krylov._lanczos_core(bop, cu(c).reshape(-1), k)
     n2, al2, be2, V2 = krylov._lanczos_core(lambda x: bop(x), cu(c).reshape(-1), k)
-    assert n1 == n2 and np.array_equal(al1, al2) and np.array_equal(be1, be2) and torch.equal(V1, V2)   # same entry point
+    if cuda_lib.ptb_local_step_small_fits(Dl, 1, Dr, cl, cl, k):
+        # small problems: the fused run is the one-kernel local step (csrc/lanczos_small.cu) -- same numbers up to
+        # summation order
+        assert n1 == n2 and np.allclose(al1, al2, rtol=1e-12, atol=1e-12 * np.abs(al2).max())
+        assert np.allclose(be1, be2, rtol=1e-11) and rel(V1.cpu().numpy(), V2.cpu().numpy()) < 1e-10
+    else:
+        assert n1 == n2 and np.array_equal(al1, al2) and np.array_equal(be1, be2) and torch.equal(V1, V2)   # same entry point
     oal, obe, oV = oracle.lanczos_iteration(
         lambda x: oracle.apply_local_bond_contraction(x.reshape(Dl, Dr), l, r2).reshape(-1), c.reshape(-1), k)
     assert np.allclose(al1, oal, rtol=1e-9, atol=1e-9 * np.abs(oal).max()) and np.allclose(be1, obe, rtol=1e-8)
@@ -294,3 +300,62 @@ def test_arnoldi_and_general_expm(cuda_lib, cplx):
     # host-buffer entry
     got_h = ptb.expm_krylov(lambda x: m @ x, v, dt, 25)
     assert isinstance(got_h, np.ndarray) and rel(got_h, expm(dt * m) @ v) < 1e-10
+
+
+@pytest.mark.parametrize("cplx,wc,dims", [(True, False, (16, 2, 20, 5, 5)), (False, False, (12, 2, 9, 4, 5)),
+                                          (True, True, (7, 3, 5, 3, 2)), (True, False, (4, 4, 4, 3, 3)),
+                                          (True, False, (2, 2, 3, 1, 4)), (False, False, (16, 2, 16, 5, 5))])
+@pytest.mark.parametrize("k", [1, 5, 8])
+def test_one_kernel_local_step_matches_oracle(cuda_lib, cplx, wc, dims, k):
+    """ptb_local_step_small (csrc/lanczos_small.cu: start, all Lanczos iterations, k x k problem and combination in ONE
+    kernel) against the oracle: alphas / betas / Lanczos vectors of krylov.lanczos_iteration and the result of
+    expm_krylov, for the site problem (real and complex MPO tensor, real and complex state, real-time and
+    imaginary-time steps) and the zero-site problem."""
+    import oracle.lanczos as ol
+    from pytenet_b200 import krylov, _sweep
+    Dl, d, Dr, cl, cr = dims
+    assert cuda_lib.ptb_local_step_small_fits(Dl, d, Dr, cl, cr, k)
+    rng = np.random.default_rng(Dl * 1000 + Dr * 10 + k)
+
+    def rnd(shape, c):
+        x = rng.normal(size=shape)
+        return x + 1j * rng.normal(size=shape) if c else x
+
+    def herm_env(D, chi):
+        e = rnd((D, chi, D), cplx)
+        return np.ascontiguousarray(e + e.conj().transpose(2, 1, 0))
+
+    l, r = herm_env(Dl, cl), herm_env(Dr, cr)
+    w = rnd((cl, d, d, cr), wc)
+    w = np.ascontiguousarray(w + w.conj().transpose(0, 2, 1, 3))     # Hermitian in (s', s) for every (k, K)
+    w[np.abs(w) < 0.6] = 0
+    a = rnd((Dl, d, Dr), cplx)
+    hfun = lambda x: oracle.apply_local_hamiltonian(x.reshape(Dl, d, Dr), w, l, r).reshape(-1)      # noqa: E731
+    op = _sweep.HeffOperator(cu(w), cu(l), cu(r), (Dl, d, Dr))
+    for dt in ((0.05j, -0.1) if not wc else (0.05j,)):
+        oal, obe, oV = ol.lanczos_iteration(hfun, a.reshape(-1), k)
+        res = op.ptb_expm_run(cu(a).reshape(-1), dt, k)
+        assert res is not None
+        out, scal = res
+        sc = scal.cpu().numpy()
+        assert abs(sc[0] - np.linalg.norm(a)) < 1e-13 * np.linalg.norm(a)
+        assert np.allclose(sc[1:1 + len(oal)], oal, rtol=1e-10, atol=1e-10 * max(1.0, np.abs(oal).max()))
+        assert np.allclose(sc[1 + k:1 + k + len(obe)], obe, rtol=1e-9)
+        want = ol.expm_krylov(hfun, a.reshape(-1), dt, k, hermitian=True)
+        assert rel(out.cpu().numpy(), want) < 1e-10
+        # the public driver takes the same path
+        got = krylov.expm_krylov(op, cu(a).reshape(-1), dt, k, hermitian=True)
+        assert torch.equal(got, out)
+    # Lanczos run only (eigh_krylov's use)
+    n1, al1, be1, V1 = krylov._lanczos_core(op, cu(a).reshape(-1), k)
+    assert np.allclose(al1, oal, rtol=1e-10, atol=1e-10 * max(1.0, np.abs(oal).max()))
+    assert rel(V1.cpu().numpy()[:oV.shape[1]], oV.T) < 1e-8
+    # zero-site problem
+    r2 = herm_env(Dr, cl)
+    c = rnd((Dl, Dr), cplx)
+    kfun = lambda x: oracle.apply_local_bond_contraction(x.reshape(Dl, Dr), l, r2).reshape(-1)      # noqa: E731
+    bop = _sweep.BondOperator(cu(l), cu(r2), (Dl, Dr))
+    res = bop.ptb_expm_run(cu(c).reshape(-1), -0.03j, k)
+    assert res is not None
+    want = ol.expm_krylov(kfun, c.reshape(-1), -0.03j, k, hermitian=True)
+    assert rel(res[0].cpu().numpy(), want) < 1e-10
