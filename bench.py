@@ -134,11 +134,11 @@ def block_sparse_block(torch, ptb, device, time_ms, peak_tflops, D=2048):
     lib = op.lib
     st = torch.cuda.current_stream().cuda_stream
     n1, n3 = len(pplan.tiles1_host), len(pplan.tiles3_host)
-    ms_g1 = time_ms(lambda: lib.ptb_gemm_grouped(op.dt, x.data_ptr(), op.rb.data_ptr(), op.t1.data_ptr(),
-                                                 op.tabs["tiles1"].data_ptr(), n1, st), reps=10)
+    ms_g1 = time_ms(lambda: lib.ptb_gemm_grouped_v(op.dt, pplan.var1, x.data_ptr(), op.rb.data_ptr(), op.t1.data_ptr(),
+                                                   op.tabs["tiles1"].data_ptr(), n1, st), reps=10)
     ms_w = time_ms(lambda: op.wtab.run(lib, op.dt, op.t1, op.t2, st), reps=10)
-    ms_g3 = time_ms(lambda: lib.ptb_gemm_grouped(op.dt, op.t2.data_ptr(), op.lp.data_ptr(), op.o.data_ptr(),
-                                                 op.tabs["tiles3"].data_ptr(), n3, st), reps=10)
+    ms_g3 = time_ms(lambda: lib.ptb_gemm_grouped_v(op.dt, pplan.var3, op.t2.data_ptr(), op.lp.data_ptr(), op.o.data_ptr(),
+                                                   op.tabs["tiles3"].data_ptr(), n3, st), reps=10)
     ms_rp = time_ms(lambda: op.tabs["repack"].run(lib, op.dt, op.o, y, st), reps=10)
     ms_pack = time_ms(lambda: op.pack(a), reps=3)
     ms_unpack = time_ms(lambda: op.unpack(y), reps=3)
@@ -152,7 +152,7 @@ def block_sparse_block(torch, ptb, device, time_ms, peak_tflops, D=2048):
         "tflops_visited_gemm_kernels": pfc["visited"] / (ms_g1 + ms_g3) / 1e9,
         "gemm_kernels_frac_of_fp64_peak": pfc["visited"] / (ms_g1 + ms_g3) / 1e9 / peak_tflops,
         "kernel_ms": {"grouped_gemm_step1": ms_g1, "w_gather": ms_w, "grouped_gemm_step3": ms_g3, "repack": ms_rp},
-        "tiles": {"step1": n1, "step3": n3},
+        "tiles": {"step1": n1, "step3": n3, "tile_variant_step1": pplan.var1, "tile_variant_step3": pplan.var3},
         "once_per_lanczos_run_ms": {"pack": ms_pack, "unpack": ms_unpack},
         "packed_vector_elements": pplan.nX, "dense_vector_elements": D * d1 * d1 * D,
         "intermediate_bytes": {"t1": pplan.nT1 * es, "t2": pplan.nT2 * es, "dense_layout_t1": 16.0 * D * d1 * d1 * 6 * D},

@@ -459,6 +459,13 @@ typedef struct ptb_group_tile {
 } ptb_group_tile;                       /* 64 bytes */
 int ptb_gemm_grouped(int dtype, const void* a, const void* b, void* c, const ptb_group_tile* tiles, int ntiles,
                      void* stream);
+/* Tile variants of the grouped GEMM: 0 = the engine's 128 x 64 (complex) / 128 x 128 (real) tile (ptb_gemm_grouped),
+ * 1 = 64 x 32 / 64 x 64 for groups whose sector-sized extents would leave most of the large tile empty (zero-site
+ * problem, fragmented sector profiles).  The tile table must be built for the variant's shape
+ * (ptb_gemm_grouped_tile_shape); same table format and operand conventions. */
+int ptb_gemm_grouped_tile_shape(int dtype, int variant, int* bm, int* bn);
+int ptb_gemm_grouped_v(int dtype, int variant, const void* a, const void* b, void* c, const ptb_group_tile* tiles,
+                       int ntiles, void* stream);
 
 typedef struct ptb_gather_chunk {
     int64_t dst_off;

@@ -76,6 +76,8 @@ SIGNATURES = {
     "ptb_block_svd_max_block_bytes": (_sz, []),
     "ptb_block_svd": (_int, [_int, _ptr, _i64, _int, _ptr, _int, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr]),
     "ptb_gemm_grouped": (_int, [_int, _ptr, _ptr, _ptr, _ptr, _int, _ptr]),
+    "ptb_gemm_grouped_tile_shape": (_int, [_int, _int, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
+    "ptb_gemm_grouped_v": (_int, [_int, _int, _ptr, _ptr, _ptr, _ptr, _int, _ptr]),
     "ptb_block_gather": (_int, [_int, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _ptr]),
     "ptb_svd_polar_workspace_bytes": (_int, [_int, _i64, _i64, ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
     "ptb_svd_polar": (_int, [_int, _i64, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _sz, _ptr, _sz, _ptr,

@@ -31,11 +31,35 @@ struct GroupTile {      // layout of ptb_group_tile (64 bytes); offsets in eleme
 };
 static_assert(sizeof(GroupTile) == 64, "ptb_group_tile must be 64 bytes");
 
+// Small-tile configuration: 64 x 32 complex (64 x 64 real) CTA tiles, warp tiles 16 x 8 (16 x 16), for groups whose
+// sector-sized extents leave most of a 128 x 64 tile empty (the zero-site problem: both output extents of step 3 are
+// sector sized; fragmented sector profiles with a median of ~14 rows).  Fewer DMMA per fragment load than the large
+// tile (the 16 warps of a CTA are always all busy, though), more and shorter tiles per launch, a deeper stage ring.
 template <bool CPLX>
-__global__ void __launch_bounds__(WsCfg<CPLX>::THREADS, 1)
+struct GroupSmallCfg {
+    static constexpr int E = CPLX ? 2 : 1;
+    static constexpr int BM = 64;
+    static constexpr int BN = CPLX ? 32 : 64;
+    static constexpr int BK = 16;
+    static constexpr int WTM = 16;
+    static constexpr int WTN = CPLX ? 8 : 16;
+    static constexpr int MT = WTM / 8;
+    static constexpr int NT = WTN / 8;
+    static constexpr int PAD = CPLX ? 2 : 4;
+    static constexpr int STAGES = 8;
+    static constexpr int CONSUMER_WARPS = 16;
+    static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
+    static constexpr int PRODUCER_REGS = 24;
+    static constexpr int CONSUMER_REGS = 112;
+    static constexpr int SA = BK * (BM + PAD) * E;
+    static constexpr int SB = BK * (BN + PAD) * E;
+    static constexpr int SMEM_BYTES = STAGES * (SA + SB) * 8 + 2 * STAGES * 8 + 128;
+};
+
+template <bool CPLX, class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
 gemm_grouped_kernel(const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase,
                     const GroupTile* __restrict__ tiles, int ntiles) {
-    using Cfg = WsCfg<CPLX>;
     constexpr int E = Cfg::E, BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK;
     constexpr int MT = Cfg::MT, NT = Cfg::NT, PAD = Cfg::PAD, STAGES = Cfg::STAGES;
     constexpr int SA = Cfg::SA, SB = Cfg::SB;
@@ -205,12 +229,11 @@ gemm_grouped_kernel(const double* __restrict__ Abase, const double* __restrict__
     }
 }
 
-template <bool CPLX>
+template <bool CPLX, class Cfg>
 static int launch_grouped(const double* a, const double* b, double* c, const GroupTile* tiles, int ntiles,
                           cudaStream_t stream) {
-    using Cfg = WsCfg<CPLX>;
     if (ntiles <= 0) return PTB_OK;
-    auto kern = gemm_grouped_kernel<CPLX>;
+    auto kern = gemm_grouped_kernel<CPLX, Cfg>;
     static DeviceFlags configured;
     PTB_TRY(ensure_dynamic_smem(configured, kern, Cfg::SMEM_BYTES));
     const int num_sms = device_sm_count();

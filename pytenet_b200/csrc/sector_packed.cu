@@ -53,22 +53,39 @@ __global__ void __launch_bounds__(GATHER_THREADS) block_gather_kernel(const doub
 
 extern "C" {
 
-int ptb_gemm_grouped(int dtype, const void* a, const void* b, void* c, const ptb_group_tile* tiles, int ntiles,
-                     void* stream) {
-    if (ntiles < 0) return PTB_ERR_BAD_ARG;
+int ptb_gemm_grouped_tile_shape(int dtype, int variant, int* bm, int* bn) {
+    if (!bm || !bn || variant < 0 || variant > 1) return PTB_ERR_BAD_ARG;
+    if (dtype != PTB_COMPLEX128 && dtype != PTB_REAL64) return PTB_ERR_BAD_DTYPE;
+    const bool cplx = dtype == PTB_COMPLEX128;
+    if (variant == 0) { *bm = cplx ? WsCfg<true>::BM : WsCfg<false>::BM; *bn = cplx ? WsCfg<true>::BN : WsCfg<false>::BN; }
+    else { *bm = cplx ? GroupSmallCfg<true>::BM : GroupSmallCfg<false>::BM; *bn = cplx ? GroupSmallCfg<true>::BN : GroupSmallCfg<false>::BN; }
+    return PTB_OK;
+}
+
+int ptb_gemm_grouped_v(int dtype, int variant, const void* a, const void* b, void* c, const ptb_group_tile* tiles,
+                       int ntiles, void* stream) {
+    if (ntiles < 0 || variant < 0 || variant > 1) return PTB_ERR_BAD_ARG;
     if (ntiles == 0) return PTB_OK;
     if (!a || !b || !c || !tiles) return PTB_ERR_BAD_ARG;
     auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
     if (!al16(a) || !al16(b) || !al16(c) || !al16(tiles)) return PTB_ERR_ALIGNMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const GroupTile* gt = reinterpret_cast<const GroupTile*>(tiles);
+    const double* ad = static_cast<const double*>(a);
+    const double* bd = static_cast<const double*>(b);
+    double* cd = static_cast<double*>(c);
     if (dtype == PTB_COMPLEX128)
-        return launch_grouped<true>(static_cast<const double*>(a), static_cast<const double*>(b),
-                                    static_cast<double*>(c), gt, ntiles, st);
+        return variant == 0 ? launch_grouped<true, WsCfg<true>>(ad, bd, cd, gt, ntiles, st)
+                            : launch_grouped<true, GroupSmallCfg<true>>(ad, bd, cd, gt, ntiles, st);
     if (dtype == PTB_REAL64)
-        return launch_grouped<false>(static_cast<const double*>(a), static_cast<const double*>(b),
-                                     static_cast<double*>(c), gt, ntiles, st);
+        return variant == 0 ? launch_grouped<false, WsCfg<false>>(ad, bd, cd, gt, ntiles, st)
+                            : launch_grouped<false, GroupSmallCfg<false>>(ad, bd, cd, gt, ntiles, st);
     return PTB_ERR_BAD_DTYPE;
+}
+
+int ptb_gemm_grouped(int dtype, const void* a, const void* b, void* c, const ptb_group_tile* tiles, int ntiles,
+                     void* stream) {
+    return ptb_gemm_grouped_v(dtype, 0, a, b, c, tiles, ntiles, stream);
 }
 
 int ptb_block_gather(int dtype, const void* src, void* dst, const ptb_gather_chunk* chunks,

@@ -37,6 +37,7 @@ Sector layouts are untouched (qbonds / retained indices stay bit-exact).  Bonds 
 is False and the callers use the banded path of sectors.py.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -181,6 +182,43 @@ def _k_pieces(klen, live):
     return pc_g, pc_k0, pc_k1, npc, pc_first
 
 
+# Tile variants of the grouped GEMM (ptb_gemm_grouped_v): 0 = the engine's large tile, 1 = the small tile.  A table is
+# built for both and the cheaper one is taken: cost = executed flops / relative efficiency of the variant (the small
+# tile issues fewer DMMA per fragment load but measured within 5 % of the large tile's rate on full tiles, and its finer
+# granularity balances the persistent CTAs better: it wins on every sector profile measured so far).
+_SMALL_TILE_EFFICIENCY = 0.95
+_FORCE_VARIANT = os.environ.get("PYTENET_B200_GROUPED_TILE", "auto")
+_TILE_SHAPES = {}
+
+
+def _tile_shapes(cplx):
+    hit = _TILE_SHAPES.get(bool(cplx))
+    if hit is None:
+        lib = _lib.load()
+        hit = []
+        for variant in (0, 1):
+            bm, bn = ctypes.c_int(), ctypes.c_int()
+            _lib.check(lib.ptb_gemm_grouped_tile_shape(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, variant,
+                                                       ctypes.byref(bm), ctypes.byref(bn)), "ptb_gemm_grouped_tile_shape")
+            hit.append((bm.value, bn.value))
+        _TILE_SHAPES[bool(cplx)] = hit
+    return hit
+
+
+def _choose_tiles(cplx, build):
+    """`build(BM, BN)` -> tile table for that tile shape; returns (variant, table) of the cheaper variant."""
+    best = None
+    for variant, (BM, BN) in enumerate(_tile_shapes(cplx)):
+        if _FORCE_VARIANT in ("0", "1") and int(_FORCE_VARIANT) != variant:
+            continue
+        tab = build(BM, BN)
+        cost = float(BM * BN) * float(np.sum((tab["k"].astype(np.int64) + 3) // 4 * 4))
+        cost /= (1.0 if variant == 0 else _SMALL_TILE_EFFICIENCY)
+        if best is None or cost < best[0]:
+            best = (cost, variant, tab, (BM, BN))
+    return best[1], best[2], best[3]
+
+
 def _tiles_of(groups_m, groups_n, BM, BN):
     """Tile enumeration of a list of (m x n) matrices: per tile (matrix index, row start, column start)."""
     ntm, ntn = -(-groups_m // BM), -(-groups_n // BN)
@@ -214,12 +252,6 @@ class PackedHeffPlan:
         self._wcache = {}
         if not self.supported:
             return
-        lib = _lib.load()
-        bm, bn, bk = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
-        _lib.check(lib.ptb_gemm_tile_shape(_lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64, ctypes.byref(bm),
-                                           ctypes.byref(bn), ctypes.byref(bk)), "ptb_gemm_tile_shape")
-        BM, BN = bm.value, bn.value
-        self.tile = (BM, BN, bk.value)
         qL, oL, nL = L
         qR, oR, nR = R
         self.L, self.R = L, R
@@ -304,17 +336,22 @@ class PackedHeffPlan:
 
         # ---- GEMM tile tables ----
         live1 = np.flatnonzero((M > 0) & (N1 > 0))
-        gi, tm, tn = _tiles_of(Mp[live1], N1p[live1], BM, BN)
-        b = live1[gi]
-        self.tiles1_host = _tile_table_cols(self.offX[b] + tm, self.offRB[b] + tn, self.offT1[b] + tm * N1p[b] + tn,
-                                            Mp[b], N1p[b], N1p[b], np.minimum(BM, Mp[b] - tm),
-                                            np.minimum(BN, N1p[b] - tn), nR[b])
-        gi, tm, tn = _tiles_of(N3p[pc_ap], nLp[pc_ap], BM, BN)
-        ap, k0 = pc_ap[gi], pc_k0[gi]
-        self.tiles3_host = _tile_table_cols(self.offT2[ap] + k0 * N3p[ap] + tm, self.offLP[ap] + k0 * nLp[ap] + tn,
-                                            pc_off[gi] + tm * nLp[ap] + tn, N3p[ap], nLp[ap], nLp[ap],
-                                            np.minimum(BM, N3p[ap] - tm), np.minimum(BN, nLp[ap] - tn),
-                                            pc_k1[gi] - k0)
+
+        def build1(BM, BN):
+            gi, tm, tn = _tiles_of(Mp[live1], N1p[live1], BM, BN)
+            b = live1[gi]
+            return _tile_table_cols(self.offX[b] + tm, self.offRB[b] + tn, self.offT1[b] + tm * N1p[b] + tn,
+                                    Mp[b], N1p[b], N1p[b], np.minimum(BM, Mp[b] - tm), np.minimum(BN, N1p[b] - tn),
+                                    nR[b])
+
+        def build3(BM, BN):
+            gi, tm, tn = _tiles_of(N3p[pc_ap], nLp[pc_ap], BM, BN)
+            ap, k0 = pc_ap[gi], pc_k0[gi]
+            return _tile_table_cols(self.offT2[ap] + k0 * N3p[ap] + tm, self.offLP[ap] + k0 * nLp[ap] + tn,
+                                    pc_off[gi] + tm * nLp[ap] + tn, N3p[ap], nLp[ap], nLp[ap],
+                                    np.minimum(BM, N3p[ap] - tm), np.minimum(BN, nLp[ap] - tn), pc_k1[gi] - k0)
+        self.var1, self.tiles1_host, self.tile1 = _choose_tiles(self.cplx, build1)
+        self.var3, self.tiles3_host, self.tile3 = _choose_tiles(self.cplx, build3)
 
         # ---- gather tables that depend on the quantum numbers only ----
         one = np.ones(len(xb), dtype=np.int64)
@@ -343,15 +380,14 @@ class PackedHeffPlan:
     def flop_counts(self):
         """`exact`: flops of the non-zero sector blocks (two GEMM steps); `visited`: what the grouped GEMMs execute
         (whole 128 x 64 tiles, contraction length rounded up to the DMMA k = 4)."""
-        BM, BN, _ = self.tile
         per = 8.0 if self.cplx else 2.0
         _, _, nL = self.L
         _, _, nR = self.R
         exact = per * (float(np.sum(self.M * self.N1 * nR)) + float(np.sum(self.N3 * nL * self.K3)))
         vis = 0.0
-        for tab in (self.tiles1_host, self.tiles3_host):
+        for tab, (BM, BN) in ((self.tiles1_host, self.tile1), (self.tiles3_host, self.tile3)):
             vis += per * BM * BN * float(np.sum((tab["k"].astype(np.int64) + 3) // 4 * 4))
-        return {"exact": exact, "visited": vis}
+        return {"exact": exact, "visited": vis, "tile_variants": (self.var1, self.var3)}
 
     def _w_tables(self, w):
         """Block-gather tables of the W step for the MPO tensor `w` (device tensor; cached per tensor version)."""
@@ -487,12 +523,12 @@ class PackedHeffOperator:
         y = (torch.empty if plan.cplx else torch.zeros)(max(plan.nX, 1), dtype=x.dtype, device=x.device)
         n1, n3 = len(plan.tiles1_host), len(plan.tiles3_host)
         if n1:
-            _lib.check(lib.ptb_gemm_grouped(dt, x.data_ptr(), self.rb.data_ptr(), self.t1.data_ptr(),
-                                            self.tabs["tiles1"].data_ptr(), n1, stream), "ptb_gemm_grouped(1)")
+            _lib.check(lib.ptb_gemm_grouped_v(dt, plan.var1, x.data_ptr(), self.rb.data_ptr(), self.t1.data_ptr(),
+                                              self.tabs["tiles1"].data_ptr(), n1, stream), "ptb_gemm_grouped(1)")
         self.wtab.run(lib, dt, self.t1, self.t2, stream)
         if n3:
-            _lib.check(lib.ptb_gemm_grouped(dt, self.t2.data_ptr(), self.lp.data_ptr(), self.o.data_ptr(),
-                                            self.tabs["tiles3"].data_ptr(), n3, stream), "ptb_gemm_grouped(3)")
+            _lib.check(lib.ptb_gemm_grouped_v(dt, plan.var3, self.t2.data_ptr(), self.lp.data_ptr(), self.o.data_ptr(),
+                                              self.tabs["tiles3"].data_ptr(), n3, stream), "ptb_gemm_grouped(3)")
         self.tabs["repack"].run(lib, dt, self.o, y, stream)
         return y[:plan.nX]
 
@@ -535,7 +571,6 @@ class PackedEnvPlan:
         if not self.supported:
             return
         Dl, d, Dr, cl, cr = base.dims              # of the (possibly mirrored) problem
-        BM, BN, _ = base.tile
         _, oL, nL = base.L
         _, oR, nR = base.R
         excl = lambda v: np.cumsum(v) - v          # noqa: E731
@@ -548,11 +583,14 @@ class PackedEnvPlan:
                                 oL[xal] * sx + xs * ss + oR[xb] * sy, one * sy, one * sx)
         # T1^T_b = RB_b^T X_b
         live1 = np.flatnonzero((base.M > 0) & (base.N1 > 0))
-        gi, tm, tn = _tiles_of(N1p[live1], Mp[live1], BM, BN)
-        b = live1[gi]
-        self.tiles1 = _tile_table_cols(base.offRB[b] + tm, base.offX[b] + tn, base.offT1[b] + tm * Mp[b] + tn,
-                                       N1p[b], Mp[b], Mp[b], np.minimum(BM, N1p[b] - tm), np.minimum(BN, Mp[b] - tn),
-                                       nR[b])
+
+        def build1(BM, BN):
+            gi, tm, tn = _tiles_of(N1p[live1], Mp[live1], BM, BN)
+            b = live1[gi]
+            return _tile_table_cols(base.offRB[b] + tm, base.offX[b] + tn, base.offT1[b] + tm * Mp[b] + tn,
+                                    N1p[b], Mp[b], Mp[b], np.minimum(BM, N1p[b] - tm), np.minimum(BN, Mp[b] - tn),
+                                    nR[b])
+        self.var1, self.tiles1, _ = _choose_tiles(self.cplx, build1)
         # BT_a'[(n_off(s') + j'), i'] = conj(X[g][j', m_off(a', s') + i'])
         tc_ap, tc_sp, tc_g, tc_n = base.tc
         self.offBT = excl(N3 * nLp)
@@ -565,11 +603,14 @@ class PackedEnvPlan:
         pc_size = K3p[pc_ap] * nLp[pc_ap]
         pc_off = excl(pc_size)
         self.nO = int(pc_size.sum())
-        gi, tm, tn = _tiles_of(K3p[pc_ap], nLp[pc_ap], BM, BN)
-        ap, k0 = pc_ap[gi], pc_k0[gi]
-        self.tiles3 = _tile_table_cols(base.offT2T[ap] + k0 * K3p[ap] + tm, self.offBT[ap] + k0 * nLp[ap] + tn,
-                                       pc_off[gi] + tm * nLp[ap] + tn, K3p[ap], nLp[ap], nLp[ap],
-                                       np.minimum(BM, K3p[ap] - tm), np.minimum(BN, nLp[ap] - tn), pc_k1[gi] - k0)
+
+        def build3(BM, BN):
+            gi, tm, tn = _tiles_of(K3p[pc_ap], nLp[pc_ap], BM, BN)
+            ap, k0 = pc_ap[gi], pc_k0[gi]
+            return _tile_table_cols(base.offT2T[ap] + k0 * K3p[ap] + tm, self.offBT[ap] + k0 * nLp[ap] + tn,
+                                    pc_off[gi] + tm * nLp[ap] + tn, K3p[ap], nLp[ap], nLp[ap],
+                                    np.minimum(BM, K3p[ap] - tm), np.minimum(BN, nLp[ap] - tn), pc_k1[gi] - k0)
+        self.var3, self.tiles3, _ = _choose_tiles(self.cplx, build3)
         # out[oL[alpha]+i, k, oL[a']+i'] = sum_p O_(a',p)[kk + i, i']
         tr_ap, tr_k, tr_al, tr_kk = base.tr
         cnt = npc[tr_ap]
@@ -642,13 +683,13 @@ class PackedEnvPlan:
         tabs["pack_r"].run(lib, dt, env, rb, stream)
         n1, n3 = len(self.tiles1), len(self.tiles3)
         if n1:
-            _lib.check(lib.ptb_gemm_grouped(dt, rb.data_ptr(), x.data_ptr(), t1.data_ptr(), tabs["tiles1"].data_ptr(),
-                                            n1, stream), "ptb_gemm_grouped(env 1)")
+            _lib.check(lib.ptb_gemm_grouped_v(dt, self.var1, rb.data_ptr(), x.data_ptr(), t1.data_ptr(),
+                                              tabs["tiles1"].data_ptr(), n1, stream), "ptb_gemm_grouped(env 1)")
         wtab.run(lib, dt, t1, t2, stream)
         tabs["pack_bt"].run(lib, dt, x, bt, stream)
         if n3:
-            _lib.check(lib.ptb_gemm_grouped(dt, t2.data_ptr(), bt.data_ptr(), o.data_ptr(), tabs["tiles3"].data_ptr(),
-                                            n3, stream), "ptb_gemm_grouped(env 3)")
+            _lib.check(lib.ptb_gemm_grouped_v(dt, self.var3, t2.data_ptr(), bt.data_ptr(), o.data_ptr(),
+                                              tabs["tiles3"].data_ptr(), n3, stream), "ptb_gemm_grouped(env 3)")
         out = torch.zeros((Dl, cl, Dl), dtype=dtype, device=device)
         tabs["unpack"].run(lib, dt, o, out, stream)
         return out

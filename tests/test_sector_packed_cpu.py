@@ -85,8 +85,7 @@ def test_packed_tables_reproduce_the_dense_contraction(cuda_lib, seed, Dl, d, Dr
     ref = oracle.apply_local_hamiltonian(a, w, l, r)
     assert np.linalg.norm(out.reshape(Dl, d, Dr) - ref) / np.linalg.norm(ref) < 1e-13
     # tiles are sorted by decreasing contraction length and never exceed the engine's tile
-    BM, BN, _ = plan.tile
-    for tab in (plan.tiles1_host, plan.tiles3_host):
+    for tab, (BM, BN) in ((plan.tiles1_host, plan.tile1), (plan.tiles3_host, plan.tile3)):
         assert np.all(np.diff(tab["k"]) <= 0) and tab["m"].max() <= BM and tab["n"].max() <= BN
     fc = plan.flop_counts()
     assert fc["visited"] >= fc["exact"] > 0

@@ -58,6 +58,66 @@ def test_grouped_gemm_kernel_against_numpy(cuda_lib):
     assert np.array_equal(got[untouched], C0[untouched])
 
 
+@pytest.mark.parametrize("cplx", [True, False])
+def test_grouped_gemm_small_tile_variant_against_numpy(cuda_lib, cplx):
+    """ptb_gemm_grouped_v, variant 1 (64 x 32 complex / 64 x 64 real tiles): ragged extents, contraction lengths 1 ... 300,
+    arbitrary (complex) / even (real) leading dimensions and offsets, untouched elements of C outside the tiles."""
+    import ctypes
+    from pytenet_b200.sector_packed import _tile_table
+    bm, bn = ctypes.c_int(), ctypes.c_int()
+    assert cuda_lib.ptb_gemm_grouped_tile_shape(1 if cplx else 0, 1, ctypes.byref(bm), ctypes.byref(bn)) == 0
+    BM, BN = bm.value, bn.value
+    assert (BM, BN) == ((64, 32) if cplx else (64, 64))
+    rng = np.random.default_rng(14)
+    nA, nB, nC = 300000, 200000, 200000
+    mk = (lambda n: rng.normal(size=n) + 1j * rng.normal(size=n)) if cplx else (lambda n: rng.normal(size=n))
+    A, B, C0 = mk(nA), mk(nB), mk(nC)
+    ev = 1 if cplx else 2
+    tiles, want = [], C0.copy()
+    c_pos = 0
+    for (m, n, k) in [(BM, BN, 16), (BM, BN, 300), (2, 2, 1), (6, 4, 2), (38, BN, 50), (BM, 10, 7), (34, 18, 129),
+                      (BM, BN // 2, 4), (BM // 2, BN, 33), (50, 20, 1), (2, BN, 18), (BM, 2, 5), (62, 30, 255)] * 3:
+        lda = m + ev * int(rng.integers(0, 5)); ldb = n + ev * int(rng.integers(0, 5)); ldc = n + int(rng.integers(0, 5))
+        a_off = ev * int(rng.integers(0, (nA - k * lda - m) // ev)); b_off = ev * int(rng.integers(0, (nB - k * ldb - n) // ev))
+        c_off = c_pos
+        c_pos += m * ldc + 7
+        assert c_pos < nC
+        tiles.append((a_off, b_off, c_off, lda, ldb, ldc, m, n, k))
+        a = A[a_off + np.arange(k)[:, None] * lda + np.arange(m)[None, :]]
+        b = B[b_off + np.arange(k)[:, None] * ldb + np.arange(n)[None, :]]
+        want[c_off + np.arange(m)[:, None] * ldc + np.arange(n)[None, :]] = a.T @ b
+    tab = _tile_table(tiles)
+    dA, dB, dC = cu(A), cu(B), cu(C0)
+    dT = torch.from_numpy(tab.view(np.uint8).reshape(-1)).cuda()
+    st = cuda_lib.ptb_gemm_grouped_v(1 if cplx else 0, 1, dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), dT.data_ptr(),
+                                     len(tab), torch.cuda.current_stream().cuda_stream)
+    assert st == 0
+    got = dC.cpu().numpy()
+    assert rel(got, want) < 1e-13
+    untouched = np.ones(nC, dtype=bool)
+    for (a_off, b_off, c_off, lda, ldb, ldc, m, n, k) in tiles:
+        untouched[(c_off + np.arange(m)[:, None] * ldc + np.arange(n)[None, :]).reshape(-1)] = False
+    assert np.array_equal(got[untouched], C0[untouched])
+
+
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_packed_plans_with_forced_tile_variant(cuda_lib, monkeypatch, variant):
+    """The packed matvec and both environment updates with every grouped GEMM forced to one tile variant: equal to
+    the oracle whichever tile shape the tables were built for."""
+    import pytenet_b200.sector_packed as sp
+    monkeypatch.setattr(sp, "_FORCE_VARIANT", variant)
+    rng = np.random.default_rng(31)
+    qn, a, w, l, r = _block_sparse_problem(rng, 230, 3, 310, 4, 5)
+    plan = sp.PackedHeffPlan(*qn, cplx=True)
+    assert (plan.var1, plan.var3) == (int(variant), int(variant))
+    got = plan.bind(cu(w), cu(l), cu(r)).apply_dense(cu(a)).cpu().numpy()
+    assert rel(got, oracle.apply_local_hamiltonian(a, w, l, r)) < TOL
+    er = sp.PackedEnvPlan(*qn, cplx=True, side="right")
+    assert rel(er.apply(cu(a), cu(w), cu(r)).cpu().numpy(), oracle.contraction_operator_step_right(a, a, w, r)) < TOL
+    el = sp.PackedEnvPlan(*qn, cplx=True, side="left")
+    assert rel(el.apply(cu(a), cu(w), cu(l)).cpu().numpy(), oracle.contraction_operator_step_left(a, a, w, l)) < TOL
+
+
 def test_grouped_gemm_kernel_float64_against_numpy(cuda_lib):
     """float64 tiles (128 x 128): the bulk copies move 16-byte granules, so offsets, leading dimensions and the m / n
     extents are even (what `PackedHeffPlan(cplx=False)` emits); contraction lengths arbitrary."""
