@@ -353,6 +353,23 @@ def block_sparse_eigh(a, q0):
 _POLAR_MIN = int(os.environ.get("PYTENET_B200_POLAR_SVD_MIN", "64"))
 
 
+_POLAR_WS = {}
+
+
+def _polar_workspace(lib, dt, rows, cols):
+    """(device bytes, host bytes) of the polar driver for one shape, cached: the query is a cuSOLVER call."""
+    key = (dt, rows, cols)
+    hit = _POLAR_WS.get(key)
+    if hit is None:
+        nd, nh = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        _lib.check(lib.ptb_svd_polar_workspace_bytes(dt, rows, cols, ctypes.byref(nd), ctypes.byref(nh)),
+                   "ptb_svd_polar_workspace_bytes")
+        if len(_POLAR_WS) > 4096:
+            _POLAR_WS.clear()
+        hit = _POLAR_WS[key] = (nd.value, nh.value)
+    return hit
+
+
 _POLAR_SKIP = {}
 _POLAR_BACKOFF = 8
 
@@ -388,14 +405,12 @@ def dense_svd(a):
     vbuf = torch.empty((k, cols), dtype=a.dtype, device=a.device)       # column-major cols x k
     sdev = torch.empty(k, dtype=dev.F64, device=a.device)
     info = torch.zeros(1, dtype=torch.int32, device=a.device)
-    nd, nh = ctypes.c_size_t(0), ctypes.c_size_t(0)
-    _lib.check(lib.ptb_svd_polar_workspace_bytes(dt, rows, cols, ctypes.byref(nd), ctypes.byref(nh)),
-               "ptb_svd_polar_workspace_bytes")
-    dws = dev.workspace(max(nd.value, 16), a.device, tag="svd")
-    hws = np.empty(max(nh.value, 16), dtype=np.uint8)
+    nd, nh = _polar_workspace(lib, dt, rows, cols)
+    dws = dev.workspace(max(nd, 16), a.device, tag="svd")
+    hws = np.empty(max(nh, 16), dtype=np.uint8)
     err = ctypes.c_double(0.0)
     st = lib.ptb_svd_polar(dt, rows, cols, work.data_ptr(), rows, sdev.data_ptr(), ubuf.data_ptr(), rows,
-                           vbuf.data_ptr(), cols, dws.data_ptr(), nd.value, hws.ctypes.data, nh.value, info.data_ptr(),
+                           vbuf.data_ptr(), cols, dws.data_ptr(), nd, hws.ctypes.data, nh, info.data_ptr(),
                            ctypes.byref(err), dev.stream_ptr(a.device))
     _lib.check(st, "ptb_svd_polar")
     if int(info.item()) != 0 or not (err.value <= 1e-11):
@@ -445,10 +460,7 @@ def dense_svd_batch(mats):
             tall = m > n
             work = dev.dense(a.mH) if tall else a.clone()
             rows, cols = work.shape[1], work.shape[0]
-            nd, nh = ctypes.c_size_t(0), ctypes.c_size_t(0)
-            _lib.check(lib.ptb_svd_polar_workspace_bytes(dt, rows, cols, ctypes.byref(nd), ctypes.byref(nh)),
-                       "ptb_svd_polar_workspace_bytes")
-            need.append((max(nd.value, 16) + 255) // 256 * 256)
+            need.append((max(_polar_workspace(lib, dt, rows, cols)[0], 16) + 255) // 256 * 256)
             keep.append((tall, work, rows, cols))
         ws = dev.workspace(sum(need), device, tag="svd_batch")
         infos = torch.zeros(len(jobs_idx), dtype=torch.int32, device=device)

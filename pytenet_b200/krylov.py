@@ -54,7 +54,7 @@ def _lanczos_steps(lib, afunc, x, numiter, V, scal, sfx, stream, scratch):
                          vj + row, scratch, stream), "lanczos_ortho_step")
 
 
-def _lanczos_device(afunc, vstart, numiter):
+def _lanczos_device(afunc, vstart, numiter, transient=False):
     """Enqueue the Lanczos recursion on the device; returns (n, V, scal) with V the resident (numiter, n)
     Lanczos-vector buffer and scal = [|vstart|, alpha[0:k], beta[0:k-1]] device doubles.
     All `numiter` steps are enqueued without host synchronisation; the breakdown
@@ -71,7 +71,14 @@ def _lanczos_device(afunc, vstart, numiter):
     sfx = "z" if cplx else "d"
     stream = dev.stream_ptr(device)
     scratch = dev.lanczos_scratch(device).data_ptr()
-    V = torch.empty((numiter, n), dtype=x.dtype, device=device)
+    if transient:
+        # the caller consumes the Lanczos vectors before the next run on this stream (expm_krylov): a view of the
+        # grow-only workspace instead of a fresh allocation per run (sizes change with every split of a two-site
+        # sweep, and a caching-allocator miss is a cudaMalloc)
+        es = x.element_size()
+        V = dev.workspace(numiter * n * es, device, tag="krylov_V")[:numiter * n * es].view(x.dtype).reshape(numiter, n)
+    else:
+        V = torch.empty((numiter, n), dtype=x.dtype, device=device)
     # device scalars: [nrm, alpha[0:k], beta[0:k-1]]
     scal = torch.zeros(2 * numiter, dtype=dev.F64, device=device)
     # operators that know the fused C entry (one call enqueues the whole run: _sweep.HeffOperator /
@@ -363,6 +370,12 @@ def expm_krylov(afunc, vec, dt, numiter, hermitian=False):
 _EXPM_DEVICE_MAX_ITER = 64
 
 
+def _CAPTURE_SAFE_ONLY():
+    """True while a sweep step is being captured into a CUDA graph: the workspace must not be (re)allocated then."""
+    from . import block_sparse_util as bsu
+    return bsu._CAPTURING
+
+
 def _expm_device(afunc, x, dt, numiter):
     """expm_krylov with the k x k problem solved on the device (ptb_krylov_expm_apply): no device->host
     transfer on the way; the scalar checks follow immediately, or at the end of a `deferred_checks()` block."""
@@ -381,7 +394,7 @@ def _expm_device(afunc, x, dt, numiter):
             else:
                 _check_scalars(scal.cpu().numpy(), _threshold_length(afunc, n), numiter)
             return out
-    n, V, scal = _lanczos_device(afunc, x, numiter)
+    n, V, scal = _lanczos_device(afunc, x, numiter, transient=not _CAPTURE_SAFE_ONLY())
     vc = V.dtype.is_complex
     dtc = complex(dt)
     out_cplx = vc or isinstance(dt, (complex, np.complexfloating))
