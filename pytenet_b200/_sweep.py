@@ -202,16 +202,27 @@ class _AbsorbRight(AbsorbSectorPlan):
         super().__init__(qc_rows, qc_cols, qs, q_other, False, cplx=cplx)
 
 
+_SMALL_FITS = {}        # (Dl, d, Dr, cl, cr, numiter) -> bool: ptb_local_step_small_fits, asked once per shape
+
+
 def _small_local_step(x, w, l, r, dims, numiter, dt, V=None, scal=None):
     """The whole local problem in ONE kernel launch (csrc/lanczos_small.cu: ptb_local_step_small) when it is small
-    enough for a single CTA -- the launch-latency regime (README config, METTS, chain edges).  `dt is None`: the
-    Lanczos run only (fills `V`, `scal`; returns True).  Otherwise returns (exp(-dt H) x ... as `out`, scal).
+    enough -- the launch-latency regime (README config, METTS, chain edges).  `dt is None`: the Lanczos run only
+    (fills `V`, `scal`; returns True).  Otherwise returns (exp(-dt H) x ... as `out`, scal); the Lanczos vectors
+    then live in a per-stream scratch buffer, and `scal` may be a page-locked HOST tensor (krylov._defer_slot):
+    the kernel writes its 2 numiter scalars straight into it (mapped memory), no copy is enqueued.
     Returns None when the problem does not qualify."""
     Dl, d, Dr, cl, cr = dims
     lib = _lib.load()
-    if numiter > 64 or not lib.ptb_local_step_small_fits(Dl, d, Dr, cl, cr, numiter):
+    key = (Dl, d, Dr, cl, cr, numiter)
+    fits = _SMALL_FITS.get(key)
+    if fits is None:
+        fits = numiter <= 64 and bool(lib.ptb_local_step_small_fits(Dl, d, Dr, cl, cr, numiter))
+        _SMALL_FITS[key] = fits
+    if not fits:
         return None
-    if not all(isinstance(t, torch.Tensor) and t.is_cuda for t in (x, l, r)):
+    if not (isinstance(x, torch.Tensor) and isinstance(l, torch.Tensor) and isinstance(r, torch.Tensor)
+            and x.is_cuda and l.is_cuda and r.is_cuda):
         return None
     cplx = x.dtype.is_complex
     if x.dtype not in (dev.F64, dev.C128):
@@ -231,10 +242,10 @@ def _small_local_step(x, w, l, r, dims, numiter, dt, V=None, scal=None):
     n = Dl * d * Dr
     dt_code = _lib.PTB_COMPLEX128 if cplx else _lib.PTB_REAL64
     if V is None:
-        V = torch.empty((numiter, n), dtype=x.dtype, device=device)
+        # internal to the step: (numiter x n) elements of a grow-only, stream-ordered scratch buffer
+        V = dev.workspace(numiter * n * (16 if cplx else 8), device, tag="small_step_V")
+    if scal is None:
         scal = torch.empty(2 * numiter, dtype=dev.F64, device=device)      # the kernel writes every entry
-    nbytes = lib.ptb_local_step_small_workspace_bytes(dt_code, Dl, d, Dr, cl, cr)
-    ws = dev.workspace(nbytes, device, tag="small_step")
     out = None
     apply_expm, dre, dim_, out_cplx = 0, 0.0, 0.0, 0
     if dt is not None:
@@ -245,9 +256,10 @@ def _small_local_step(x, w, l, r, dims, numiter, dt, V=None, scal=None):
     st = lib.ptb_local_step_small(dt_code, x.data_ptr(), w.data_ptr() if w is not None else None, int(w_cplx),
                                   l.data_ptr(), r.data_ptr(), Dl, d, Dr, cl, cr, numiter, V.data_ptr(),
                                   scal.data_ptr(), apply_expm, dre, dim_, out_cplx,
-                                  out.data_ptr() if out is not None else None, ws.data_ptr(), nbytes,
+                                  out.data_ptr() if out is not None else None, None, 0,
                                   dev.stream_ptr(device))
-    _lib.check(st, "ptb_local_step_small")
+    if st != 0:
+        _lib.check(st, "ptb_local_step_small")
     return True if dt is None else (out, scal)
 
 
@@ -273,10 +285,10 @@ class HeffOperator:
             return None
         return Dl, d, Dr, cl, cr
 
-    def ptb_expm_run(self, x, dt, numiter):
+    def ptb_expm_run(self, x, dt, numiter, scal=None):
         """exp(dt H_eff) x in one kernel launch when the problem is small (krylov._expm_device prefers it)."""
         dims = self._dims(x)
-        return None if dims is None else _small_local_step(x, self.w, self.l, self.r, dims, numiter, dt)
+        return None if dims is None else _small_local_step(x, self.w, self.l, self.r, dims, numiter, dt, scal=scal)
 
     def ptb_lanczos_run(self, x, numiter, V, scal):
         w, l, r = self.w, self.l, self.r
@@ -332,9 +344,9 @@ class BondOperator:
             return None
         return Dl, 1, Dr, chi, chi
 
-    def ptb_expm_run(self, x, dt, numiter):
+    def ptb_expm_run(self, x, dt, numiter, scal=None):
         dims = self._dims(x)
-        return None if dims is None else _small_local_step(x, None, self.l, self.r, dims, numiter, dt)
+        return None if dims is None else _small_local_step(x, None, self.l, self.r, dims, numiter, dt, scal=scal)
 
     def ptb_lanczos_run(self, x, numiter, V, scal):
         l, r = self.l, self.r

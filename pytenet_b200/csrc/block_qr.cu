@@ -14,8 +14,9 @@ using namespace ptb;
 
 namespace {
 
-constexpr int QR_THREADS = 256;
-constexpr int QR_WARPS = QR_THREADS / 32;
+// threads per CTA: one warp per column of the trailing update (blocks of up to 8 columns: 256 threads, else 1024 --
+// the kernel is latency bound, a warp that has to walk over several columns serialises them)
+constexpr int QR_MAX_THREADS = 1024;
 
 struct Cx {
     double re, im;
@@ -37,17 +38,45 @@ __device__ __forceinline__ void st(double* s, int idx, Cx v) {
     else s[idx] = v.re;
 }
 
+// column c of `a` (column-major, m rows) <- (I - f v v^H) column c, with v = (1, a[j+1.., j]) the reflector stored below
+// the diagonal of column j: one warp, rows j .. m-1.  Not inlined and not unrolled: the kernel runs once per launch
+// with a cold instruction cache, the code fetched matters more than the loop overhead.
+template <bool CPLX>
+__device__ __noinline__ void apply_reflector(double* a, int m, int j, int c, Cx f0, int lane) {
+    Cx w = {0.0, 0.0};
+#pragma unroll 1
+    for (int i = j + 1 + lane; i < m; i += 32) {
+        const Cx p = cmulc(ld<CPLX>(a, j * m + i), ld<CPLX>(a, c * m + i));
+        w.re += p.re; w.im += p.im;
+    }
+    w.re = warp_sum(w.re);
+    if (CPLX) w.im = warp_sum(w.im);
+    // the row-j element of column c is read and written by lane 0 only (broadcast by shuffle)
+    Cx top = {0.0, 0.0};
+    if (lane == 0) top = ld<CPLX>(a, c * m + j);
+    top.re = __shfl_sync(0xffffffffu, top.re, 0);
+    if (CPLX) top.im = __shfl_sync(0xffffffffu, top.im, 0);
+    w.re += top.re; w.im += top.im;                       // v_j = 1
+    const Cx f = cmul(f0, w);
+    if (lane == 0) st<CPLX>(a, c * m + j, Cx{top.re - f.re, top.im - f.im});
+#pragma unroll 1
+    for (int i = j + 1 + lane; i < m; i += 32) {
+        const Cx g = cmul(f, ld<CPLX>(a, j * m + i));
+        const Cx o = ld<CPLX>(a, c * m + i);
+        st<CPLX>(a, c * m + i, Cx{o.re - g.re, o.im - g.im});
+    }
+}
+
 // meta per sector: {m, n, row_off, col_off, pos, 0, 0, 0}
 template <bool CPLX>
-__global__ void __launch_bounds__(QR_THREADS) sector_qr_kernel(const double* __restrict__ A, int64_t lda,
+__global__ void __launch_bounds__(QR_MAX_THREADS) sector_qr_kernel(const double* __restrict__ A, int64_t lda,
                                                                const int* __restrict__ meta,
                                                                const int* __restrict__ rowidx,
                                                                const int* __restrict__ colidx, double* __restrict__ Q,
                                                                int64_t ldq, double* __restrict__ R, int64_t ldr) {
     constexpr int E = CPLX ? 2 : 1;
     extern __shared__ double smem[];
-    __shared__ double red[32];
-    __shared__ double bc[4];
+    __shared__ double ssh[2];
     const int* mt = meta + 8 * blockIdx.x;
     const int m = mt[0], n = mt[1], pos = mt[4];
     const int* ri = rowidx + mt[2];
@@ -56,8 +85,10 @@ __global__ void __launch_bounds__(QR_THREADS) sector_qr_kernel(const double* __r
     double* a = smem;                         // m x n column-major
     double* tau = smem + (size_t)m * n * E;   // kmax entries
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int QR_THREADS = blockDim.x, QR_WARPS = blockDim.x >> 5;
 
     // gather (consecutive threads walk along a row of the global matrix: columns are the contiguous direction)
+#pragma unroll 1
     for (int idx = tid; idx < m * n; idx += QR_THREADS) {
         const int i = idx / n, j = idx - i * n;
         const double* src = A + ((int64_t)ri[i] * lda + ci[j]) * E;
@@ -67,65 +98,62 @@ __global__ void __launch_bounds__(QR_THREADS) sector_qr_kernel(const double* __r
     __syncthreads();
 
     // ---- Householder factorisation (zgeqr2) ----
-    for (int j = 0; j < kmax; j++) {
+    // Two CTA barriers per column: every thread derives the reflector scalars itself (identical values) from the
+    // squared norm of the sub-diagonal part, which warp 0 computed right after it updated that column in the previous
+    // step; the diagonal entry is overwritten by beta only after the barrier that ends the scaling phase.
+    if (warp == 0) {
         double ss = 0.0;
-        for (int i = j + 1 + tid; i < m; i += QR_THREADS) {
-            const Cx x = ld<CPLX>(a, j * m + i);
+        for (int i = 1 + lane; i < m; i += 32) {
+            const Cx x = ld<CPLX>(a, i);
             ss += x.re * x.re + x.im * x.im;
         }
-        ss = block_sum(ss, red);
-        if (tid == 0) {
-            const Cx alpha = ld<CPLX>(a, j * m + j);
-            const double xnorm = sqrt(ss);
-            Cx t = {0.0, 0.0}, scal = {0.0, 0.0};
-            double beta = alpha.re;
-            if (!(xnorm == 0.0 && alpha.im == 0.0)) {
-                beta = -copysign(sqrt(alpha.re * alpha.re + alpha.im * alpha.im + ss), alpha.re);
-                t = {(beta - alpha.re) / beta, -alpha.im / beta};
-                // 1 / (alpha - beta)
-                const double dr = alpha.re - beta, di = alpha.im;
-                const double den = dr * dr + di * di;
-                scal = {dr / den, -di / den};
-                st<CPLX>(a, j * m + j, Cx{beta, 0.0});
-            }
-            bc[0] = t.re; bc[1] = t.im; bc[2] = scal.re; bc[3] = scal.im;
-            st<CPLX>(tau, j, t);
+        ss = warp_sum(ss);
+        if (lane == 0) ssh[0] = ss;
+    }
+    __syncthreads();
+    for (int j = 0; j < kmax; j++) {
+        const double ss = ssh[j & 1];
+        const Cx alpha = ld<CPLX>(a, j * m + j);
+        Cx t = {0.0, 0.0}, scal = {0.0, 0.0};
+        double beta = alpha.re;
+        if (!(ss == 0.0 && alpha.im == 0.0)) {
+            beta = -copysign(sqrt(alpha.re * alpha.re + alpha.im * alpha.im + ss), alpha.re);
+            t = {(beta - alpha.re) / beta, -alpha.im / beta};
+            // 1 / (alpha - beta)
+            const double dr = alpha.re - beta, di = alpha.im;
+            const double den = dr * dr + di * di;
+            scal = {dr / den, -di / den};
         }
-        __syncthreads();
-        const Cx t = {bc[0], bc[1]};
-        const Cx scal = {bc[2], bc[3]};
-        if (t.re != 0.0 || t.im != 0.0) {
+        const bool reflect = t.re != 0.0 || t.im != 0.0;
+        if (tid == 0) st<CPLX>(tau, j, t);
+        if (reflect) {
+#pragma unroll 1
             for (int i = j + 1 + tid; i < m; i += QR_THREADS) st<CPLX>(a, j * m + i, cmul(scal, ld<CPLX>(a, j * m + i)));
         }
         __syncthreads();
-        if (t.re != 0.0 || t.im != 0.0) {
+        if (tid == 0 && reflect) st<CPLX>(a, j * m + j, Cx{beta, 0.0});      // not read again before the next barrier
+        if (reflect) {
             // apply H^H = I - conj(tau) v v^H to columns j+1 .. n-1 (one warp per column)
             const Cx tc = {t.re, -t.im};
-            for (int c = j + 1 + warp; c < n; c += QR_WARPS) {
-                Cx w = {0.0, 0.0};
-                for (int i = j + 1 + lane; i < m; i += 32) {
-                    const Cx p = cmulc(ld<CPLX>(a, j * m + i), ld<CPLX>(a, c * m + i));
-                    w.re += p.re; w.im += p.im;
-                }
-                w.re = warp_sum(w.re); w.im = warp_sum(w.im);
-                // the row-j element of column c is read and written by lane 0 only (broadcast by shuffle)
-                Cx top = {0.0, 0.0};
-                if (lane == 0) top = ld<CPLX>(a, c * m + j);
-                top.re = __shfl_sync(0xffffffffu, top.re, 0); top.im = __shfl_sync(0xffffffffu, top.im, 0);
-                w.re += top.re; w.im += top.im;                       // v_j = 1
-                const Cx f = cmul(tc, w);
-                if (lane == 0) st<CPLX>(a, c * m + j, Cx{top.re - f.re, top.im - f.im});
-                for (int i = j + 1 + lane; i < m; i += 32) {
-                    const Cx g = cmul(f, ld<CPLX>(a, j * m + i));
-                    const Cx o = ld<CPLX>(a, c * m + i);
-                    st<CPLX>(a, c * m + i, Cx{o.re - g.re, o.im - g.im});
-                }
+#pragma unroll 1
+            for (int c = j + 1 + warp; c < n; c += QR_WARPS) apply_reflector<CPLX>(a, m, j, c, tc, lane);
+        }
+        if (warp == 0 && j + 1 < kmax) {
+            // squared norm of the next column below its diagonal (warp 0 owns column j+1 in the loop above)
+            __syncwarp();
+            double sn = 0.0;
+            for (int i = j + 2 + lane; i < m; i += 32) {
+                const Cx x = ld<CPLX>(a, (j + 1) * m + i);
+                sn += x.re * x.re + x.im * x.im;
             }
+            sn = warp_sum(sn);
+            if (lane == 0) ssh[(j + 1) & 1] = sn;
         }
         __syncthreads();
     }
 
     // ---- R: upper trapezoid, rows 0..kmax-1, scattered to r[pos + row, ci[col]] ----
+#pragma unroll 1
     for (int idx = tid; idx < kmax * n; idx += QR_THREADS) {
         const int i = idx / n, j = idx - i * n;
         if (j < i) continue;
@@ -137,47 +165,50 @@ __global__ void __launch_bounds__(QR_THREADS) sector_qr_kernel(const double* __r
     __syncthreads();
 
     // ---- Q = H_0 H_1 ... H_{kmax-1} restricted to kmax columns (zung2r, in place) ----
+    // One CTA barrier per column: column j+1 is turned from its reflector into its Q form
+    // (0, ..., 0, 1 - tau, -tau v) by the warp that owns it, right before that warp applies H_j to it; the other
+    // warps read the reflector of column j only.
     for (int j = kmax - 1; j >= 0; j--) {
         const Cx t = ld<CPLX>(tau, j);
-        // apply H_j = I - tau v v^H to the already formed columns j+1 .. kmax-1 (rows j .. m-1)
-        if (t.re != 0.0 || t.im != 0.0) {
-            for (int c = j + 1 + warp; c < kmax; c += QR_WARPS) {
-                Cx w = {0.0, 0.0};
-                for (int i = j + 1 + lane; i < m; i += 32) {
-                    const Cx p = cmulc(ld<CPLX>(a, j * m + i), ld<CPLX>(a, c * m + i));
-                    w.re += p.re; w.im += p.im;
+        const bool reflect = t.re != 0.0 || t.im != 0.0;
+#pragma unroll 1
+        for (int c = j + 1 + warp; c < kmax; c += QR_WARPS) {
+            if (c == j + 1) {
+                const Cx tc1 = ld<CPLX>(tau, c);
+#pragma unroll 1
+                for (int i = lane; i < m; i += 32) {
+                    Cx v;
+                    if (i < c) v = {0.0, 0.0};
+                    else if (i == c) v = {1.0 - tc1.re, -tc1.im};
+                    else {
+                        const Cx p = cmul(tc1, ld<CPLX>(a, c * m + i));
+                        v = {-p.re, -p.im};
+                    }
+                    st<CPLX>(a, c * m + i, v);
                 }
-                w.re = warp_sum(w.re); w.im = warp_sum(w.im);
-                Cx top = {0.0, 0.0};
-                if (lane == 0) top = ld<CPLX>(a, c * m + j);
-                top.re = __shfl_sync(0xffffffffu, top.re, 0); top.im = __shfl_sync(0xffffffffu, top.im, 0);
-                w.re += top.re; w.im += top.im;
-                const Cx f = cmul(t, w);
-                if (lane == 0) st<CPLX>(a, c * m + j, Cx{top.re - f.re, top.im - f.im});
-                for (int i = j + 1 + lane; i < m; i += 32) {
-                    const Cx g = cmul(f, ld<CPLX>(a, j * m + i));
-                    const Cx o = ld<CPLX>(a, c * m + i);
-                    st<CPLX>(a, c * m + i, Cx{o.re - g.re, o.im - g.im});
-                }
+                __syncwarp();
             }
-        }
-        __syncthreads();
-        // column j of Q: (0, ..., 0, 1 - tau, -tau v_{j+1..})
-        for (int i = tid; i < m; i += QR_THREADS) {
-            Cx v;
-            if (i < j) v = {0.0, 0.0};
-            else if (i == j) v = {1.0 - t.re, -t.im};
-            else {
-                const Cx x = ld<CPLX>(a, j * m + i);
-                const Cx p = cmul(t, x);
-                v = {-p.re, -p.im};
-            }
-            st<CPLX>(a, j * m + i, v);
+            if (reflect) apply_reflector<CPLX>(a, m, j, c, t, lane);   // H_j = I - tau v v^H on the formed column c
         }
         __syncthreads();
     }
+    if (kmax > 0) {
+        const Cx t0 = ld<CPLX>(tau, 0);
+#pragma unroll 1
+        for (int i = tid; i < m; i += QR_THREADS) {
+            Cx v;
+            if (i == 0) v = {1.0 - t0.re, -t0.im};
+            else {
+                const Cx p = cmul(t0, ld<CPLX>(a, i));
+                v = {-p.re, -p.im};
+            }
+            st<CPLX>(a, i, v);
+        }
+    }
+    __syncthreads();
 
     // ---- scatter Q to q[ri[row], pos + col] ----
+#pragma unroll 1
     for (int idx = tid; idx < m * kmax; idx += QR_THREADS) {
         const int i = idx / kmax, j = idx - i * kmax;
         const Cx v = ld<CPLX>(a, j * m + i);
@@ -205,16 +236,18 @@ int ptb_block_qr(int dtype, const void* a, int64_t lda, int nsec, const int32_t*
     // shared memory: the gathered block + one tau per reflector (kmax <= sqrt(m n) <= max_block_elems, capped)
     const size_t ntau = max_block_elems < 1024 ? (size_t)max_block_elems : 1024;
     const size_t smem_need = ((size_t)max_block_elems + ntau) * es;
+    // more than 8 columns are only possible with more than 64 elements (the larger extent is at least as long)
+    const int threads = max_block_elems > 64 ? QR_MAX_THREADS : 256;
     if (cplx) {
         static DeviceFlags configured;
         PTB_TRY(ensure_dynamic_smem(configured, sector_qr_kernel<true>, 220 * 1024));
-        sector_qr_kernel<true><<<nsec, QR_THREADS, smem_need, st>>>(
+        sector_qr_kernel<true><<<nsec, threads, smem_need, st>>>(
             static_cast<const double*>(a), lda, meta, rowidx, colidx, static_cast<double*>(q), ldq,
             static_cast<double*>(r), ldr);
     } else {
         static DeviceFlags configured;
         PTB_TRY(ensure_dynamic_smem(configured, sector_qr_kernel<false>, 220 * 1024));
-        sector_qr_kernel<false><<<nsec, QR_THREADS, smem_need, st>>>(
+        sector_qr_kernel<false><<<nsec, threads, smem_need, st>>>(
             static_cast<const double*>(a), lda, meta, rowidx, colidx, static_cast<double*>(q), ldq,
             static_cast<double*>(r), ldr);
     }

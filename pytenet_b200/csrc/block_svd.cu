@@ -112,12 +112,25 @@ __global__ void __launch_bounds__(SVD_MAX_THREADS) sector_svd_kernel(const doubl
                 a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr); cim = warp_sum(cim);
                 a = __shfl_sync(0xffffffffu, a, 0); b = __shfl_sync(0xffffffffu, b, 0);
                 cr = __shfl_sync(0xffffffffu, cr, 0); cim = __shfl_sync(0xffffffffu, cim, 0);
-                const double absc = sqrt(cr * cr + cim * cim);
-                if (absc > eps * sqrt(a * b) && absc > 0.0) {
-                    const Cz ph = {cr / absc, cim / absc};
-                    const double zeta = (b - a) / (2.0 * absc);
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                // |c|^2 > (eps |g_p| |g_q|)^2 instead of two square roots; reciprocal square roots (one special-function
+                // step + Newton, ~1 ulp) instead of sqrt + division on the dependent chain of the rotation parameters
+                const double c2 = cr * cr + cim * cim;
+                bool rot;
+                double inv;
+                if (c2 > 1e-280 && c2 < 1e280 && a < 1e140 && b < 1e140) {
+                    rot = c2 > (eps * eps) * (a * b);
+                    inv = rsqrt(c2);
+                } else {                                             // squares leave the double range: scaled forms
+                    const double absc = hypot(cr, cim);
+                    rot = absc > eps * (sqrt(a) * sqrt(b)) && absc > 0.0;
+                    inv = rot ? 1.0 / absc : 0.0;
+                }
+                if (rot) {
+                    const Cz ph = {cr * inv, cim * inv};
+                    const double zeta = 0.5 * (b - a) * inv;
+                    const double z1 = 1.0 + zeta * zeta;
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + z1 * rsqrt(z1));
+                    const double cs = rsqrt(1.0 + t * t), sn = cs * t;
                     rotate_columns<CPLX>(g, rows, p, q, cs, sn, ph, lane);
                     rotate_columns<CPLX>(v, k, p, q, cs, sn, ph, lane);
                     if (lane == 0) rotated = 1;

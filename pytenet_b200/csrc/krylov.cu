@@ -235,10 +235,11 @@ __global__ void __launch_bounds__(SMALL_THREADS) ortho_small_kernel(double* w, c
 // eigenvector matrix; thread r ends up holding U[r, :].  The breakdown rule of krylov.py:44-50 is applied to
 // the betas first: k_eff = first j with beta[j] < thresh, plus one.
 
-__global__ void __launch_bounds__(TRIDIAG_MAX) expm_coeff_kernel(const double* __restrict__ scal, int numiter,
+__global__ void __launch_bounds__(2 * TRIDIAG_MAX) expm_coeff_kernel(const double* __restrict__ scal, int numiter,
                                                                  double thresh, double dt_re, double dt_im,
                                                                  double* __restrict__ coeff, int* __restrict__ keff_out) {
-    tridiag_expm_coeff(scal, numiter, thresh, dt_re, dt_im, coeff, keff_out);
+    __shared__ __align__(16) double scratch[TAYLOR_SCRATCH_DOUBLES];
+    tridiag_expm_solve(scal, numiter, thresh, dt_re, dt_im, coeff, keff_out, scratch);
 }
 
 // out[n] = sum_{j < *k_eff} coeff[j] V[j, :]  (complex coefficients; OC: out complex, else the real part is
@@ -378,7 +379,7 @@ int ptb_krylov_expm_apply(int v_dtype, int64_t n, int numiter, const void* v, in
     double* coeff = static_cast<double*>(coeff_ws);
     int* keff = reinterpret_cast<int*>(coeff + 2 * TRIDIAG_MAX);
     const double thresh = 100.0 * (double)n * 2.220446049250313e-16;      // krylov.py:44
-    expm_coeff_kernel<<<1, TRIDIAG_MAX, 0, st>>>(scal, numiter, thresh, dt_re, dt_im, coeff, keff);
+    expm_coeff_kernel<<<1, 2 * TRIDIAG_MAX, 0, st>>>(scal, numiter, thresh, dt_re, dt_im, coeff, keff);
     int64_t gb64 = (n + 255) / 256;
     const int gb = (int)(gb64 > 148 * 16 ? 148 * 16 : gb64);
     const double* vd = static_cast<const double*>(v);

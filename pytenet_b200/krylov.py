@@ -211,6 +211,19 @@ def _defer(scal, n, numiter):
     _Deferred.meta.append((n, numiter))
 
 
+def _defer_slot(n, numiter):
+    """Reserve the next slot of the page-locked ring for a kernel that writes its scalars there itself (mapped host
+    memory: the one-kernel local step) -> the slot as a host tensor of 2 numiter doubles.  Examined like the slots
+    filled by `_defer`."""
+    if _Deferred.ring is None:
+        _Deferred.ring = torch.empty((_DEFER_SLOTS, _DEFER_WIDTH), dtype=dev.F64, pin_memory=True)
+    if len(_Deferred.meta) == _DEFER_SLOTS:
+        _flush_deferred()
+    slot = len(_Deferred.meta)
+    _Deferred.meta.append((n, numiter))
+    return _Deferred.ring[slot, :2 * numiter]
+
+
 def _host_afunc(afunc):
     """Adapter for the host-buffer entry: afunc sees / returns NumPy vectors."""
     return lambda t: dev.to_device(np.asarray(afunc(dev.to_host(t))), t.device)
@@ -385,15 +398,20 @@ def _expm_device(afunc, x, dt, numiter):
         # small local problems: Lanczos run, k x k problem and combination in ONE kernel (csrc/lanczos_small.cu)
         xf = x.reshape(-1)
         xf = dev.as_dtype(xf, xf.dtype.is_complex)
-        res = fused(xf, dt, numiter)
-        if res is not None:
-            out, scal = res
-            n = xf.shape[0]
-            if _Deferred.depth > 0:
-                _defer(scal, _threshold_length(afunc, n), numiter)
-            else:
+        n = xf.shape[0]
+        if _Deferred.depth > 0:
+            # inside a sweep driver: the kernel writes alpha / beta / |x| straight into a page-locked slot
+            nmeta = len(_Deferred.meta)
+            res = fused(xf, dt, numiter, scal=_defer_slot(_threshold_length(afunc, n), numiter))
+            if res is not None:
+                return res[0]
+            del _Deferred.meta[nmeta:]           # the problem did not qualify: give the slot back
+        else:
+            res = fused(xf, dt, numiter)
+            if res is not None:
+                out, scal = res
                 _check_scalars(scal.cpu().numpy(), _threshold_length(afunc, n), numiter)
-            return out
+                return out
     n, V, scal = _lanczos_device(afunc, x, numiter, transient=not _CAPTURE_SAFE_ONLY())
     vc = V.dtype.is_complex
     dtc = complex(dt)

@@ -42,6 +42,8 @@ class _StepGraph:
     page-locked slots owned by the graph and are checked after every replay (same warnings / assertions as the
     eager path)."""
 
+    last_error = None        # repr of the exception that made the most recent capture fall back to eager steps
+
     def __init__(self, psi, lblocks, rblocks, one_step):
         import torch
         from . import krylov
@@ -63,8 +65,9 @@ class _StepGraph:
                         raise RuntimeError("state layout changed during the time step")
                     dst.copy_(src)
             same_q = all(np.array_equal(x, y) for x, y in zip(q0, psi.qbonds))
-        except Exception:                    # anything not capturable: keep running eagerly
+        except Exception as exc:             # anything not capturable: keep running eagerly
             same_q = False
+            _StepGraph.last_error = repr(exc)
             try:
                 torch.cuda.synchronize()
             except Exception:

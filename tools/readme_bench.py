@@ -35,7 +35,8 @@ vec_gpu = psi.to_vector()
 # local problems per step: 2 sweeps x (L site steps + (L-1) bond steps), minus the shared turning points
 local = args.steps * (2 * n + 2 * (n - 1))
 res = {"config": "README XXZ L=10 tdvp_singlesite", "steps": args.steps, "k": k, "bond_dims": psi.bond_dims,
-       "gpu_s": gpu_s, "gpu_s_per_step": gpu_s / args.steps, "gpu_us_per_local_problem": 1e6 * gpu_s / local}
+       "gpu_s": gpu_s, "gpu_s_per_step": gpu_s / args.steps, "gpu_us_per_local_problem": 1e6 * gpu_s / local,
+       "graphs": os.environ.get("PYTENET_B200_GRAPHS", "auto"), "graph_capture_error": ptb.tdvp._StepGraph.last_error}
 if args.cpu:
     from oracle import sweeps as osw
     ch = osw.Chain([a.copy() for a in pa], z["psi0/qsite"], [q.copy() for q in pq])
