@@ -252,6 +252,60 @@ def _qr_plan(q0, q1, shape, es, device):
     return plan
 
 
+_dense_svd_tables = {}
+
+
+def single_block_svd(a):
+    """
+    Thin SVD of a matrix whose quantum numbers are all zero -- ONE sector covering the whole matrix -- through the
+    batched Jacobi kernel, without the sector bookkeeping of `block_sparse_svd` (no quantum-number arrays, sparsity
+    assertion or plan lookup: in the launch-latency regime, e.g. METTS at bond dimension 4, that host work costs
+    more than the factorisation).  Returns `(u, s_host, v, s_dev)` exactly as `block_sparse_svd` would (including
+    the cuSOLVER refactorisation of a numerically rank-deficient block), or None when the matrix is too large for
+    the kernel (the caller then takes the general path).
+    """
+    m, n = a.shape
+    if m == 0 or n == 0 or not _BATCHED_SVD or a.dtype not in (dev.F64, dev.C128):
+        return None
+    es = a.element_size()
+    key = (m, n, es, a.device.index)
+    ent = _dense_svd_tables.get(key)
+    if ent is None:
+        k = min(m, n)
+        work = max(m, n) * k + k * k
+        if work > _lib.load().ptb_block_svd_max_block_bytes() // es:
+            ent = False
+        else:
+            meta = np.zeros(8, dtype=np.int32)
+            meta[:5] = (m, n, 0, 0, 0)
+            tables = np.concatenate([meta, np.arange(m, dtype=np.int32), np.arange(n, dtype=np.int32)])
+            ent = (torch.from_numpy(tables).to(a.device), 4 * 8, 4 * (8 + m), int(work))
+        if len(_dense_svd_tables) >= 4096:
+            _dense_svd_tables.clear()
+        _dense_svd_tables[key] = ent
+    if ent is False:
+        return None
+    tab, row_off, col_off, max_work = ent
+    a = dev.dense(a)
+    nb = min(m, n)
+    u = torch.empty((m, nb), dtype=a.dtype, device=a.device)
+    v = torch.empty((nb, n), dtype=a.dtype, device=a.device)
+    s_dev = torch.empty(nb, dtype=dev.F64, device=a.device)
+    tp = tab.data_ptr()
+    st = _lib.load().ptb_block_svd(_lib.PTB_COMPLEX128 if a.dtype.is_complex else _lib.PTB_REAL64, a.data_ptr(), n, 1,
+                                   tp, max_work, tp + row_off, tp + col_off, u.data_ptr(), nb, s_dev.data_ptr(),
+                                   v.data_ptr(), n, dev.stream_ptr(a.device))
+    if st != 0:
+        _lib.check(st, "ptb_block_svd")
+    s_host = s_dev.cpu().numpy()
+    if s_host[0] > 0 and s_host[-1] <= _RANK_EPS * max(m, n) * s_host[0]:
+        # numerically rank deficient: same treatment as block_sparse_svd (LAPACK's noise-level values and completed
+        # basis, so that the retained indices equal the reference's)
+        u, s_dev, v = torch.linalg.svd(a, full_matrices=False, driver=_SVD_DRIVER)
+        s_host = s_dev.cpu().numpy()
+    return u, s_host, v, s_dev
+
+
 _QR_STREAMS = {}
 _QR_MAX_STREAMS = 6
 

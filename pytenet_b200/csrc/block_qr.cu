@@ -38,11 +38,13 @@ __device__ __forceinline__ void st(double* s, int idx, Cx v) {
     else s[idx] = v.re;
 }
 
-// column c of `a` (column-major, m rows) <- (I - f v v^H) column c, with v = (1, a[j+1.., j]) the reflector stored below
-// the diagonal of column j: one warp, rows j .. m-1.  Not inlined and not unrolled: the kernel runs once per launch
-// with a cold instruction cache, the code fetched matters more than the loop overhead.
+// column c of `a` (column-major, m rows) <- (I - f0 v v^H) column c for the reflector v = (1, sc * x), x = the
+// UNSCALED sub-diagonal part of column j as the factorisation left it: one warp, rows j .. m-1.  Keeping x unscaled
+// lets the dot product x^H a_c start before the reflector scalars (a square root and two divisions) are known, and
+// removes the scaling pass with its barrier.  Not inlined, loops not unrolled: the kernel runs once per launch with a
+// cold instruction cache.
 template <bool CPLX>
-__device__ __noinline__ void apply_reflector(double* a, int m, int j, int c, Cx f0, int lane) {
+__device__ __noinline__ void apply_reflector(double* a, int m, int j, int c, Cx sc, Cx f0, int lane) {
     Cx w = {0.0, 0.0};
 #pragma unroll 1
     for (int i = j + 1 + lane; i < m; i += 32) {
@@ -51,6 +53,7 @@ __device__ __noinline__ void apply_reflector(double* a, int m, int j, int c, Cx 
     }
     w.re = warp_sum(w.re);
     if (CPLX) w.im = warp_sum(w.im);
+    w = cmulc(sc, w);                                     // v^H a_c = conj(sc) x^H a_c + a_c[j]
     // the row-j element of column c is read and written by lane 0 only (broadcast by shuffle)
     Cx top = {0.0, 0.0};
     if (lane == 0) top = ld<CPLX>(a, c * m + j);
@@ -59,9 +62,10 @@ __device__ __noinline__ void apply_reflector(double* a, int m, int j, int c, Cx 
     w.re += top.re; w.im += top.im;                       // v_j = 1
     const Cx f = cmul(f0, w);
     if (lane == 0) st<CPLX>(a, c * m + j, Cx{top.re - f.re, top.im - f.im});
+    const Cx fs = cmul(f, sc);
 #pragma unroll 1
     for (int i = j + 1 + lane; i < m; i += 32) {
-        const Cx g = cmul(f, ld<CPLX>(a, j * m + i));
+        const Cx g = cmul(fs, ld<CPLX>(a, j * m + i));
         const Cx o = ld<CPLX>(a, c * m + i);
         st<CPLX>(a, c * m + i, Cx{o.re - g.re, o.im - g.im});
     }
@@ -70,10 +74,10 @@ __device__ __noinline__ void apply_reflector(double* a, int m, int j, int c, Cx 
 // meta per sector: {m, n, row_off, col_off, pos, 0, 0, 0}
 template <bool CPLX>
 __global__ void __launch_bounds__(QR_MAX_THREADS) sector_qr_kernel(const double* __restrict__ A, int64_t lda,
-                                                               const int* __restrict__ meta,
-                                                               const int* __restrict__ rowidx,
-                                                               const int* __restrict__ colidx, double* __restrict__ Q,
-                                                               int64_t ldq, double* __restrict__ R, int64_t ldr) {
+                                                                   const int* __restrict__ meta,
+                                                                   const int* __restrict__ rowidx,
+                                                                   const int* __restrict__ colidx, double* __restrict__ Q,
+                                                                   int64_t ldq, double* __restrict__ R, int64_t ldr) {
     constexpr int E = CPLX ? 2 : 1;
     extern __shared__ double smem[];
     __shared__ double ssh[2];
@@ -83,7 +87,9 @@ __global__ void __launch_bounds__(QR_MAX_THREADS) sector_qr_kernel(const double*
     const int* ci = colidx + mt[3];
     const int kmax = m < n ? m : n;
     double* a = smem;                         // m x n column-major
-    double* tau = smem + (size_t)m * n * E;   // kmax entries
+    double* tau = smem + (size_t)m * n * E;   // kmax reflector factors tau_j
+    double* scl = tau + (size_t)kmax * E;     // kmax scalings: v_j = (1, scl_j x_j)
+    double* dg = scl + (size_t)kmax * E;      // kmax diagonal entries of R (beta_j, real)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int QR_THREADS = blockDim.x, QR_WARPS = blockDim.x >> 5;
 
@@ -98,11 +104,13 @@ __global__ void __launch_bounds__(QR_MAX_THREADS) sector_qr_kernel(const double*
     __syncthreads();
 
     // ---- Householder factorisation (zgeqr2) ----
-    // Two CTA barriers per column: every thread derives the reflector scalars itself (identical values) from the
-    // squared norm of the sub-diagonal part, which warp 0 computed right after it updated that column in the previous
-    // step; the diagonal entry is overwritten by beta only after the barrier that ends the scaling phase.
+    // ONE CTA barrier per column: every warp that owns a trailing column derives the reflector scalars itself
+    // (identical values) from the squared norm of the sub-diagonal part -- computed by warp 0 right after it updated
+    // that column in the previous step -- and applies the reflector to its columns; nothing of column j is
+    // overwritten (the scaling lives in scl_j, the diagonal of R in dg_j), so no warp waits for another inside a step.
     if (warp == 0) {
         double ss = 0.0;
+#pragma unroll 1
         for (int i = 1 + lane; i < m; i += 32) {
             const Cx x = ld<CPLX>(a, i);
             ss += x.re * x.re + x.im * x.im;
@@ -112,42 +120,42 @@ __global__ void __launch_bounds__(QR_MAX_THREADS) sector_qr_kernel(const double*
     }
     __syncthreads();
     for (int j = 0; j < kmax; j++) {
-        const double ss = ssh[j & 1];
-        const Cx alpha = ld<CPLX>(a, j * m + j);
-        Cx t = {0.0, 0.0}, scal = {0.0, 0.0};
-        double beta = alpha.re;
-        if (!(ss == 0.0 && alpha.im == 0.0)) {
-            beta = -copysign(sqrt(alpha.re * alpha.re + alpha.im * alpha.im + ss), alpha.re);
-            t = {(beta - alpha.re) / beta, -alpha.im / beta};
-            // 1 / (alpha - beta)
-            const double dr = alpha.re - beta, di = alpha.im;
-            const double den = dr * dr + di * di;
-            scal = {dr / den, -di / den};
-        }
-        const bool reflect = t.re != 0.0 || t.im != 0.0;
-        if (tid == 0) st<CPLX>(tau, j, t);
-        if (reflect) {
-#pragma unroll 1
-            for (int i = j + 1 + tid; i < m; i += QR_THREADS) st<CPLX>(a, j * m + i, cmul(scal, ld<CPLX>(a, j * m + i)));
-        }
-        __syncthreads();
-        if (tid == 0 && reflect) st<CPLX>(a, j * m + j, Cx{beta, 0.0});      // not read again before the next barrier
-        if (reflect) {
-            // apply H^H = I - conj(tau) v v^H to columns j+1 .. n-1 (one warp per column)
-            const Cx tc = {t.re, -t.im};
-#pragma unroll 1
-            for (int c = j + 1 + warp; c < n; c += QR_WARPS) apply_reflector<CPLX>(a, m, j, c, tc, lane);
-        }
-        if (warp == 0 && j + 1 < kmax) {
-            // squared norm of the next column below its diagonal (warp 0 owns column j+1 in the loop above)
-            __syncwarp();
-            double sn = 0.0;
-            for (int i = j + 2 + lane; i < m; i += 32) {
-                const Cx x = ld<CPLX>(a, (j + 1) * m + i);
-                sn += x.re * x.re + x.im * x.im;
+        if (warp == 0 || j + 1 + warp < n) {
+            const double ss = ssh[j & 1];
+            const Cx alpha = ld<CPLX>(a, j * m + j);
+            Cx t = {0.0, 0.0}, scal = {0.0, 0.0};
+            double beta = alpha.re;
+            if (!(ss == 0.0 && alpha.im == 0.0)) {
+                beta = -copysign(sqrt(alpha.re * alpha.re + alpha.im * alpha.im + ss), alpha.re);
+                t = {(beta - alpha.re) / beta, -alpha.im / beta};
+                // 1 / (alpha - beta)
+                const double dr = alpha.re - beta, di = alpha.im;
+                const double den = dr * dr + di * di;
+                scal = {dr / den, -di / den};
             }
-            sn = warp_sum(sn);
-            if (lane == 0) ssh[(j + 1) & 1] = sn;
+            if (tid == 0) {
+                st<CPLX>(tau, j, t);
+                st<CPLX>(scl, j, scal);
+                dg[j] = beta;
+            }
+            if (t.re != 0.0 || t.im != 0.0) {
+                // apply H^H = I - conj(tau) v v^H to columns j+1 .. n-1 (one warp per column)
+                const Cx tc = {t.re, -t.im};
+#pragma unroll 1
+                for (int c = j + 1 + warp; c < n; c += QR_WARPS) apply_reflector<CPLX>(a, m, j, c, scal, tc, lane);
+            }
+            if (warp == 0 && j + 1 < kmax) {
+                // squared norm of the next column below its diagonal (warp 0 owns column j+1 in the loop above)
+                __syncwarp();
+                double sn = 0.0;
+#pragma unroll 1
+                for (int i = j + 2 + lane; i < m; i += 32) {
+                    const Cx x = ld<CPLX>(a, (j + 1) * m + i);
+                    sn += x.re * x.re + x.im * x.im;
+                }
+                sn = warp_sum(sn);
+                if (lane == 0) ssh[(j + 1) & 1] = sn;
+            }
         }
         __syncthreads();
     }
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(QR_MAX_THREADS) sector_qr_kernel(const double*
     for (int idx = tid; idx < kmax * n; idx += QR_THREADS) {
         const int i = idx / n, j = idx - i * n;
         if (j < i) continue;
-        const Cx v = ld<CPLX>(a, j * m + i);
+        const Cx v = j == i ? Cx{dg[i], 0.0} : ld<CPLX>(a, j * m + i);
         double* dst = R + ((int64_t)(pos + i) * ldr + ci[j]) * E;
         dst[0] = v.re;
         if (CPLX) dst[1] = v.im;
@@ -169,37 +177,39 @@ __global__ void __launch_bounds__(QR_MAX_THREADS) sector_qr_kernel(const double*
     // (0, ..., 0, 1 - tau, -tau v) by the warp that owns it, right before that warp applies H_j to it; the other
     // warps read the reflector of column j only.
     for (int j = kmax - 1; j >= 0; j--) {
-        const Cx t = ld<CPLX>(tau, j);
+        const Cx t = ld<CPLX>(tau, j), sc = ld<CPLX>(scl, j);
         const bool reflect = t.re != 0.0 || t.im != 0.0;
 #pragma unroll 1
         for (int c = j + 1 + warp; c < kmax; c += QR_WARPS) {
             if (c == j + 1) {
                 const Cx tc1 = ld<CPLX>(tau, c);
+                const Cx ts1 = cmul(tc1, ld<CPLX>(scl, c));
 #pragma unroll 1
                 for (int i = lane; i < m; i += 32) {
                     Cx v;
                     if (i < c) v = {0.0, 0.0};
                     else if (i == c) v = {1.0 - tc1.re, -tc1.im};
                     else {
-                        const Cx p = cmul(tc1, ld<CPLX>(a, c * m + i));
+                        const Cx p = cmul(ts1, ld<CPLX>(a, c * m + i));
                         v = {-p.re, -p.im};
                     }
                     st<CPLX>(a, c * m + i, v);
                 }
                 __syncwarp();
             }
-            if (reflect) apply_reflector<CPLX>(a, m, j, c, t, lane);   // H_j = I - tau v v^H on the formed column c
+            if (reflect) apply_reflector<CPLX>(a, m, j, c, sc, t, lane);   // H_j = I - tau v v^H on the formed column c
         }
         __syncthreads();
     }
     if (kmax > 0) {
         const Cx t0 = ld<CPLX>(tau, 0);
+        const Cx ts0 = cmul(t0, ld<CPLX>(scl, 0));
 #pragma unroll 1
         for (int i = tid; i < m; i += QR_THREADS) {
             Cx v;
             if (i == 0) v = {1.0 - t0.re, -t0.im};
             else {
-                const Cx p = cmul(t0, ld<CPLX>(a, i));
+                const Cx p = cmul(ts0, ld<CPLX>(a, i));
                 v = {-p.re, -p.im};
             }
             st<CPLX>(a, i, v);
@@ -234,8 +244,9 @@ int ptb_block_qr(int dtype, const void* a, int64_t lda, int nsec, const int32_t*
     if ((size_t)max_block_elems * es > ptb_block_qr_max_block_bytes()) return PTB_ERR_TOO_LARGE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // shared memory: the gathered block + one tau per reflector (kmax <= sqrt(m n) <= max_block_elems, capped)
-    const size_t ntau = max_block_elems < 1024 ? (size_t)max_block_elems : 1024;
-    const size_t smem_need = ((size_t)max_block_elems + ntau) * es;
+    size_t ntau = 1;                           // kmax = min(m, n) <= sqrt(m n) <= sqrt(max_block_elems)
+    while (ntau * ntau < (size_t)max_block_elems) ntau++;
+    const size_t smem_need = ((size_t)max_block_elems + 3 * ntau) * es;      // block + tau, scl, dg
     // more than 8 columns are only possible with more than 64 elements (the larger extent is at least as long)
     const int threads = max_block_elems > 64 ? QR_MAX_THREADS : 256;
     if (cplx) {

@@ -318,6 +318,8 @@ __global__ void __launch_bounds__(MAX_THREADS) lanczos_small_kernel(const RunPar
             if (CPLX) p.V[g + 1] = vfull[g + 1];
         }
     }
+    // every CTA of the cluster must be running before the first store into a peer's shared memory
+    if (C > 1) cg::this_cluster().sync();
     double* alpha_g = p.scal + 1;
     double* beta_g = alpha_g + k;
     const int nk3 = Dl * cl;                                       // length of the step-3 sum

@@ -12,7 +12,8 @@ import numpy as np
 import torch
 
 from . import _device as dev
-from .block_sparse_util import qnumber_outer_sum, qnumber_flatten, block_sparse_qr, block_sparse_eigh, is_qsparse
+from .block_sparse_util import (qnumber_outer_sum, qnumber_flatten, block_sparse_qr, block_sparse_eigh, is_qsparse,
+                                single_block_svd)
 from .bond_ops import split_block_sparse_matrix_svd, retained_bond_indices
 from .scalars import crandn
 
@@ -382,6 +383,33 @@ def mps_split_tensor_svd(a, qsite0, qsite1, qbonds_outer, svd_distr: str, tol=0)
     d0, d1 = len(qsite0), len(qsite1)
     assert d0 * d1 == a.shape[1], "physical dimension of MPS tensor must be equal to d0 * d1"
     b0, b2 = a.shape[0], a.shape[2]
+    if (isinstance(a, torch.Tensor) and a.is_cuda
+            and not (qsite0.any() or qsite1.any() or np.any(qbonds_outer[0]) or np.any(qbonds_outer[1]))):
+        # all quantum numbers zero: one dense block (block_sparse_util.single_block_svd); same results as the
+        # general path below
+        res = single_block_svd(a.reshape(b0 * d0, d1 * b2))
+        if res is not None:
+            u, sigma, v, sig = res
+            keep = retained_bond_indices(sigma, tol)
+            nb = len(keep)
+            if nb != len(sigma):
+                if nb > 0 and keep[-1] == nb - 1:
+                    u, v, sig = u[:, :nb], v[:nb], sig[:nb]
+                else:
+                    kt = torch.as_tensor(keep, device=u.device)
+                    u, v, sig = u.index_select(1, kt), v.index_select(0, kt), sig.index_select(0, kt)
+            if svd_distr == "left":
+                u = u * sig
+            elif svd_distr == "right":
+                v = v * sig[:, None]
+            elif svd_distr == "sqrt":
+                rt = torch.sqrt(sig)
+                u = u * rt
+                v = v * rt[:, None]
+            else:
+                raise ValueError('`svd_distr` parameter must be "left", "right" or "sqrt".')
+            qbond = np.zeros(nb, dtype=np.result_type(np.asarray(qbonds_outer[0]).dtype, qsite0.dtype))
+            return dev.dense(u.reshape(b0, d0, nb)), dev.dense(v.reshape(nb, d1, b2)), qbond
     q0 = qnumber_flatten([qbonds_outer[0], qsite0])
     q1 = qnumber_flatten([-qsite1, qbonds_outer[1]])
     u, sigma, v, qbond, sig = split_block_sparse_matrix_svd(a.reshape(b0 * d0, d1 * b2), q0, q1, tol,

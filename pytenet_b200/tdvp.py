@@ -43,6 +43,7 @@ class _StepGraph:
     eager path)."""
 
     last_error = None        # repr of the exception that made the most recent capture fall back to eager steps
+    _pending = None          # scalars of the most recent replay, not yet examined
 
     def __init__(self, psi, lblocks, rblocks, one_step):
         import torch
@@ -88,14 +89,24 @@ class _StepGraph:
         self.ok = True
 
     def replay(self):
+        """Enqueue one time step; the scalars of the PREVIOUS replay are examined while the device runs this one
+        (the slots are overwritten by every replay, so they are copied out right after the synchronisation)."""
         import torch
-        from . import krylov
         self.graph.replay()
+        self.finish()
         if self.meta:
+            from . import krylov
             torch.cuda.current_stream().synchronize()
             host = krylov._Deferred.ring.numpy()
-            for i, (n, numiter) in enumerate(self.meta):
-                krylov._check_scalars(host[self.slot0 + i], n, numiter)
+            self._pending = host[self.slot0:self.slot0 + len(self.meta)].copy()
+
+    def finish(self):
+        """Examine the scalars of the last replay (same warnings / assertions as the eager path)."""
+        pending, self._pending = self._pending, None
+        if pending is not None:
+            from . import krylov
+            for row, (n, numiter) in zip(pending, self.meta):
+                krylov._check_scalars(row, n, numiter)
 
 
 @defer_checks
@@ -187,6 +198,8 @@ def tdvp_singlesite(hamiltonian: MPO, psi: MPS, dt, numsteps: int, numiter_lancz
         prev_sig = sig
         one_step()
         step += 1
+    if graph is not None:
+        graph.finish()
 
     return nrm
 
