@@ -405,15 +405,22 @@ int ptb_bond_lanczos(int dtype, const void* c, const void* l, const void* r, int
 /* ---------------------------------------------------------------------------
  * One kernel per local problem (launch-latency regime: README config, METTS, chain edges)
  *   pytenet/tdvp.py:223-238, dmrg.py:181-189 (closures) + krylov.py:12-57 (Lanczos) + krylov.py:110-139 (expm_krylov)
- * A single CTA runs the start normalisation, all `numiter` Lanczos iterations on H_eff = (l, w, r) -- the three
- * contraction steps of chain_ops.py:273-278 as FP64 FMA loops over L2-resident operands --, and, with
+ * ONE launch runs the start normalisation, all `numiter` Lanczos iterations on H_eff = (l, w, r) -- the three
+ * contraction steps of chain_ops.py:273-278 as FP64 FMA loops over operands staged in shared memory --, and, with
  * `apply_expm`, the numiter x numiter tridiagonal problem and out = exp(dt H_eff) x as the combination of the
- * Lanczos vectors (dt = dt_re + i dt_im; the drivers pass -dt).  `w == NULL` is the zero-site problem
+ * Lanczos vectors (dt = dt_re + i dt_im; the drivers pass -dt).  The launch is a thread-block cluster of 1, 2, 4 or
+ * 8 CTAs, each owning a slice of the right bond index of the output; the Lanczos vector and the two scalars of an
+ * iteration are exchanged through distributed shared memory.  `w == NULL` is the zero-site problem
  * (apply_local_bond_contraction, chain_ops.py:282-317: d == 1, chi_l == chi_r).  V (numiter x n elements) receives the
- * Lanczos vectors, scal = [|x|, alpha[0:numiter], beta[0:numiter-1]] as ptb_heff_lanczos; all numiter steps are
- * executed, the breakdown rule of krylov.py:44-50 is applied to the betas inside the k x k solve (and by the caller
- * to `scal`).  ptb_local_step_small_fits: 1 when one matvec is small enough for a single CTA (<= 160 000 complex
- * multiply-adds) and numiter <= 64; otherwise ptb_local_step_small returns PTB_ERR_TOO_LARGE.
+ * Lanczos vectors, scal = [|x|, alpha[0:numiter], beta[0:numiter-1]] as ptb_heff_lanczos -- `scal` is only written
+ * and may point to page-locked host memory (mapped): the drivers let the kernel deposit its scalars in the ring their
+ * deferred checks read.  All numiter steps are executed, the breakdown rule of krylov.py:44-50 is applied to the
+ * betas inside the k x k solve (and by the caller to `scal`).  The k x k solve: Krylov spaces up to 16 by the
+ * shifted, scaled Taylor series of the tridiagonal matrix with squaring (same result as the eigenvector formula of
+ * krylov.py:136 to a few 2^s eps; refused when |Re dt| |T - mean| > 1.5 or more than ten squarings are needed),
+ * otherwise the implicit QL iteration.  ptb_local_step_small_fits: 1 when one matvec is at most 400 000 complex
+ * multiply-adds, the operands fit the shared memory of the cluster and numiter <= 64; otherwise
+ * ptb_local_step_small returns PTB_ERR_TOO_LARGE.  `workspace` is unused (kept for ABI stability; may be NULL).
  * ------------------------------------------------------------------------- */
 int ptb_local_step_small_fits(int64_t Dl, int64_t d, int64_t Dr, int64_t chi_l, int64_t chi_r, int numiter);
 size_t ptb_local_step_small_workspace_bytes(int dtype, int64_t Dl, int64_t d, int64_t Dr, int64_t chi_l, int64_t chi_r);

@@ -148,10 +148,12 @@ static __device__ __noinline__ void tridiag_expm_coeff(const double* scal, int n
 // four matrix elements, the running sum in registers), s squarings.  All arithmetic is backward stable at this
 // norm; the result equals the eigen-decomposition formula to a few 2^s eps (tests: 1e-12).  Returns false --
 // uniformly over the CTA, before any barrier -- when the space is larger than 16, the norm needs more than ten
-// squarings or the scalars are not finite; the caller then runs the QL path.
+// squarings, the real part of dt times the norm exceeds 1.5 (see below) or the scalars are not finite; the caller
+// then runs the QL path.
 constexpr int TAYLOR_MAX_K = 16;
 constexpr int TAYLOR_TERMS = 16;
 constexpr int TAYLOR_MAX_SQUARINGS = 10;
+constexpr double TAYLOR_MAX_REAL_NORM = 1.5;                      // |Re dt| |T - mu|_inf allowed on the Taylor path
 constexpr int TAYLOR_SLOTS = 2;                                   // matrix elements per thread (blockDim.x >= 128)
 constexpr int TAYLOR_SCRATCH_DOUBLES = 3 * TAYLOR_MAX_K * TAYLOR_MAX_K * 2;
 static __constant__ double TAYLOR_INV[TAYLOR_TERMS + 1] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7,
@@ -178,6 +180,11 @@ static __device__ __noinline__ bool tridiag_expm_taylor(const double* scal, int 
         nb = fmax(nb, fabs(alpha[i] - mu) + (i > 0 ? fabs(beta[i - 1]) : 0.0) + (i < n - 1 ? fabs(beta[i]) : 0.0));
     double na = nb * (fabs(dt_re) + fabs(dt_im));                 // >= |dt| |T - mu|_inf
     if (!(na < ldexp(0.5, TAYLOR_MAX_SQUARINGS)) || !(fabs(mu) < 1e300)) return false;   // too large, or NaN
+    // A real part of dt makes exp(dt (T - mu)) non-unitary: its largest eigen-component (<= e^{|Re dt| nb}) can
+    // dominate the matrix while e_0 barely overlaps with it, and the rounding errors of the squarings -- relative to
+    // the MATRIX norm -- would then exceed those of the eigenvector formula, which are relative to the result.
+    // Bounded amplification only: e^{2 * 1.5} = 20.
+    if (!(nb * fabs(dt_re) <= TAYLOR_MAX_REAL_NORM)) return false;
     int s = 0;
     while (na > 0.5) { na *= 0.5; s++; }
     const double sc = ldexp(1.0, -s);
