@@ -277,13 +277,18 @@ __global__ void __launch_bounds__(MAX_THREADS) lanczos_small_kernel(const RunPar
     // spare (the l^T t2 sum is split over them), else up to MAX_OWN elements per thread.  Local index
     // e = sj * Dl + i' with sj = s' * wj + jl (lanes run along i', the contiguous index of l); g = global element
     // index (i', s', j0 + jl).  Only the first lane of a group (`owner`) stores and contributes to the sums.
+    // Lane layout of a split element: a warp holds EPW = 32 / KS consecutive elements, lane = kpart * EPW + element,
+    // so the eight lanes served together by a 128-bit shared-memory load read eight consecutive i' of one row of l
+    // (conflict free) and one t2 entry (broadcast); with kpart as the fast lane index the KS partial sums of an
+    // element sat on the same banks (ncu: 262 k load bank conflicts per launch at the README bulk site).
     const int KS = p.ksplit;
-    const int kpart = tid & (KS - 1);
+    const int EPW = 32 / KS;
+    const int kpart = (tid & 31) / EPW;
     const bool owner = kpart == 0;
     int gidx[MAX_OWN], o3l[MAX_OWN], o3t[MAX_OWN];
 #pragma unroll
     for (int m = 0; m < MAX_OWN; m++) {
-        const int e = KS > 1 ? (m == 0 ? tid / KS : nown) : tid + m * NT;
+        const int e = KS > 1 ? (m == 0 ? (tid >> 5) * EPW + (tid & 31) % EPW : nown) : tid + m * NT;
         gidx[m] = -1; o3l[m] = 0; o3t[m] = 0;
         if (e < nown) {
             const int ip = e % Dl, sj = e / Dl;
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(MAX_THREADS) lanczos_small_kernel(const RunPar
                 y[m] = dot_strided<CPLX>(lsrc + o3l[m] + (size_t)kpart * Dl * E, Dl * KS,
                                          t2 + o3t[m] + (size_t)kpart * d * wj * E, d * wj * KS, len3);
             if (m == 0 && KS > 1) {
-                for (int o = 1; o < KS; o <<= 1) {                  // all lanes of the warp take part
+                for (int o = EPW; o < 32; o <<= 1) {                // all lanes of the warp take part
                     y[0].re += __shfl_xor_sync(0xffffffffu, y[0].re, o);
                     if (CPLX) y[0].im += __shfl_xor_sync(0xffffffffu, y[0].im, o);
                 }
