@@ -989,7 +989,9 @@ def run_ours(args):
                                     "value": world * F / e2e_pageable_s / 1e9,
                                     "note": "same call with ordinary (pageable) NumPy arrays"},
                 "host_numa_binding": numa},
-        "gpu_launches": 3 * steps,
+        # per matvec: step-1 GEMM, the reduction of its split-K tail tiles, the sparse W step, step-3 GEMM
+        # (profiles/r02_launches_bench.md: gemm_ws_kernel, tail_reduce_kernel, wapply_csr_kernel, gemm_ws_kernel)
+        "gpu_launches": 4 * steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "sharded": sharded,
