@@ -63,3 +63,25 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_local_step_plan_rules_on_the_host(cuda_lib):
+    """ptb_local_step_small_fits is host arithmetic (cluster size, shared-memory layout, slots per thread): the
+    shapes of the launch-latency regime qualify, larger ones and bad arguments do not; argument checks of the entry
+    itself reject before any launch."""
+    fits = cuda_lib.ptb_local_step_small_fits
+    for dims in [(4, 4, 4, 3, 3), (1, 2, 2, 1, 4), (4, 2, 8, 5, 5), (8, 2, 16, 5, 5), (16, 2, 28, 5, 5),
+                 (28, 2, 16, 5, 5), (16, 1, 28, 5, 5), (28, 1, 28, 5, 5), (48, 2, 4, 5, 5)]:
+        assert fits(*dims, 5) == 1, dims                       # README config (D <= 28), METTS (D = 4), chain edges
+        assert fits(*dims, 64) == 1 and fits(*dims, 65) == 0   # numiter <= 64 (tridiagonal solve on the device)
+    # more than 400 000 multiply-adds per matvec: the multi-kernel path
+    assert fits(48, 2, 40, 5, 5, 6) == 0 and fits(64, 2, 64, 5, 5, 5) == 0 and fits(2048, 2, 2048, 5, 5, 25) == 0
+    assert fits(0, 2, 4, 3, 3, 5) == 0 and fits(4, 2, 4, 3, 3, 0) == 0 and fits(4, -1, 4, 3, 3, 5) == 0
+    assert cuda_lib.ptb_local_step_small_workspace_bytes(1, 16, 2, 28, 5, 5) >= 16
+    args = [16, 2, 28, 5, 5, 5]
+    # null pointers / unknown dtype / zero-site problem with a physical index: rejected on the host
+    assert cuda_lib.ptb_local_step_small(1, None, None, 0, 16, 16, *args, 16, 16, 0, 0.0, 0.0, 1, None, None, 0, None) == -1
+    assert cuda_lib.ptb_local_step_small(7, 16, 16, 0, 16, 16, *args, 16, 16, 0, 0.0, 0.0, 1, None, None, 0, None) == -2
+    assert cuda_lib.ptb_local_step_small(1, 16, None, 0, 16, 16, *args, 16, 16, 0, 0.0, 0.0, 1, None, None, 0, None) == -1
+    # real state with a complex time step needs a complex output
+    assert cuda_lib.ptb_local_step_small(0, 16, 16, 0, 16, 16, *args, 16, 16, 1, 0.0, 0.5, 0, 16, None, 0, None) == -1
