@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(SVD_MAX_THREADS) sector_svd_kernel(const doubl
                     const Cz ph = {cr * inv, cim * inv};
                     const double zeta = 0.5 * (b - a) * inv;
                     const double z1 = 1.0 + zeta * zeta;
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + z1 * rsqrt(z1));
+                    // (1 + zeta^2 overflows only for column norms ~1e150 apart: the rotation angle is then zero)
+                    const double t = z1 < 1e300 ? copysign(1.0, zeta) / (fabs(zeta) + z1 * rsqrt(z1)) : 0.0;
                     const double cs = rsqrt(1.0 + t * t), sn = cs * t;
                     rotate_columns<CPLX>(g, rows, p, q, cs, sn, ph, lane);
                     rotate_columns<CPLX>(v, k, p, q, cs, sn, ph, lane);
