@@ -401,8 +401,9 @@ def _expm_device(afunc, x, dt, numiter):
         n = xf.shape[0]
         if _Deferred.depth > 0:
             # inside a sweep driver: the kernel writes alpha / beta / |x| straight into a page-locked slot
-            nmeta = len(_Deferred.meta)
-            res = fused(xf, dt, numiter, scal=_defer_slot(_threshold_length(afunc, n), numiter))
+            slot = _defer_slot(_threshold_length(afunc, n), numiter)
+            nmeta = len(_Deferred.meta) - 1      # (after the reservation: a full ring is flushed inside _defer_slot)
+            res = fused(xf, dt, numiter, scal=slot)
             if res is not None:
                 return res[0]
             del _Deferred.meta[nmeta:]           # the problem did not qualify: give the slot back
